@@ -1,0 +1,239 @@
+/* cavgym.h — C-ABI of libcavgym_sm100.so, the B200 batched stepping engine for CAV-Gym.
+ *
+ * The reference (TSL-UOB/CAV-Gym) has no FFI: its boundary is the Python protocol
+ *   CAVEnv(bodies, constants, env_config, np_random)        library/environment.py:59
+ *   CAVEnv.reset() -> joint_obs                              library/environment.py:225-229
+ *   CAVEnv.step(joint_action) -> (obs, reward, done, info)   library/environment.py:119-223
+ * Every entry point below names the reference interface it replaces.  Plain
+ * pointers and sizes only; no torch types.  Device buffers are raw device
+ * pointers (torch.Tensor.data_ptr()); the caller owns every I/O buffer, the
+ * engine owns its tables, body state, agent state, RNG counters and liveness.
+ *
+ * Layout (all per-env arrays are SoA with the environment index fastest):
+ *   state    [M][4][N]  x, y, velocity, orientation          (bodies.py:48-60)
+ *   actions  [M][2][N]  throttle, steering_angle             (bodies.py:104-109)
+ *                       PelicanCrossing body: TrafficLightAction value in [.][0]
+ *   reward   [M][N]     joint reward                          (environment.py:131-146,208-213)
+ *   done     [N] u8, winner [N] i32 (-1 = no 'winner' key)    (environment.py:148-220)
+ *   liveness [M][N] i32 episode_liveness                      (environment.py:144-146)
+ * real = double (dtype 0) or float (dtype 1).
+ *
+ * Errors: every call returns 0 or a negative CAV_E* code and never throws;
+ * cavgym_last_error() gives the message of the calling thread's last failure.
+ * One engine per device; an engine is not thread-safe.  No call synchronises the
+ * host with the device except cavgym_stats, cavgym_error_count and the *_host calls.
+ */
+#ifndef CAVGYM_H
+#define CAVGYM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define CAV_MAX_ROADS 4         /* road_map.roads: major + minor roads (assets.py:115-120) */
+#define CAV_MAX_STATICS 8       /* traffic lights + obstacle (environment.py:94-101) */
+#define CAV_MAX_SPAWN_BOXES 2   /* pedestrians.py:45-68 */
+#define CAV_MAX_SPAWN_ORIENT 4
+#define CAV_MAX_TYPES 8
+#define CAV_SMALL_M 8           /* thread-per-env fused kernel up to this many bodies */
+#define CAV_MAX_BODIES 512      /* block-per-env dense kernel up to this many bodies */
+#define CAV_AGENT_WORDS 5       /* CrossingAgent state (pedestrian.py:14-31); NaN = None */
+#define CAV_DRAWS 3             /* [0,1) draws an agent may consume per step */
+
+enum { CAV_F64 = 0, CAV_F32 = 1 };
+
+enum {                          /* negative return codes */
+  CAV_OK = 0,
+  CAV_EINVAL = -22,             /* bad argument / unsupported scenario */
+  CAV_ENOMEM = -12,
+  CAV_ECUDA = -5,               /* a CUDA runtime call failed */
+  CAV_ESTATE = -1               /* call not valid in the engine's current state */
+};
+
+enum { CAV_BODY_DYNAMIC = 0,    /* DynamicBody and subclasses (bodies.py:78-346) */
+       CAV_BODY_PELICAN = 1 };  /* PelicanCrossing (bodies.py:409-461) */
+
+enum { CAV_FLAG_PEDESTRIAN = 1, /* isinstance(body, Pedestrian) (environment.py:192,199) */
+       CAV_FLAG_SPAWN = 2 };    /* SpawnPedestrian: re-drawn on reset (bodies.py:290-312) */
+
+enum { CAV_AGENT_EXTERNAL = 0,            /* action comes from the `actions` buffer */
+       CAV_AGENT_NOOP = 1,                /* NoopAgent            (template.py:24-37) */
+       CAV_AGENT_RANDOM = 2,              /* RandomAgent          (template.py:40-62) */
+       CAV_AGENT_RANDOM_CONSTRAINED = 3,  /* RandomConstrainedAgent (pedestrian.py:72-75) */
+       CAV_AGENT_PROXIMITY = 4 };         /* ProximityAgent       (pedestrian.py:78-91) */
+
+enum { CAV_COLLISIONS_NONE = 0, CAV_COLLISIONS_EGO = 1, CAV_COLLISIONS_ALL = 2 }; /* config.py:237-240 */
+
+/* Convex quadrilateral, corners in the reference's order rear_left, front_left,
+ * front_right, rear_right (geometry.py:96-107). */
+typedef struct CavQuad { double x[4]; double y[4]; } CavQuad;
+
+/* DynamicBodyConstants (bodies.py:63-75); track is cosmetic and omitted. */
+typedef struct CavBodyType {
+  double length, width, wheelbase;
+  double min_velocity, max_velocity;
+  double min_throttle, max_throttle;
+  double min_steering_angle, max_steering_angle;
+} CavBodyType;
+
+/* SpawnPedestrianState (bodies.py:283-287). */
+typedef struct CavSpawn {
+  int32_t n_boxes, n_orientations;
+  CavQuad boxes[CAV_MAX_SPAWN_BOXES];
+  double orientations[CAV_MAX_SPAWN_ORIENT];
+  double velocity;
+} CavSpawn;
+
+typedef struct CavBody {
+  int32_t kind;              /* CAV_BODY_* */
+  int32_t type_id;           /* row of CavScenario.types (dynamic bodies) */
+  int32_t flags;             /* CAV_FLAG_* */
+  int32_t spawn_id;          /* row of CavScenario.spawns, or -1 */
+  int32_t agent;             /* CAV_AGENT_* */
+  int32_t reserved;
+  double agent_epsilon;      /* RandomAgent / RandomConstrainedAgent epsilon */
+  double agent_threshold;    /* ProximityAgent distance_threshold */
+  double init_state[4];      /* x, y, v, theta; PelicanCrossing: TrafficLightState in [0] */
+  CavQuad static_box;        /* PelicanCrossing.static_bounding_box (bodies.py:415) */
+} CavBody;
+
+/* Everything CAVEnv.__init__ receives, flattened (environment.py:59-92). */
+typedef struct CavScenario {
+  int32_t n_bodies, n_types, n_roads, n_statics, n_spawns;
+  int32_t terminate_collisions;      /* CAV_COLLISIONS_* (config.json "terminate_collisions") */
+  int32_t terminate_ego_zones;       /* bool */
+  int32_t terminate_ego_offroad;     /* bool */
+  int64_t max_timesteps;
+  double reward_win, reward_draw, cost_step;
+  double viewer_width;               /* CAVEnvConstants.viewer_width (environment.py:47-51) */
+  double time_resolution;            /* 1/frequency = 1/60 (environment.py:65-66) */
+  double ego_maintenance_velocity;   /* environment.py:87 */
+  double ego_max_velocity_offset;    /* environment.py:88 */
+  double centre_line[4];             /* major road longitudinal_line(): start x,y, end x,y (config.py:363) */
+  CavQuad roads[CAV_MAX_ROADS];      /* roads[0] = major road */
+  CavQuad statics[CAV_MAX_STATICS];  /* collidable traffic lights, then the obstacle */
+  CavBodyType types[CAV_MAX_TYPES];
+  const CavSpawn* spawns;            /* host pointer, n_spawns rows (copied by cavgym_create) */
+  const CavBody* bodies;             /* host pointer, n_bodies rows (copied by cavgym_create) */
+} CavScenario;
+
+typedef struct CavEngine CavEngine;
+
+/* Indices of cavgym_stats' ten int64 counters (reporting.py:227-269 definitions). */
+enum { CAV_STAT_EPISODES = 0, CAV_STAT_INTERESTING = 1, CAV_STAT_SUM_T = 2, CAV_STAT_SUM_T2 = 3,
+       CAV_STAT_SUM_SCORE = 4, CAV_STAT_SUM_SCORE2 = 5, CAV_STAT_ENV_STEPS = 6, CAV_STAT_BODY_STEPS = 7,
+       CAV_STAT_TANGENT = 8, CAV_STAT_ERRORS = 9, CAV_N_STATS = 10 };
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+
+/* CAVEnv.__init__ x n_envs (environment.py:59-92; Config.setup config.py:272-415).
+ * Copies the tables to `device`, allocates per-env storage and performs the
+ * constructor-time spawn of every SpawnPedestrian (bodies.py:296).  `seed` keys
+ * the Philox streams of the on-device agents and spawners. */
+int cavgym_create(const CavScenario* tables, int64_t n_envs, int dtype, int device, uint64_t seed, CavEngine** out);
+int cavgym_destroy(CavEngine* engine);
+
+/* Env-sharding (experiments.py:121-122 analogue): this engine holds global env ids
+ * [offset, offset + n_envs).  Philox is keyed by the GLOBAL id, so results do not
+ * depend on how envs are split across GPUs.  Call before the first reset. */
+int cavgym_set_shard(CavEngine* engine, int64_t global_env_offset);
+
+/* CAVEnv.reset (environment.py:225-229; Body.reset bodies.py:32-33,111-114;
+ * SpawnPedestrian.reset bodies.py:298-300; Agent.reset pedestrian.py:27-31).
+ * mask  : device u8[N] or NULL (= all); envs with mask!=0 are reset.
+ * init_state: device real[M][4][N] or NULL; when given it REPLACES the spawn draw
+ *         (replay of reference-generated initial states). */
+int cavgym_reset(CavEngine* engine, const uint8_t* mask, const void* init_state, cudaStream_t stream);
+
+/* ---- stepping -------------------------------------------------------------------- */
+
+/* CAVEnv.step (environment.py:119-223) over all N envs, one fused launch.
+ * actions : device real[M][2][N]; may be NULL iff no body has CAV_AGENT_EXTERNAL
+ *           (bodies with an on-device agent ignore their rows).
+ * state_out, reward_out, done_out, winner_out, tangent_flag_out: device, each
+ *           nullable.  state_out may be cavgym_state_ptr() (no extra write).
+ * An env whose episode has ended stays frozen (reward 0, done 1) until it is reset.
+ * Invalid actions (environment.py:120) set the env's error flag instead of aborting
+ * the batch; see cavgym_error_count. */
+int cavgym_step(CavEngine* engine, const void* actions, void* state_out, void* reward_out,
+                uint8_t* done_out, int32_t* winner_out, uint8_t* tangent_flag_out, cudaStream_t stream);
+
+/* Simulation.run's inner loop (simulation.py:70-97) on device: n_steps fused
+ * transitions with the on-device agents; with auto_reset, an env whose episode ends
+ * (done, or max_timesteps reached, simulation.py:69-70) is scored
+ * (reporting.py:227-243) and reset in the same kernel. */
+int cavgym_rollout(CavEngine* engine, int n_steps, int auto_reset, cudaStream_t stream);
+
+/* Replayed joint actions, n_steps transitions in one launch:
+ * actions real[T][M][2][N]; trajectory outputs (each nullable) state real[T][M][4][N],
+ * reward real[T][M][N], done u8[T][N], winner i32[T][N], tangent u8[T][N]. */
+int cavgym_replay(CavEngine* engine, int n_steps, const void* actions, void* state_traj, void* reward_traj,
+                  uint8_t* done_traj, int32_t* winner_traj, uint8_t* tangent_traj, cudaStream_t stream);
+
+/* cavgym_step with HOST buffers (same shapes): copies in, steps and copies out in
+ * env-chunks pipelined over internal streams; returns when the outputs are on the host. */
+int cavgym_step_host(CavEngine* engine, const void* actions, void* state_out, void* reward_out,
+                     uint8_t* done_out, int32_t* winner_out, uint8_t* tangent_flag_out);
+
+/* ---- accounting ------------------------------------------------------------------ */
+
+/* reporting.analyse_episode / analyse_run (reporting.py:227-269) sums over episodes
+ * scored so far; out10 is a HOST int64[CAV_N_STATS].  Synchronises. */
+int cavgym_stats(CavEngine* engine, int64_t* out10);
+int cavgym_error_count(CavEngine* engine, int64_t* out);   /* envs with the invalid-action flag set */
+int cavgym_launch_count(CavEngine* engine, int64_t* out);  /* kernels launched by this engine so far */
+
+/* ---- engine-owned device buffers (zero-copy views for the host shim) --------------- */
+void* cavgym_state_ptr(CavEngine* engine);          /* real[M][4][N] */
+int32_t* cavgym_liveness_ptr(CavEngine* engine);    /* i32[M][N] episode_liveness */
+void* cavgym_agent_state_ptr(CavEngine* engine);    /* real[M][5][N] CrossingAgent state, NaN = None */
+void* cavgym_action_ptr(CavEngine* engine);         /* real[M][2][N] last joint action taken */
+int32_t* cavgym_timestep_ptr(CavEngine* engine);    /* i32[N] timesteps into the current episode */
+uint8_t* cavgym_done_ptr(CavEngine* engine);        /* u8[N] latched done */
+int32_t* cavgym_winner_ptr(CavEngine* engine);      /* i32[N] latched winner */
+uint8_t* cavgym_error_ptr(CavEngine* engine);       /* u8[N] invalid-action flag */
+
+/* ---- knobs ----------------------------------------------------------------------- */
+
+/* Replace the Philox draws by caller-provided [0,1) numbers (replay of the
+ * reference's MT19937 draws): device f64[M][CAV_DRAWS][N] read by every later
+ * step, NULL restores Philox.  Slot 0 = epsilon test (template.py:61-62), slots
+ * 1,2 = Box.sample components / Discrete.sample. */
+int cavgym_set_uniform_override(CavEngine* engine, const double* uniforms);
+
+/* Replace the five spawn draws (box, triangle, u, v, orientation) of every
+ * SpawnPedestrian by caller-provided [0,1) numbers: device f64[M][5][N], NULL restores Philox. */
+int cavgym_set_spawn_override(CavEngine* engine, const double* draws);
+
+/* CAVEnv.current_timestep (environment.py:90,222) is never reset by the reference;
+ * the engine keeps ONE counter of step calls for the whole batch. */
+int cavgym_set_global_timestep(CavEngine* engine, int64_t t);
+
+/* Near-tangent tolerance in pixels (default 1e-7 for f64, 5e-2 for f32). */
+int cavgym_set_tangent_tolerance(CavEngine* engine, double tau);
+
+/* ---- stand-alone kernels (per-function parity and the Body.step plugin hook) --------- */
+
+/* DynamicBody.step (bodies.py:214-275) for n independent bodies of one type:
+ * state real[4][n] in place, actions real[2][n], device pointers. */
+int cavgym_bodies_step(const CavBodyType* type, void* state, const void* actions, int64_t n, double time_resolution,
+                       int dtype, cudaStream_t stream);
+
+/* Shape.intersects / contains / percentage_intersects (geometry.py:74-87) for n quad pairs:
+ * quads_a, quads_b real[8][n] (x0..x3, y0..y3); out real[4][n] = a.intersects(b), b.contains(a),
+ * a.percentage_intersects(b), near-tangent flag. */
+int cavgym_geometry_probe(const void* quads_a, const void* quads_b, void* out, int64_t n, int dtype, cudaStream_t stream);
+
+const char* cavgym_last_error(void);
+const char* cavgym_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAVGYM_H */

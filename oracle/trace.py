@@ -7,6 +7,7 @@ post-step state, joint reward, done, winner, episode_liveness, the [0,1) draws
 each agent consumed, and each CrossingAgent's internal state after
 `process_feedback`.  The arrays are what tests/golden/*.npz hold.
 """
+import copy
 import math
 
 import numpy as np
@@ -119,7 +120,7 @@ def record(config_dict, max_draws=3):
 
     seeding.set_rng_wrapper(wrap)
     try:
-        cfg = mods["config"].make_config(dict(config_dict))
+        cfg = mods["config"].make_config(copy.deepcopy(config_dict))  # make_config pops keys
         _, env, agents, keyboard_agent = cfg.setup()
     finally:
         seeding.set_rng_wrapper(None)

@@ -1,0 +1,70 @@
+"""Shared test utilities: golden fixtures and scenario construction from their metadata."""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+
+from cavgym_b200.scenario import AgentSpec, compile_scenario
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f != "geometry_kat.npz")
+
+
+def load_golden(name):
+    data = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
+    meta = json.loads(bytes(data["meta"]).decode())
+    episodes = []
+    for e in range(int(data["n_episodes"])):
+        prefix = f"ep{e}_"
+        episodes.append({k[len(prefix):]: data[k] for k in data.files if k.startswith(prefix)})
+    return meta, episodes
+
+
+def env_config_from(cfg):
+    return SimpleNamespace(**{k: cfg[k] for k in ("terminate_collisions", "terminate_ego_zones", "terminate_ego_offroad",
+                                                 "max_timesteps", "reward_win", "reward_draw", "cost_step")})
+
+
+def bodies_and_constants(cfg):
+    option = cfg["scenario_config"]["option"]
+    if option == "pedestrians":
+        from cavgym_b200.examples.environments import pedestrians as mod
+        sc = cfg["scenario_config"]
+        bodies = mod.make_bodies(sc["num_pedestrians"], sc["outbound_pavement"], sc["inbound_pavement"],
+                                 np_random=np.random.RandomState(0))
+    elif option == "crossroads":
+        from cavgym_b200.examples.environments import crossroads as mod
+        bodies = mod.make_bodies()
+    elif option == "bus-stop":
+        from cavgym_b200.examples.environments import bus_stop as mod
+        bodies = mod.make_bodies()
+    elif option == "pelican-crossing":
+        from cavgym_b200.examples.environments import pelican_crossing as mod
+        bodies = mod.make_bodies()
+    else:
+        raise KeyError(option)
+    return bodies, mod.env_constants
+
+
+def agent_specs(cfg, bodies, mode):
+    """mode 'external': replayed joint actions.  mode 'device': the on-device agents Config.setup would build."""
+    if mode == "external":
+        return [AgentSpec("external") for _ in bodies]
+    ego = cfg["ego_config"]
+    tester = cfg["tester_config"]
+    specs = [AgentSpec(ego["option"], epsilon=ego.get("epsilon", 0.0))]
+    for _ in bodies[1:]:
+        specs.append(AgentSpec(tester["option"], epsilon=tester.get("epsilon", 0.0), threshold=tester.get("threshold", 0.0)))
+    return specs
+
+
+def compile_from_meta(meta, mode="external"):
+    cfg = meta["config"]
+    bodies, constants = bodies_and_constants(cfg)
+    return compile_scenario(bodies, constants, env_config_from(cfg), agent_specs(cfg, bodies, mode))
+
+
+def soa(per_env):
+    """[N][M][C] -> [M][C][N] contiguous."""
+    return np.ascontiguousarray(np.transpose(np.asarray(per_env), (1, 2, 0)))
