@@ -1,0 +1,207 @@
+// agents.cuh — kinematics, on-device agents and the counter-based RNG.
+//
+//  body_step              DynamicBody.step                    library/bodies.py:214-275
+//  make_steering_action   inverse bicycle arc                 examples/agents/dynamic_body.py:33-49
+//  choose_crossing_action CrossingAgent state machine         examples/agents/pedestrian.py:50-69
+//  crossing_feedback      CrossingAgent.process_feedback      examples/agents/pedestrian.py:36-48
+//  spawn_body             SpawnPedestrian.spawn               library/bodies.py:302-312
+//  philox4x32_10          replaces the shared MT19937 RandomState (config.py:275)
+#pragma once
+#include "geometry.cuh"
+
+namespace cav {
+
+__device__ __forceinline__ void sincos_(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __forceinline__ void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ double tan_(double a) { return tan(a); }
+__device__ __forceinline__ float tan_(float a) { return tanf(a); }
+__device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double atan_(double a) { return atan(a); }
+__device__ __forceinline__ float atan_(float a) { return atanf(a); }
+__device__ __forceinline__ bool isnan_(double a) { return isnan(a); }
+__device__ __forceinline__ bool isnan_(float a) { return isnan(a); }
+template <typename R> __device__ __forceinline__ R nan_() { return R(NAN); }
+
+// ---------------------------------------------------------------- kinematics
+// st = x, y, v, theta in/out.  On return c, s = cos/sin of the NEW orientation (what the
+// bounding box needs); `snapped` is the steering angle after the 1e-13 snap (bodies.py:217-218).
+template <typename R>
+__device__ __forceinline__ void body_step(const DevType<R>& k, R st[4], R throttle, R steer, R dt, R& c, R& s, R& snapped) {
+  if (rabs(steer) < R(0.0000000000001)) steer = R(0);
+  snapped = steer;
+  const R x = st[0], y = st[1], v = st[2], th = st[3];
+  const R v1 = rmax(k.vmin, rmin(k.vmax, v + (throttle * dt)));
+  const R d = v * dt;
+  if (th == R(0)) { c = R(1); s = th; }  // cos(+-0) = 1, sin(+-0) = +-0
+  else sincos_(th, &s, &c);
+  st[2] = v1;
+  if (steer == R(0)) {
+    st[0] = x + d * c;
+    st[1] = y + d * s;
+  } else {
+    const R wbo = k.wheelbase / R(2);
+    const R rx = x - wbo * c, ry = y - wbo * s;
+    const R kk = k.wheelbase / tan_(steer);
+    const R cx = rx - kk * s, cy = ry + kk * c;
+    const R dx = x - cx, dy = y - cy;
+    const R q = d / rsqrt_(dx * dx + dy * dy);
+    const R theta = steer < R(0) ? -q : q;
+    R ct, sn;
+    sincos_(theta, &sn, &ct);
+    st[0] = cx + dx * ct - dy * sn;
+    st[1] = cy + dx * sn + dy * ct;
+    const R ot = th + theta;
+    R so, co;
+    sincos_(ot, &so, &co);
+    const R th1 = atan2_(so, co);
+    st[3] = th1;
+    if (th1 == R(0)) { c = R(1); s = th1; }
+    else sincos_(th1, &s, &c);
+  }
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 53-bit uniform in [0,1) from two words (numpy legacy random_sample construction).
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+  return ((a >> 5) * 67108864.0 + (b >> 6)) / 9007199254740992.0;
+}
+
+enum { KIND_AGENT0 = 0, KIND_AGENT1 = 1, KIND_SPAWN0 = 2, KIND_SPAWN1 = 3, KIND_SPAWN2 = 4 };
+
+// Stream: key = seed; counter = (env_lo, env_hi | kind<<8 | body<<16, episode, timestep).
+__device__ __forceinline__ void draw_block(uint64_t seed, uint64_t global_env, int body, int kind, uint32_t episode, uint32_t t,
+                                           double u[2]) {
+  uint32_t w[4];
+  philox4x32_10((uint32_t)global_env, (uint32_t)((global_env >> 32) & 0xFFu) | ((uint32_t)kind << 8) | ((uint32_t)body << 16),
+                episode, t, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+  u[0] = u53(w[0], w[1]);
+  u[1] = u53(w[2], w[3]);
+}
+
+// ---------------------------------------------------------------- spawn
+template <typename R>
+__device__ __forceinline__ R triangle_area(R rx, R ry, R flx, R fly, R frx, R fry) {  // geometry.py:352-354
+  return rabs((rx * (fly - fry) + flx * (fry - ry) + frx * (ry - fly)) / R(2));
+}
+
+// numpy legacy choice(p=...) = searchsorted(cumsum(p)/last, u, 'right'); the area arithmetic is done in
+// double in both modes so fp32 and fp64 engines pick the same box/triangle for the same draws.
+template <typename R>
+__device__ __noinline__ void spawn_body(const DevSpawn<R>& sp, const double u[5], R st[4]) {
+  double areas[CAV_MAX_SPAWN_BOXES], larea[CAV_MAX_SPAWN_BOXES], total = 0.0;
+  for (int i = 0; i < sp.n_boxes; ++i) {
+    const Quad<R>& q = sp.boxes[i];
+    larea[i] = triangle_area<double>(q.x[1], q.y[1], q.x[2], q.y[2], q.x[0], q.y[0]);
+    const double r = triangle_area<double>(q.x[3], q.y[3], q.x[0], q.y[0], q.x[2], q.y[2]);
+    areas[i] = 0.0 + larea[i] + r;
+    total += areas[i];
+  }
+  double cdf[CAV_MAX_SPAWN_BOXES], acc = 0.0;
+  for (int i = 0; i < sp.n_boxes; ++i) { acc += areas[i] / total; cdf[i] = acc; }
+  int box = 0;
+  for (int i = 0; i < sp.n_boxes; ++i) box += (cdf[i] / cdf[sp.n_boxes - 1] <= u[0]);
+  if (box >= sp.n_boxes) box = sp.n_boxes - 1;
+  const Quad<R>& q = sp.boxes[box];
+  const double la = larea[box];
+  const double sa = la + triangle_area<double>(q.x[3], q.y[3], q.x[0], q.y[0], q.x[2], q.y[2]);
+  const double f = la / sa, c0 = f, c1 = f + (1 - f);
+  int tri = ((c0 / c1) <= u[1]) + ((c1 / c1) <= u[1]);
+  if (tri > 1) tri = 1;
+  R rx, ry, flx, fly, frx, fry;
+  if (tri == 0) { rx = q.x[1]; ry = q.y[1]; flx = q.x[2]; fly = q.y[2]; frx = q.x[0]; fry = q.y[0]; }
+  else          { rx = q.x[3]; ry = q.y[3]; flx = q.x[0]; fly = q.y[0]; frx = q.x[2]; fry = q.y[2]; }
+  double a = u[2], b = u[3];
+  if (a + b > 1) { a = 1 - a; b = 1 - b; }
+  st[0] = R((double(rx) + (double(flx) - double(rx)) * a) + (double(frx) - double(rx)) * b);
+  st[1] = R((double(ry) + (double(fly) - double(ry)) * a) + (double(fry) - double(ry)) * b);
+  st[2] = sp.velocity;
+  int oi = (int)floor(u[4] * sp.n_orient);
+  if (oi >= sp.n_orient) oi = sp.n_orient - 1;
+  st[3] = sp.orient[oi];
+}
+
+// ---------------------------------------------------------------- crossing agents
+template <typename R>
+__device__ __noinline__ R steering_towards(const DevType<R>& k, R v, R theta, R dt, R target) {
+  R so, co;
+  sincos_(target - theta, &so, &co);
+  const R tta = atan2_(so, co);
+  const R csa = tta < R(0) ? k.smin : k.smax;
+  const R wb = k.wheelbase;
+  const R tn = tan_(csa);
+  const R mta = (csa < R(0) ? R(-2) : R(2)) * dt * v / rsqrt_((wb * wb) * (R(1) + R(4) / (tn * tn)));
+  const R ta = (tta / mta > R(1)) ? mta : tta;
+  const R steer = atan_(R(2) * wb * rsqrt_((ta * ta) / (R(4) * (v * v) * (dt * dt) - (wb * wb) * (ta * ta))));
+  return ta < R(0) ? -steer : steer;
+}
+
+template <typename R>
+__device__ __forceinline__ R make_steering_action(const DevType<R>& k, const R st[4], R dt, R target) {
+  R steer = R(0);
+  if (!(st[2] == R(0) || isnan_(target))) steer = steering_towards(k, st[2], st[3], dt, target);
+  return rmin(k.smax, rmax(k.smin, steer));
+}
+
+template <typename R>
+__device__ __forceinline__ R point_distance(R sx, R sy, R ox, R oy) {  // Point.distance geometry.py:18-19
+  const R dy = oy - sy, dx = ox - sx;
+  return rsqrt_((dy * dy) + (dx * dx));
+}
+
+// ag = initial_distance, waypoint x, waypoint y, target_orientation, prior_orientation (NaN = None).
+template <typename R>
+__device__ __noinline__ void start_crossing(const R cl[4], const R st[4], R ag[CAV_AGENT_WORDS]) {
+  const R dx = cl[2] - cl[0], dy = cl[3] - cl[1];
+  const R denominator = (dx * dx) + (dy * dy);
+  const R a = (dy * (st[1] - cl[1]) + dx * (st[0] - cl[0])) / denominator;  // Line.closest_point_from geometry.py:412-416
+  const R cx = cl[0] + a * dx, cy = cl[1] + a * dy;
+  const R rel = atan2_(cy - st[1], cx - st[0]);
+  if (isnan_(ag[0])) ag[0] = point_distance(st[0], st[1], cx, cy);
+  R sr, cr;
+  sincos_(rel, &sr, &cr);
+  ag[1] = cx + ag[0] * cr;
+  ag[2] = cy + ag[0] * sr;
+  ag[3] = atan2_(ag[2] - st[1], ag[1] - st[0]);
+  ag[4] = st[3];
+}
+
+template <typename R>
+__device__ __forceinline__ R choose_crossing_action(const DevScenario<R>& sc, const DevType<R>& k, const R st[4],
+                                                    R ag[CAV_AGENT_WORDS], bool condition, bool& dirty) {
+  if (isnan_(ag[1]) && isnan_(ag[3]) && condition) {
+    start_crossing(sc.cl, st, ag);
+    dirty = true;
+  }
+  return make_steering_action(k, st, sc.dt, ag[3]);
+}
+
+template <typename R>
+__device__ __forceinline__ void crossing_feedback(const DevScenario<R>& sc, const R st[4], R ag[CAV_AGENT_WORDS], bool& dirty) {
+  if (!isnan_(ag[1])) {
+    if (point_distance(st[0], st[1], ag[1], ag[2]) < R(1)) {
+      ag[1] = nan_<R>(); ag[2] = nan_<R>(); ag[3] = ag[4]; ag[4] = nan_<R>();
+      dirty = true;
+    }
+  }
+  if (!isnan_(ag[3])) {
+    R sd, cd;
+    sincos_(ag[3] - st[3], &sd, &cd);
+    if (rabs(atan2_(sd, cd)) < sc.target_err) { ag[3] = nan_<R>(); dirty = true; }
+  }
+}
+
+}  // namespace cav

@@ -1,0 +1,70 @@
+"""Build libcavgym_sm100.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m cavgym_b200.csrc.build [--force] [--jobs N]
+
+One translation unit per body count (small_mK.cu) so the kernels compile in parallel.
+-fmad=false keeps the fp64 arithmetic in the reference's operation order (no FMA contraction).
+"""
+import argparse
+import concurrent.futures
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+LIB = os.path.join(PKG, "libcavgym_sm100.so")
+OBJ_DIR = os.path.join(HERE, "build")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+         "-Xcompiler", "-fPIC,-O2", "--threads", "1"]
+
+
+def sources():
+    return sorted(f for f in os.listdir(HERE) if f.endswith(".cu"))
+
+
+def headers_mtime():
+    paths = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".cuh")]
+    paths.append(os.path.join(PKG, "..", "include", "cavgym.h"))
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def compile_one(src, force, verbose):
+    obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+    src_path = os.path.join(HERE, src)
+    if not force and os.path.isfile(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src_path), headers_mtime()):
+        return obj, ""
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src_path, "-o", obj]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{proc.stdout}\n{proc.stderr}")
+    return obj, proc.stderr
+
+
+def build(force=False, jobs=None, verbose=False):
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    srcs = sources()
+    jobs = jobs or min(len(srcs), os.cpu_count() or 4)
+    logs = []
+    with concurrent.futures.ThreadPoolExecutor(max_workers=jobs) as pool:
+        results = list(pool.map(lambda s: compile_one(s, force, verbose), srcs))
+    objs = [obj for obj, _ in results]
+    logs = [log for _, log in results if log]
+    if force or not os.path.isfile(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(o) for o in objs):
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError(f"link failed:\n{proc.stdout}\n{proc.stderr}")
+    if verbose:
+        print("\n".join(logs))
+    return LIB
+
+
+if __name__ == "__main__":
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--force", action="store_true")
+    parser.add_argument("--jobs", type=int, default=None)
+    parser.add_argument("--verbose", action="store_true")
+    args = parser.parse_args()
+    print(build(args.force, args.jobs, args.verbose))

@@ -1,0 +1,570 @@
+// engine.cu — the C-ABI of libcavgym_sm100.so (include/cavgym.h): engine lifetime, table
+// conversion, kernel dispatch, the pipelined host-buffer step, statistics and the
+// stand-alone per-function kernels.  No torch types; callers pass raw device pointers.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels_small.cuh"
+
+namespace cav {
+
+#define CAV_FOR_EACH_M(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#define CAV_DECLARE(K)                                   \
+  extern const SmallLaunchers<double> kSmallF64M##K;     \
+  extern const SmallLaunchers<float> kSmallF32M##K;
+CAV_FOR_EACH_M(CAV_DECLARE)
+#undef CAV_DECLARE
+
+template <> const SmallLaunchers<double>* small_launchers<double>(int m) {
+  switch (m) {
+#define CAV_CASE(K) case K: return &kSmallF64M##K;
+    CAV_FOR_EACH_M(CAV_CASE)
+#undef CAV_CASE
+    default: return nullptr;
+  }
+}
+template <> const SmallLaunchers<float>* small_launchers<float>(int m) {
+  switch (m) {
+#define CAV_CASE(K) case K: return &kSmallF32M##K;
+    CAV_FOR_EACH_M(CAV_CASE)
+#undef CAV_CASE
+    default: return nullptr;
+  }
+}
+
+static thread_local std::string g_error;
+
+static int fail(int code, const std::string& message) {
+  g_error = message;
+  return code;
+}
+
+#define CUDA_TRY(call)                                                                             \
+  do {                                                                                             \
+    cudaError_t err_ = (call);                                                                     \
+    if (err_ != cudaSuccess)                                                                       \
+      return fail(CAV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(err_));                \
+  } while (0)
+
+// ---------------------------------------------------------------- table conversion
+template <typename R>
+static Quad<R> to_quad(const CavQuad& q) {
+  // Normalise to clockwise order; the predicates do not depend on which corner comes first.
+  double twice_area = 0.0;
+  for (int i = 0; i < 4; ++i) {
+    const int j = (i + 1) & 3;
+    twice_area += q.x[i] * q.y[j] - q.x[j] * q.y[i];
+  }
+  Quad<R> out;
+  for (int i = 0; i < 4; ++i) {
+    const int src = twice_area > 0 ? 3 - i : i;
+    out.x[i] = (R)q.x[src];
+    out.y[i] = (R)q.y[src];
+  }
+  return out;
+}
+
+template <typename R>
+static Aabb<R> host_aabb(const Quad<R>& q) {
+  Aabb<R> b{q.x[0], q.x[0], q.y[0], q.y[0]};
+  for (int i = 1; i < 4; ++i) {
+    b.x0 = std::fmin(b.x0, q.x[i]); b.x1 = std::fmax(b.x1, q.x[i]);
+    b.y0 = std::fmin(b.y0, q.y[i]); b.y1 = std::fmax(b.y1, q.y[i]);
+  }
+  return b;
+}
+
+template <typename R>
+static DevType<R> to_type(const CavBodyType& t) {
+  return {(R)t.length, (R)t.width, (R)t.wheelbase, (R)t.min_velocity, (R)t.max_velocity, (R)t.min_throttle,
+          (R)t.max_throttle, (R)t.min_steering_angle, (R)t.max_steering_angle};
+}
+
+template <typename R>
+static void convert(const CavScenario& in, double tau, DevScenario<R>& out) {
+  std::memset(&out, 0, sizeof(out));
+  out.n_bodies = in.n_bodies; out.n_types = in.n_types; out.n_roads = in.n_roads; out.n_statics = in.n_statics;
+  out.n_spawns = in.n_spawns;
+  out.collisions = in.terminate_collisions; out.zones = in.terminate_ego_zones; out.offroad = in.terminate_ego_offroad;
+  out.max_timesteps = in.max_timesteps;
+  out.reward_win = (R)in.reward_win; out.reward_draw = (R)in.reward_draw; out.cost_step = (R)in.cost_step;
+  out.W = (R)in.viewer_width; out.dt = (R)in.time_resolution;
+  out.v_maint = (R)in.ego_maintenance_velocity; out.v_off = (R)in.ego_max_velocity_offset;
+  out.tau = (R)tau;
+  out.target_err = sizeof(R) == 8 ? (R)0.000000000000001 : (R)1e-6;  // dynamic_body.py:8; one float ulp at pi/2 is 1.2e-7
+  for (int i = 0; i < 4; ++i) out.cl[i] = (R)in.centre_line[i];
+  for (int i = 0; i < in.n_roads; ++i) { out.roads[i] = to_quad<R>(in.roads[i]); out.road_bb[i] = host_aabb(out.roads[i]); }
+  for (int i = 0; i < in.n_statics; ++i) { out.statics[i] = to_quad<R>(in.statics[i]); out.static_bb[i] = host_aabb(out.statics[i]); }
+  for (int b = 0; b < in.n_bodies && b < CAV_SMALL_M; ++b) {
+    const CavBody& src = in.bodies[b];
+    DevBody<R>& dst = out.bodies[b];
+    dst.kind = src.kind; dst.type_id = src.type_id; dst.flags = src.flags; dst.agent = src.agent; dst.spawn_id = src.spawn_id;
+    dst.epsilon = src.agent_epsilon; dst.threshold = (R)src.agent_threshold;
+    for (int c = 0; c < 4; ++c) dst.init[c] = (R)src.init_state[c];
+    if (src.kind == CAV_BODY_DYNAMIC) dst.k = to_type<R>(in.types[src.type_id]);
+    dst.sbox = to_quad<R>(src.static_box);
+  }
+}
+
+template <typename R>
+static DevSpawn<R> to_spawn(const CavSpawn& in) {
+  DevSpawn<R> out;
+  std::memset(&out, 0, sizeof(out));
+  out.n_boxes = in.n_boxes; out.n_orient = in.n_orientations;
+  for (int i = 0; i < in.n_boxes; ++i)
+    for (int c = 0; c < 4; ++c) { out.boxes[i].x[c] = (R)in.boxes[i].x[c]; out.boxes[i].y[c] = (R)in.boxes[i].y[c]; }
+  for (int i = 0; i < in.n_orientations; ++i) out.orient[i] = (R)in.orientations[i];
+  out.velocity = (R)in.velocity;
+  return out;
+}
+
+// ---------------------------------------------------------------- small kernels living in this TU
+__global__ void live_steps_kernel(const int32_t* t_ep, const uint8_t* done, const uint8_t* err, int64_t n,
+                                  unsigned long long* out /* [2]: live steps, errors */) {
+  unsigned long long steps = 0, errors = 0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    if (!done[e]) steps += (unsigned long long)t_ep[e];
+    errors += err[e];
+  }
+  steps = warp_sum(steps);
+  errors = warp_sum(errors);
+  if ((threadIdx.x & 31) == 0) {
+    if (steps) atomicAdd(&out[0], steps);
+    if (errors) atomicAdd(&out[1], errors);
+  }
+}
+
+// DynamicBody.step alone (bodies.py:214-275): SoA state[4][n] in place, actions[2][n].
+template <typename R>
+__global__ void bodies_step_kernel(const __grid_constant__ DevType<R> k, R* state, const R* actions, int64_t n, R dt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  R st[4] = {state[i], state[n + i], state[2 * n + i], state[3 * n + i]};
+  R c, s, snapped;
+  body_step(k, st, actions[i], actions[n + i], dt, c, s, snapped);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) state[j * n + i] = st[j];
+}
+
+// Shape.intersects / contains / percentage_intersects on n quad pairs (geometry.py:74-87).
+template <typename R>
+__global__ void geometry_probe_kernel(const R* qa, const R* qb, R* out, int64_t n, R tau) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Quad<R> A, B;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    A.x[c] = qa[c * n + i]; A.y[c] = qa[(4 + c) * n + i];
+    B.x[c] = qb[c * n + i]; B.y[c] = qb[(4 + c) * n + i];
+  }
+  auto clockwise = [](Quad<R>& q) {  // the device predicates assume clockwise rings
+    R twice_area = R(0);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) twice_area += q.x[c] * q.y[(c + 1) & 3] - q.x[(c + 1) & 3] * q.y[c];
+    if (twice_area > R(0)) {
+      R t = q.x[0]; q.x[0] = q.x[3]; q.x[3] = t; t = q.x[1]; q.x[1] = q.x[2]; q.x[2] = t;
+      t = q.y[0]; q.y[0] = q.y[3]; q.y[3] = t; t = q.y[1]; q.y[1] = q.y[2]; q.y[2] = t;
+    }
+  };
+  clockwise(A);
+  clockwise(B);
+  bool tangent = false;
+  const bool hit = intersects(A, aabb_of(A), B, aabb_of(B), tau, tangent);
+  bool inside = false;
+  R share = R(0);
+  if (hit) inside = contains(B, A, tau, tangent);
+  if (!(aabb_gap(aabb_of(A), aabb_of(B)) > tau)) share = percentage_intersects(A, B, tau, tangent);
+  out[i] = hit ? R(1) : R(0);
+  out[n + i] = inside ? R(1) : R(0);
+  out[2 * n + i] = share;
+  out[3 * n + i] = tangent ? R(1) : R(0);
+}
+
+}  // namespace cav
+
+using namespace cav;
+
+// ---------------------------------------------------------------- engine object
+struct CavEngine {
+  int dtype = CAV_F64, device = 0, m = 0;
+  int64_t n = 0, t_global = 0, launches = 0;
+  uint64_t seed = 0;
+  bool has_external = false, has_device_agents = false;
+  double tau = 1e-7;
+  CavScenario host{};
+  std::vector<CavBody> bodies;
+  std::vector<CavSpawn> spawns;
+  DevScenario<double> sc64;
+  DevScenario<float> sc32;
+  EnvBuffers<double> buf64;
+  EnvBuffers<float> buf32;
+  std::vector<void*> allocations;
+  // host-buffer pipeline (cavgym_step_host)
+  static constexpr int kPipe = 3;
+  cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr};
+  void *d_actions = nullptr, *d_reward = nullptr;
+  uint8_t *d_done = nullptr, *d_tangent = nullptr;
+  int32_t* d_winner = nullptr;
+  unsigned long long* d_scratch = nullptr;
+
+  size_t real_size() const { return dtype == CAV_F64 ? 8 : 4; }
+};
+
+template <typename T>
+static int dev_alloc(CavEngine* eng, T** ptr, size_t count, bool zero = true) {
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, count * sizeof(T) > 0 ? count * sizeof(T) : sizeof(T)));
+  eng->allocations.push_back(p);
+  if (zero) CUDA_TRY(cudaMemset(p, 0, count * sizeof(T)));
+  *ptr = (T*)p;
+  return CAV_OK;
+}
+
+template <typename R>
+static int setup_buffers(CavEngine* eng, EnvBuffers<R>& buf) {
+  const int64_t n = eng->n, m = eng->m;
+  std::memset(&buf, 0, sizeof(buf));
+  buf.n = n; buf.lo = 0; buf.hi = n; buf.shard = 0; buf.seed = eng->seed;
+  int rc;
+  if ((rc = dev_alloc(eng, &buf.state, (size_t)m * 4 * n))) return rc;
+  if ((rc = dev_alloc(eng, &buf.action, (size_t)m * 2 * n))) return rc;
+  if ((rc = dev_alloc(eng, &buf.agent, (size_t)m * CAV_AGENT_WORDS * n))) return rc;
+  if ((rc = dev_alloc(eng, &buf.liveness, (size_t)m * n))) return rc;
+  if ((rc = dev_alloc(eng, &buf.t_ep, (size_t)n))) return rc;
+  if ((rc = dev_alloc(eng, &buf.episode, (size_t)n))) return rc;
+  if ((rc = dev_alloc(eng, &buf.winner, (size_t)n))) return rc;
+  if ((rc = dev_alloc(eng, &buf.done, (size_t)n))) return rc;
+  if ((rc = dev_alloc(eng, &buf.err, (size_t)n))) return rc;
+  if ((rc = dev_alloc(eng, &buf.stats, (size_t)CAV_N_STATS))) return rc;
+  std::vector<DevSpawn<R>> spawns;
+  for (const CavSpawn& s : eng->spawns) spawns.push_back(to_spawn<R>(s));
+  DevSpawn<R>* d_spawns = nullptr;
+  if ((rc = dev_alloc(eng, &d_spawns, spawns.size() ? spawns.size() : 1))) return rc;
+  if (!spawns.empty()) CUDA_TRY(cudaMemcpy(d_spawns, spawns.data(), spawns.size() * sizeof(DevSpawn<R>), cudaMemcpyHostToDevice));
+  buf.spawns = d_spawns;
+  return CAV_OK;
+}
+
+static void rebuild_tables(CavEngine* eng) {
+  convert<double>(eng->host, eng->tau, eng->sc64);
+  convert<float>(eng->host, eng->tau, eng->sc32);
+}
+
+static int check_engine(CavEngine* eng) {
+  if (!eng) return fail(CAV_EINVAL, "engine is NULL");
+  cudaError_t err = cudaSetDevice(eng->device);
+  if (err != cudaSuccess) return fail(CAV_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(err));
+  return CAV_OK;
+}
+
+static int launch_check(CavEngine* eng, const char* what, int n_launches = 1) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(CAV_ECUDA, std::string(what) + ": " + cudaGetErrorString(err));
+  eng->launches += n_launches;
+  return CAV_OK;
+}
+
+static int do_reset(CavEngine* eng, const uint8_t* mask, const void* init, int first_time, cudaStream_t stream) {
+  if (eng->dtype == CAV_F64) small_launchers<double>(eng->m)->reset(eng->sc64, eng->buf64, mask, (const double*)init, first_time, stream);
+  else small_launchers<float>(eng->m)->reset(eng->sc32, eng->buf32, mask, (const float*)init, first_time, stream);
+  return launch_check(eng, "reset kernel");
+}
+
+extern "C" {
+
+const char* cavgym_last_error(void) { return g_error.c_str(); }
+const char* cavgym_version(void) { return "cavgym_b200 0.1.0 (sm_100a)"; }
+
+int cavgym_create(const CavScenario* tables, int64_t n_envs, int dtype, int device, uint64_t seed, CavEngine** out) {
+  if (!tables || !out) return fail(CAV_EINVAL, "tables/out is NULL");
+  *out = nullptr;
+  if (n_envs <= 0) return fail(CAV_EINVAL, "n_envs must be positive");
+  if (dtype != CAV_F64 && dtype != CAV_F32) return fail(CAV_EINVAL, "dtype must be CAV_F64 or CAV_F32");
+  if (tables->n_bodies < 1 || !tables->bodies) return fail(CAV_EINVAL, "scenario has no bodies");
+  if (tables->n_bodies > CAV_SMALL_M)
+    return fail(CAV_EINVAL, "more than CAV_SMALL_M bodies: the dense block-per-environment path is not built in this library");
+  if (tables->n_roads < 1 || tables->n_roads > CAV_MAX_ROADS || tables->n_statics < 0 || tables->n_statics > CAV_MAX_STATICS ||
+      tables->n_types < 0 || tables->n_types > CAV_MAX_TYPES)
+    return fail(CAV_EINVAL, "road/static/type counts out of range");
+  if (tables->bodies[0].kind != CAV_BODY_DYNAMIC) return fail(CAV_EINVAL, "the ego (body 0) must be a dynamic body");
+  for (int b = 0; b < tables->n_bodies; ++b) {
+    const CavBody& body = tables->bodies[b];
+    if (body.kind == CAV_BODY_DYNAMIC && (body.type_id < 0 || body.type_id >= tables->n_types))
+      return fail(CAV_EINVAL, "body type_id out of range");
+    if ((body.flags & CAV_FLAG_SPAWN) && (body.spawn_id < 0 || body.spawn_id >= tables->n_spawns || !tables->spawns))
+      return fail(CAV_EINVAL, "spawn_id out of range");
+    if (body.agent < CAV_AGENT_EXTERNAL || body.agent > CAV_AGENT_PROXIMITY) return fail(CAV_EINVAL, "unknown agent kind");
+    if ((body.agent == CAV_AGENT_RANDOM_CONSTRAINED || body.agent == CAV_AGENT_PROXIMITY) &&
+        !(body.kind == CAV_BODY_DYNAMIC && (body.flags & CAV_FLAG_PEDESTRIAN)))
+      return fail(CAV_EINVAL, "crossing agents need a Pedestrian body (config.py:358-396)");
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  CavEngine* eng = new (std::nothrow) CavEngine();
+  if (!eng) return fail(CAV_ENOMEM, "out of host memory");
+  eng->dtype = dtype; eng->device = device; eng->m = tables->n_bodies; eng->n = n_envs; eng->seed = seed;
+  eng->tau = dtype == CAV_F64 ? 1e-7 : 5e-2;
+  eng->host = *tables;
+  eng->bodies.assign(tables->bodies, tables->bodies + tables->n_bodies);
+  if (tables->n_spawns > 0) eng->spawns.assign(tables->spawns, tables->spawns + tables->n_spawns);
+  eng->host.bodies = eng->bodies.data();
+  eng->host.spawns = eng->spawns.data();
+  for (const CavBody& body : eng->bodies) {
+    if (body.agent == CAV_AGENT_EXTERNAL) eng->has_external = true; else eng->has_device_agents = true;
+  }
+  rebuild_tables(eng);
+  int rc = dtype == CAV_F64 ? setup_buffers(eng, eng->buf64) : setup_buffers(eng, eng->buf32);
+  if (rc == CAV_OK) rc = dev_alloc(eng, &eng->d_scratch, 2);
+  if (rc == CAV_OK) rc = do_reset(eng, nullptr, nullptr, 1, nullptr);  // constructor-time spawn (bodies.py:296)
+  if (rc == CAV_OK) {
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) rc = fail(CAV_ECUDA, std::string("create: ") + cudaGetErrorString(err));
+  }
+  if (rc != CAV_OK) { cavgym_destroy(eng); return rc; }
+  *out = eng;
+  return CAV_OK;
+}
+
+int cavgym_destroy(CavEngine* eng) {
+  if (!eng) return CAV_OK;
+  cudaSetDevice(eng->device);
+  cudaDeviceSynchronize();
+  for (void* p : eng->allocations) cudaFree(p);
+  for (cudaStream_t s : eng->pipe) if (s) cudaStreamDestroy(s);
+  delete eng;
+  return CAV_OK;
+}
+
+int cavgym_set_shard(CavEngine* eng, int64_t offset) {
+  int rc = check_engine(eng);
+  if (rc) return rc;
+  if (offset < 0 || offset + eng->n > ((int64_t)1 << 40)) return fail(CAV_EINVAL, "global env ids must fit 40 bits");
+  eng->buf64.shard = offset; eng->buf32.shard = offset;
+  rc = do_reset(eng, nullptr, nullptr, 1, nullptr);  // redo the constructor-time spawn with the global ids
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  return CAV_OK;
+}
+
+int cavgym_reset(CavEngine* eng, const uint8_t* mask, const void* init_state, cudaStream_t stream) {
+  int rc = check_engine(eng);
+  if (rc) return rc;
+  return do_reset(eng, mask, init_state, 0, stream);
+}
+
+static int step_range(CavEngine* eng, int64_t lo, int64_t hi, const void* actions, void* state_out, void* reward_out,
+                      uint8_t* done_out, int32_t* winner_out, uint8_t* tangent_out, cudaStream_t stream) {
+  if (eng->dtype == CAV_F64) {
+    EnvBuffers<double> buf = eng->buf64; buf.lo = lo; buf.hi = hi;
+    StepIO<double> io{(const double*)actions, (double*)state_out, (double*)reward_out, done_out, winner_out, tangent_out};
+    small_launchers<double>(eng->m)->step(eng->sc64, buf, io, eng->t_global, eng->has_device_agents, stream);
+  } else {
+    EnvBuffers<float> buf = eng->buf32; buf.lo = lo; buf.hi = hi;
+    StepIO<float> io{(const float*)actions, (float*)state_out, (float*)reward_out, done_out, winner_out, tangent_out};
+    small_launchers<float>(eng->m)->step(eng->sc32, buf, io, eng->t_global, eng->has_device_agents, stream);
+  }
+  return launch_check(eng, "step kernel");
+}
+
+int cavgym_step(CavEngine* eng, const void* actions, void* state_out, void* reward_out, uint8_t* done_out, int32_t* winner_out,
+                uint8_t* tangent_flag_out, cudaStream_t stream) {
+  int rc = check_engine(eng);
+  if (rc) return rc;
+  if (!actions && eng->has_external) return fail(CAV_EINVAL, "actions is NULL but a body has CAV_AGENT_EXTERNAL");
+  rc = step_range(eng, 0, eng->n, actions, state_out, reward_out, done_out, winner_out, tangent_flag_out, stream);
+  if (rc) return rc;
+  eng->t_global += 1;
+  return CAV_OK;
+}
+
+int cavgym_rollout(CavEngine* eng, int n_steps, int auto_reset, cudaStream_t stream) {
+  int rc = check_engine(eng);
+  if (rc) return rc;
+  if (n_steps < 0) return fail(CAV_EINVAL, "n_steps must be >= 0");
+  if (eng->has_external) return fail(CAV_ESTATE, "cavgym_rollout needs an on-device agent for every body");
+  if (n_steps == 0) return CAV_OK;
+  if (eng->dtype == CAV_F64) small_launchers<double>(eng->m)->rollout(eng->sc64, eng->buf64, eng->t_global, n_steps, auto_reset, stream);
+  else small_launchers<float>(eng->m)->rollout(eng->sc32, eng->buf32, eng->t_global, n_steps, auto_reset, stream);
+  rc = launch_check(eng, "rollout kernel");
+  if (rc) return rc;
+  eng->t_global += n_steps;
+  return CAV_OK;
+}
+
+int cavgym_replay(CavEngine* eng, int n_steps, const void* actions, void* state_traj, void* reward_traj, uint8_t* done_traj,
+                  int32_t* winner_traj, uint8_t* tangent_traj, cudaStream_t stream) {
+  int rc = check_engine(eng);
+  if (rc) return rc;
+  if (n_steps < 0) return fail(CAV_EINVAL, "n_steps must be >= 0");
+  if (!actions) return fail(CAV_EINVAL, "actions is NULL");
+  if (eng->has_device_agents) return fail(CAV_ESTATE, "cavgym_replay needs CAV_AGENT_EXTERNAL for every body");
+  if (n_steps == 0) return CAV_OK;
+  if (eng->dtype == CAV_F64) {
+    StepIO<double> io{(const double*)actions, (double*)state_traj, (double*)reward_traj, done_traj, winner_traj, tangent_traj};
+    small_launchers<double>(eng->m)->replay(eng->sc64, eng->buf64, io, eng->t_global, n_steps, stream);
+  } else {
+    StepIO<float> io{(const float*)actions, (float*)state_traj, (float*)reward_traj, done_traj, winner_traj, tangent_traj};
+    small_launchers<float>(eng->m)->replay(eng->sc32, eng->buf32, io, eng->t_global, n_steps, stream);
+  }
+  rc = launch_check(eng, "replay kernel");
+  if (rc) return rc;
+  eng->t_global += n_steps;
+  return CAV_OK;
+}
+
+// Host buffers: env range split into chunks, each chunk's H2D copy -> kernel -> D2H copies queued on one of
+// kPipe streams so that copies of one chunk overlap the kernel and copies of the others (PCIe is full duplex).
+int cavgym_step_host(CavEngine* eng, const void* actions, void* state_out, void* reward_out, uint8_t* done_out,
+                     int32_t* winner_out, uint8_t* tangent_flag_out) {
+  int rc = check_engine(eng);
+  if (rc) return rc;
+  if (!actions && eng->has_external) return fail(CAV_EINVAL, "actions is NULL but a body has CAV_AGENT_EXTERNAL");
+  const int64_t n = eng->n, m = eng->m;
+  const size_t rs = eng->real_size();
+  if (!eng->pipe[0]) {
+    for (auto& s : eng->pipe) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, (size_t)m * 2 * n * rs)); eng->allocations.push_back(p); eng->d_actions = p;
+    CUDA_TRY(cudaMalloc(&p, (size_t)m * n * rs)); eng->allocations.push_back(p); eng->d_reward = p;
+    if ((rc = dev_alloc(eng, &eng->d_done, (size_t)n))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_tangent, (size_t)n))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_winner, (size_t)n))) return rc;
+  }
+  CUDA_TRY(cudaDeviceSynchronize());  // order after whatever the caller queued on other streams
+  const int64_t chunks = n >= (1 << 16) ? 8 : (n >= (1 << 12) ? 2 : 1);
+  char* d_state = (char*)(eng->dtype == CAV_F64 ? (void*)eng->buf64.state : (void*)eng->buf32.state);
+  for (int64_t c = 0; c < chunks; ++c) {
+    const int64_t lo = n * c / chunks, hi = n * (c + 1) / chunks, w = hi - lo;
+    if (w <= 0) continue;
+    cudaStream_t s = eng->pipe[c % CavEngine::kPipe];
+    if (actions)
+      CUDA_TRY(cudaMemcpy2DAsync((char*)eng->d_actions + lo * rs, n * rs, (const char*)actions + lo * rs, n * rs, w * rs, m * 2,
+                                 cudaMemcpyHostToDevice, s));
+    rc = step_range(eng, lo, hi, actions ? eng->d_actions : nullptr, nullptr, reward_out ? eng->d_reward : nullptr,
+                    done_out ? eng->d_done : nullptr, winner_out ? eng->d_winner : nullptr,
+                    tangent_flag_out ? eng->d_tangent : nullptr, s);
+    if (rc) return rc;
+    if (state_out)
+      CUDA_TRY(cudaMemcpy2DAsync((char*)state_out + lo * rs, n * rs, d_state + lo * rs, n * rs, w * rs, m * 4, cudaMemcpyDeviceToHost, s));
+    if (reward_out)
+      CUDA_TRY(cudaMemcpy2DAsync((char*)reward_out + lo * rs, n * rs, (char*)eng->d_reward + lo * rs, n * rs, w * rs, m,
+                                 cudaMemcpyDeviceToHost, s));
+    if (done_out) CUDA_TRY(cudaMemcpyAsync(done_out + lo, eng->d_done + lo, w, cudaMemcpyDeviceToHost, s));
+    if (winner_out) CUDA_TRY(cudaMemcpyAsync(winner_out + lo, eng->d_winner + lo, w * 4, cudaMemcpyDeviceToHost, s));
+    if (tangent_flag_out) CUDA_TRY(cudaMemcpyAsync(tangent_flag_out + lo, eng->d_tangent + lo, w, cudaMemcpyDeviceToHost, s));
+  }
+  for (auto& s : eng->pipe) CUDA_TRY(cudaStreamSynchronize(s));
+  eng->t_global += 1;
+  return CAV_OK;
+}
+
+int cavgym_stats(CavEngine* eng, int64_t* out10) {
+  int rc = check_engine(eng);
+  if (rc) return rc;
+  if (!out10) return fail(CAV_EINVAL, "out10 is NULL");
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemset(eng->d_scratch, 0, 2 * sizeof(unsigned long long)));
+  const int32_t* t_ep = eng->dtype == CAV_F64 ? eng->buf64.t_ep : eng->buf32.t_ep;
+  const uint8_t* done = eng->dtype == CAV_F64 ? eng->buf64.done : eng->buf32.done;
+  const uint8_t* err = eng->dtype == CAV_F64 ? eng->buf64.err : eng->buf32.err;
+  const unsigned long long* stats = eng->dtype == CAV_F64 ? eng->buf64.stats : eng->buf32.stats;
+  live_steps_kernel<<<148 * 4, 256>>>(t_ep, done, err, eng->n, eng->d_scratch);
+  rc = launch_check(eng, "stats kernel");
+  if (rc) return rc;
+  unsigned long long raw[CAV_N_STATS], extra[2];
+  CUDA_TRY(cudaMemcpy(raw, stats, sizeof(raw), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(extra, eng->d_scratch, sizeof(extra), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < CAV_N_STATS; ++i) out10[i] = (int64_t)raw[i];
+  out10[CAV_STAT_ENV_STEPS] = (int64_t)(raw[CAV_STAT_SUM_T] + extra[0]);  // finished episodes + episodes in flight
+  out10[CAV_STAT_BODY_STEPS] = out10[CAV_STAT_ENV_STEPS] * eng->m;
+  out10[CAV_STAT_ERRORS] = (int64_t)extra[1];
+  return CAV_OK;
+}
+
+int cavgym_error_count(CavEngine* eng, int64_t* out) {
+  int64_t stats[CAV_N_STATS];
+  int rc = cavgym_stats(eng, stats);
+  if (rc) return rc;
+  if (!out) return fail(CAV_EINVAL, "out is NULL");
+  *out = stats[CAV_STAT_ERRORS];
+  return CAV_OK;
+}
+
+int cavgym_launch_count(CavEngine* eng, int64_t* out) {
+  if (!eng || !out) return fail(CAV_EINVAL, "engine/out is NULL");
+  *out = eng->launches;
+  return CAV_OK;
+}
+
+#define CAV_PTR(field) (eng ? (eng->dtype == CAV_F64 ? (void*)eng->buf64.field : (void*)eng->buf32.field) : nullptr)
+void* cavgym_state_ptr(CavEngine* eng) { return CAV_PTR(state); }
+int32_t* cavgym_liveness_ptr(CavEngine* eng) { return (int32_t*)CAV_PTR(liveness); }
+void* cavgym_agent_state_ptr(CavEngine* eng) { return CAV_PTR(agent); }
+void* cavgym_action_ptr(CavEngine* eng) { return CAV_PTR(action); }
+int32_t* cavgym_timestep_ptr(CavEngine* eng) { return (int32_t*)CAV_PTR(t_ep); }
+uint8_t* cavgym_done_ptr(CavEngine* eng) { return (uint8_t*)CAV_PTR(done); }
+int32_t* cavgym_winner_ptr(CavEngine* eng) { return (int32_t*)CAV_PTR(winner); }
+uint8_t* cavgym_error_ptr(CavEngine* eng) { return (uint8_t*)CAV_PTR(err); }
+#undef CAV_PTR
+
+int cavgym_set_uniform_override(CavEngine* eng, const double* uniforms) {
+  if (!eng) return fail(CAV_EINVAL, "engine is NULL");
+  eng->buf64.uni_override = uniforms; eng->buf32.uni_override = uniforms;
+  return CAV_OK;
+}
+
+int cavgym_set_spawn_override(CavEngine* eng, const double* draws) {
+  if (!eng) return fail(CAV_EINVAL, "engine is NULL");
+  eng->buf64.spawn_override = draws; eng->buf32.spawn_override = draws;
+  return CAV_OK;
+}
+
+int cavgym_set_action_logging(CavEngine* eng, int enabled) {
+  if (!eng) return fail(CAV_EINVAL, "engine is NULL");
+  eng->buf64.log_actions = enabled; eng->buf32.log_actions = enabled;
+  return CAV_OK;
+}
+
+int cavgym_set_global_timestep(CavEngine* eng, int64_t t) {
+  if (!eng) return fail(CAV_EINVAL, "engine is NULL");
+  eng->t_global = t;
+  return CAV_OK;
+}
+
+int cavgym_set_tangent_tolerance(CavEngine* eng, double tau) {
+  if (!eng) return fail(CAV_EINVAL, "engine is NULL");
+  if (!(tau >= 0)) return fail(CAV_EINVAL, "tau must be >= 0");
+  eng->tau = tau;
+  rebuild_tables(eng);
+  return CAV_OK;
+}
+
+int cavgym_bodies_step(const CavBodyType* type, void* state, const void* actions, int64_t n, double time_resolution, int dtype,
+                       cudaStream_t stream) {
+  if (!type || !state || !actions || n < 0) return fail(CAV_EINVAL, "bad argument");
+  if (n == 0) return CAV_OK;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (dtype == CAV_F64) bodies_step_kernel<double><<<grid, 128, 0, stream>>>(to_type<double>(*type), (double*)state, (const double*)actions, n, time_resolution);
+  else if (dtype == CAV_F32) bodies_step_kernel<float><<<grid, 128, 0, stream>>>(to_type<float>(*type), (float*)state, (const float*)actions, n, (float)time_resolution);
+  else return fail(CAV_EINVAL, "dtype must be CAV_F64 or CAV_F32");
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(CAV_ECUDA, std::string("bodies_step kernel: ") + cudaGetErrorString(err));
+  return CAV_OK;
+}
+
+int cavgym_geometry_probe(const void* quads_a, const void* quads_b, void* out, int64_t n, int dtype, cudaStream_t stream) {
+  if (!quads_a || !quads_b || !out || n < 0) return fail(CAV_EINVAL, "bad argument");
+  if (n == 0) return CAV_OK;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (dtype == CAV_F64) geometry_probe_kernel<double><<<grid, 128, 0, stream>>>((const double*)quads_a, (const double*)quads_b, (double*)out, n, 1e-7);
+  else if (dtype == CAV_F32) geometry_probe_kernel<float><<<grid, 128, 0, stream>>>((const float*)quads_a, (const float*)quads_b, (float*)out, n, 5e-2f);
+  else return fail(CAV_EINVAL, "dtype must be CAV_F64 or CAV_F32");
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(CAV_ECUDA, std::string("geometry_probe kernel: ") + cudaGetErrorString(err));
+  return CAV_OK;
+}
+
+}  // extern "C"

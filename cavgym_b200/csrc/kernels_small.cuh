@@ -1,0 +1,251 @@
+// kernels_small.cuh — thread-per-environment kernels for scenarios with M <= CAV_SMALL_M bodies.
+//
+//   step_kernel     one CAVEnv.step over all N envs                 (cavgym_step)
+//   replay_kernel   T steps on replayed joint actions, state kept in registers   (cavgym_replay)
+//   rollout_kernel  T steps with on-device agents, scoring and auto-reset in-kernel  (cavgym_rollout)
+//   reset_kernel    CAVEnv.reset for masked envs                    (cavgym_reset / cavgym_create)
+//
+// HBM layout is SoA with the environment index fastest, so lane i of a warp touches
+// consecutive 8-byte (fp64) / 4-byte (fp32) words: every global access is a fully
+// coalesced 256 B / 128 B warp transaction.  All loads of a thread are issued before the
+// first dependent use (memory-level parallelism = 6M+2 independent loads per thread).
+// Roofline: HBM-bound streaming; algorithmic bytes per body-step 88 B (fp64) / 44 B (fp32)
+// on replayed actions.  No shared memory: there is no reuse across envs.
+#pragma once
+#include "transition.cuh"
+
+namespace cav {
+
+constexpr int kThreads = 128;
+
+template <typename R, int M, bool AGENTS>
+__device__ __forceinline__ void load_env(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, EnvRegs<R, M>& env) {
+  const int64_t n = buf.n;
+  env.done = buf.done[e];
+  env.t_ep = buf.t_ep[e];
+  env.winner = env.done ? buf.winner[e] : -1;
+  env.ag_dirty = 0;
+  env.episode = AGENTS ? buf.episode[e] : 0;
+#pragma unroll
+  for (int b = 0; b < M; ++b) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) env.s[b][c] = buf.state[((int64_t)b * 4 + c) * n + e];
+    env.held[b][0] = R(0); env.held[b][1] = R(0);
+    if (AGENTS && sc.bodies[b].agent == CAV_AGENT_RANDOM) {
+      env.held[b][0] = buf.action[((int64_t)b * 2 + 0) * n + e];
+      env.held[b][1] = buf.action[((int64_t)b * 2 + 1) * n + e];
+    }
+    if (AGENTS && uses_agent_state<R, M>(sc, b)) {
+#pragma unroll
+      for (int w = 0; w < CAV_AGENT_WORDS; ++w) env.ag[b][w] = buf.agent[((int64_t)b * CAV_AGENT_WORDS + w) * n + e];
+    }
+  }
+}
+
+// Write back what a kernel changed.  `all` forces every per-env word (after a reset).
+template <typename R, int M, bool AGENTS>
+__device__ __forceinline__ void store_env(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, const EnvRegs<R, M>& env,
+                                          bool all) {
+  const int64_t n = buf.n;
+#pragma unroll
+  for (int b = 0; b < M; ++b) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) buf.state[((int64_t)b * 4 + c) * n + e] = env.s[b][c];
+    if (all || (AGENTS && sc.bodies[b].agent != CAV_AGENT_EXTERNAL && (buf.log_actions || sc.bodies[b].agent == CAV_AGENT_RANDOM))) {
+      buf.action[((int64_t)b * 2 + 0) * n + e] = env.held[b][0];
+      buf.action[((int64_t)b * 2 + 1) * n + e] = env.held[b][1];
+    }
+    if (all || (AGENTS && uses_agent_state<R, M>(sc, b) && (env.ag_dirty >> b & 1u))) {
+#pragma unroll
+      for (int w = 0; w < CAV_AGENT_WORDS; ++w) buf.agent[((int64_t)b * CAV_AGENT_WORDS + w) * n + e] = env.ag[b][w];
+    }
+  }
+  buf.t_ep[e] = env.t_ep;
+  if (all || env.done) { buf.done[e] = env.done; buf.winner[e] = env.winner; }
+  if (all) buf.episode[e] = env.episode;
+}
+
+template <typename R, int M>
+__device__ __forceinline__ void write_outputs(const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t e, const EnvRegs<R, M>& env,
+                                              const R (&reward)[M], bool done, int32_t winner, bool tangent) {
+  const int64_t n = buf.n;
+  if (io.state_out && io.state_out != buf.state) {
+#pragma unroll
+    for (int b = 0; b < M; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) io.state_out[((int64_t)b * 4 + c) * n + e] = env.s[b][c];
+  }
+  if (io.reward_out) {
+#pragma unroll
+    for (int b = 0; b < M; ++b) io.reward_out[(int64_t)b * n + e] = reward[b];
+  }
+  if (io.done_out) io.done_out[e] = done ? 1 : 0;
+  if (io.winner_out) io.winner_out[e] = winner;
+  if (io.tangent_out) io.tangent_out[e] = tangent ? 1 : 0;
+}
+
+// One transition of env e held in `env`, with all the bookkeeping shared by the three kernels:
+// frozen envs, invalid actions, outputs, latching and scoring.  Returns true if the episode ended.
+template <typename R, int M, bool AGENTS>
+__device__ __forceinline__ bool advance(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t e,
+                                        int64_t t_global, EnvRegs<R, M>& env, const R (&ext)[M][2], LocalStats& ls) {
+  StepResult<R, M> res;
+  if (env.done) {  // frozen until reset
+#pragma unroll
+    for (int b = 0; b < M; ++b) res.reward[b] = R(0);
+    write_outputs<R, M>(buf, io, e, env, res.reward, env.done == 1, env.winner, false);
+    return false;
+  }
+  transition<R, M, AGENTS>(sc, buf, e, t_global, env, ext, res);
+  if (res.invalid) buf.err[e] = 1;
+  write_outputs<R, M>(buf, io, e, env, res.reward, res.terminate, res.winner, res.tangent);
+  ls.tangent += res.tangent ? 1 : 0;
+  if (env.done) {
+    score_episode<R, M>(buf, e, env, ls);
+    return true;
+  }
+  return false;
+}
+
+template <typename R, int M>
+__device__ __forceinline__ void load_actions(const R* actions, int64_t n, int64_t e, R (&ext)[M][2]) {
+#pragma unroll
+  for (int b = 0; b < M; ++b) {
+    ext[b][0] = actions ? actions[((int64_t)b * 2 + 0) * n + e] : R(0);
+    ext[b][1] = actions ? actions[((int64_t)b * 2 + 1) * n + e] : R(0);
+  }
+}
+
+template <typename R, int M, bool AGENTS>
+__global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ DevScenario<R> sc,
+                                                        const __grid_constant__ EnvBuffers<R> buf,
+                                                        const __grid_constant__ StepIO<R> io, int64_t t_global) {
+  const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  LocalStats ls;
+  if (e < buf.hi) {
+    EnvRegs<R, M> env;
+    R ext[M][2];
+    load_env<R, M, AGENTS>(sc, buf, e, env);
+    load_actions<R, M>(io.actions, buf.n, e, ext);
+    const bool was_live = env.done == 0;
+    advance<R, M, AGENTS>(sc, buf, io, e, t_global, env, ext, ls);
+    if (was_live) store_env<R, M, AGENTS>(sc, buf, e, env, false);
+  }
+  flush_stats(ls, buf.stats);
+}
+
+// Trajectory outputs are [T][...] slabs of the per-step shapes; io.* point at step 0.
+template <typename R, int M>
+__global__ void __launch_bounds__(kThreads) replay_kernel(const __grid_constant__ DevScenario<R> sc,
+                                                          const __grid_constant__ EnvBuffers<R> buf,
+                                                          const __grid_constant__ StepIO<R> io, int64_t t_global, int n_steps) {
+  const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t n = buf.n;
+  LocalStats ls;
+  if (e < buf.hi) {
+    EnvRegs<R, M> env;
+    load_env<R, M, false>(sc, buf, e, env);
+    const bool was_live = env.done == 0;
+    R ext[M][2], nxt[M][2];
+    load_actions<R, M>(io.actions, n, e, ext);
+    for (int t = 0; t < n_steps; ++t) {
+      // software prefetch: issue step t+1's action loads before step t's arithmetic
+      if (t + 1 < n_steps) load_actions<R, M>(io.actions + (int64_t)(t + 1) * M * 2 * n, n, e, nxt);
+      StepIO<R> at = io;
+      at.actions = nullptr;
+      if (io.state_out) at.state_out = io.state_out + (int64_t)t * M * 4 * n;
+      if (io.reward_out) at.reward_out = io.reward_out + (int64_t)t * M * n;
+      if (io.done_out) at.done_out = io.done_out + (int64_t)t * n;
+      if (io.winner_out) at.winner_out = io.winner_out + (int64_t)t * n;
+      if (io.tangent_out) at.tangent_out = io.tangent_out + (int64_t)t * n;
+      advance<R, M, false>(sc, buf, at, e, t_global + t, env, ext, ls);
+#pragma unroll
+      for (int b = 0; b < M; ++b) { ext[b][0] = nxt[b][0]; ext[b][1] = nxt[b][1]; }
+    }
+    if (was_live) store_env<R, M, false>(sc, buf, e, env, false);
+  }
+  flush_stats(ls, buf.stats);
+}
+
+template <typename R, int M>
+__global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant__ DevScenario<R> sc,
+                                                           const __grid_constant__ EnvBuffers<R> buf, int64_t t_global,
+                                                           int n_steps, int auto_reset) {
+  const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  LocalStats ls;
+  if (e < buf.hi) {
+    EnvRegs<R, M> env;
+    load_env<R, M, true>(sc, buf, e, env);
+    const StepIO<R> io = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    R ext[M][2];
+    load_actions<R, M>(nullptr, buf.n, e, ext);
+    bool was_reset = false;
+    for (int t = 0; t < n_steps; ++t) {
+      if (env.done) {
+        if (!auto_reset) break;
+        reset_env<R, M>(sc, buf, nullptr, e, env);
+        was_reset = true;
+      }
+      advance<R, M, true>(sc, buf, io, e, t_global + t, env, ext, ls);
+    }
+    if (auto_reset && env.done) { reset_env<R, M>(sc, buf, nullptr, e, env); was_reset = true; }
+    store_env<R, M, true>(sc, buf, e, env, was_reset);
+  }
+  flush_stats(ls, buf.stats);
+}
+
+template <typename R, int M>
+__global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__ DevScenario<R> sc,
+                                                         const __grid_constant__ EnvBuffers<R> buf, const uint8_t* mask,
+                                                         const R* init, int first_time) {
+  const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (e >= buf.hi || (mask && !mask[e])) return;
+  EnvRegs<R, M> env;
+  env.episode = first_time ? -1 : buf.episode[e];
+  reset_env<R, M>(sc, buf, init, e, env);
+  store_env<R, M, true>(sc, buf, e, env, true);
+  if (first_time) buf.err[e] = 0;
+}
+
+// ---------------------------------------------------------------- host-side launch table
+template <typename R>
+struct SmallLaunchers {
+  void (*step)(const DevScenario<R>&, const EnvBuffers<R>&, const StepIO<R>&, int64_t t_global, bool agents, cudaStream_t);
+  void (*replay)(const DevScenario<R>&, const EnvBuffers<R>&, const StepIO<R>&, int64_t t_global, int n_steps, cudaStream_t);
+  void (*rollout)(const DevScenario<R>&, const EnvBuffers<R>&, int64_t t_global, int n_steps, int auto_reset, cudaStream_t);
+  void (*reset)(const DevScenario<R>&, const EnvBuffers<R>&, const uint8_t* mask, const R* init, int first_time, cudaStream_t);
+};
+
+template <typename R> inline unsigned grid_for(const EnvBuffers<R>& buf) { return (unsigned)((buf.hi - buf.lo + kThreads - 1) / kThreads); }
+
+template <typename R, int M>
+void launch_step(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t t_global, bool agents,
+                 cudaStream_t stream) {
+  if (agents) step_kernel<R, M, true><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, io, t_global);
+  else step_kernel<R, M, false><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, io, t_global);
+}
+template <typename R, int M>
+void launch_replay(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t t_global, int n_steps,
+                   cudaStream_t stream) {
+  replay_kernel<R, M><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, io, t_global, n_steps);
+}
+template <typename R, int M>
+void launch_rollout(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t t_global, int n_steps, int auto_reset,
+                    cudaStream_t stream) {
+  rollout_kernel<R, M><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
+}
+template <typename R, int M>
+void launch_reset(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const uint8_t* mask, const R* init, int first_time,
+                  cudaStream_t stream) {
+  reset_kernel<R, M><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, mask, init, first_time);
+}
+
+template <typename R, int M>
+constexpr SmallLaunchers<R> make_launchers() {
+  return {&launch_step<R, M>, &launch_replay<R, M>, &launch_rollout<R, M>, &launch_reset<R, M>};
+}
+
+// Defined in small_mK.cu (one translation unit per body count so they compile in parallel).
+template <typename R> const SmallLaunchers<R>* small_launchers(int m);
+
+}  // namespace cav

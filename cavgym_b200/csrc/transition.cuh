@@ -1,0 +1,392 @@
+// transition.cuh — one joint transition of ONE environment, entirely in registers.
+//
+// Restates, in the reference's order (library/environment.py:119-223):
+//   joint action        agents' choose_action on the pre-step state        simulation.py:71
+//   validation          action_space.contains                              environment.py:120
+//   body.step           kinematic bicycle / traffic-light state            environment.py:122-123
+//   bounding boxes      info()['body_polygons']                            environment.py:107,125-127
+//   rewards, liveness                                                      environment.py:131-146
+//   termination cascade finish > all-collisions > off-road > ego-collision > reaction zone   :148-206
+//   terminal rewards, winner                                               environment.py:208-220
+//   process_feedback    crossing agents, post-step state                   simulation.py:86-87
+// Used by the step, replay and rollout kernels (kernels_small.cuh), so the three share one
+// definition of a transition.  Thread-per-environment: every array below is indexed by
+// compile-time constants after unrolling and lives in registers.
+#pragma once
+#include "agents.cuh"
+
+namespace cav {
+
+template <typename R, int M>
+struct EnvRegs {
+  R s[M][4];         // x, y, v, theta (PelicanCrossing: light state in [0])
+  R held[M][2];      // last action of on-device agents (RandomAgent holds it)
+  R ag[M][CAV_AGENT_WORDS];
+  int32_t t_ep, episode, winner;
+  uint32_t ag_dirty;  // bit b: ag[b] changed since it was loaded
+  uint8_t done;
+};
+
+struct LocalStats {
+  unsigned long long episodes = 0, interesting = 0, sum_t = 0, sum_t2 = 0, tangent = 0;
+  long long sum_score = 0, sum_score2 = 0;
+};
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Whole-warp call: reduce with shuffles, one atomic per counter per warp, skipped when the warp has nothing.
+__device__ __forceinline__ void flush_stats(const LocalStats& ls, unsigned long long* stats) {
+  const bool any = (ls.episodes | ls.tangent) != 0;
+  if (!__any_sync(0xffffffffu, any)) return;
+  const unsigned long long ep = warp_sum(ls.episodes), in = warp_sum(ls.interesting), st = warp_sum(ls.sum_t),
+                           st2 = warp_sum(ls.sum_t2), tg = warp_sum(ls.tangent),
+                           sc = warp_sum((unsigned long long)ls.sum_score), sc2 = warp_sum((unsigned long long)ls.sum_score2);
+  if ((threadIdx.x & 31) == 0) {
+    if (ep) atomicAdd(&stats[CAV_STAT_EPISODES], ep);
+    if (in) atomicAdd(&stats[CAV_STAT_INTERESTING], in);
+    if (st) atomicAdd(&stats[CAV_STAT_SUM_T], st);
+    if (st2) atomicAdd(&stats[CAV_STAT_SUM_T2], st2);
+    if (sc) atomicAdd(&stats[CAV_STAT_SUM_SCORE], sc);  // two's complement: wraps to the signed sum
+    if (sc2) atomicAdd(&stats[CAV_STAT_SUM_SCORE2], sc2);
+    if (tg) atomicAdd(&stats[CAV_STAT_TANGENT], tg);
+  }
+}
+
+template <typename R, int M>
+__device__ __forceinline__ bool uses_agent_state(const DevScenario<R>& sc, int b) {
+  return sc.bodies[b].agent == CAV_AGENT_RANDOM_CONSTRAINED || sc.bodies[b].agent == CAV_AGENT_PROXIMITY;
+}
+
+// Result of one transition besides the updated EnvRegs.
+template <typename R, int M>
+struct StepResult {
+  R reward[M];
+  bool terminate, tangent, invalid;
+  int32_t winner;
+};
+
+// AGENTS = false compiles the replay-only variant: every body takes its action from `ext`.
+template <typename R, int M, bool AGENTS>
+__device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, int64_t t_global,
+                                           EnvRegs<R, M>& env, const R (&ext)[M][2], StepResult<R, M>& out) {
+  const R tau = sc.tau, dt = sc.dt;
+  bool tangent = false;
+  R act[M][2];
+
+  // ---- joint action from the pre-step state
+  bool valid = true;
+#pragma unroll
+  for (int b = 0; b < M; ++b) {
+    const DevBody<R>& body = sc.bodies[b];
+    const DevType<R>& k = body.k;
+    R a0 = ext[b][0], a1 = ext[b][1];
+    if (AGENTS && body.agent != CAV_AGENT_EXTERNAL) {
+      a0 = env.held[b][0]; a1 = env.held[b][1];
+      double u[CAV_DRAWS] = {0.0, 0.0, 0.0};
+      const bool draws = body.agent == CAV_AGENT_RANDOM || body.agent == CAV_AGENT_RANDOM_CONSTRAINED;
+      if (draws) {
+        if (buf.uni_override) {
+#pragma unroll
+          for (int c = 0; c < CAV_DRAWS; ++c) u[c] = buf.uni_override[((int64_t)b * CAV_DRAWS + c) * buf.n + e];
+        } else {
+          draw_block(buf.seed, (uint64_t)(buf.shard + e), b, KIND_AGENT0, (uint32_t)env.episode, (uint32_t)env.t_ep, u);
+        }
+      }
+      if (body.agent == CAV_AGENT_NOOP) {
+        a0 = R(0); a1 = R(0);
+      } else if (body.agent == CAV_AGENT_RANDOM) {  // RandomAgent.choose_action (template.py:52-56)
+        if (u[0] < body.epsilon) {
+          if (body.kind == CAV_BODY_PELICAN) {
+            a0 = R(floor(u[1] * 4.0)); if (a0 > R(3)) a0 = R(3);
+            a1 = R(0);
+          } else {
+            if (!buf.uni_override) {
+              double w[2];
+              draw_block(buf.seed, (uint64_t)(buf.shard + e), b, KIND_AGENT1, (uint32_t)env.episode, (uint32_t)env.t_ep, w);
+              u[2] = w[0];
+            }
+            a0 = R(double(k.amin) + (double(k.amax) - double(k.amin)) * u[1]);  // Box.sample = low + (high-low)*u
+            a1 = R(double(k.smin) + (double(k.smax) - double(k.smin)) * u[2]);
+          }
+        }
+      } else if (body.agent == CAV_AGENT_RANDOM_CONSTRAINED) {  // pedestrian.py:72-75
+        a0 = R(0);
+        bool dirty = false;
+        a1 = choose_crossing_action(sc, k, env.s[b], env.ag[b], u[0] < body.epsilon, dirty);
+        if (dirty) env.ag_dirty |= 1u << b;
+      } else if (body.agent == CAV_AGENT_PROXIMITY) {  // pedestrian.py:78-91
+        const bool trigger = point_distance(env.s[b][0], env.s[b][1], env.s[0][0], env.s[0][1]) < body.threshold;
+        a0 = R(0);
+        bool dirty = false;
+        a1 = choose_crossing_action(sc, k, env.s[b], env.ag[b], trigger, dirty);
+        if (dirty) env.ag_dirty |= 1u << b;
+      }
+    }
+    act[b][0] = a0; act[b][1] = a1;
+    if (body.kind == CAV_BODY_PELICAN) valid = valid && (a0 == R(0) || a0 == R(1) || a0 == R(2) || a0 == R(3));
+    else valid = valid && (a0 >= k.amin && a0 <= k.amax && a1 >= k.smin && a1 <= k.smax);
+  }
+  out.invalid = !valid;
+  out.tangent = false;
+  out.terminate = false;
+  out.winner = -1;
+  if (!valid) {  // AssertionError before any mutation (environment.py:120)
+#pragma unroll
+    for (int b = 0; b < M; ++b) out.reward[b] = R(0);
+    return;
+  }
+
+  // ---- body.step, then what every later test needs per body: cos/sin of the new heading and the AABB
+  R co[M], si[M];
+  Aabb<R> bb[M];
+  R ego_steer = R(0);
+#pragma unroll
+  for (int b = 0; b < M; ++b) {
+    const DevBody<R>& body = sc.bodies[b];
+    if (AGENTS) { env.held[b][0] = act[b][0]; env.held[b][1] = act[b][1]; }
+    if (body.kind == CAV_BODY_PELICAN) {  // PelicanCrossing.step (bodies.py:450-461)
+      if (act[b][0] == R(1)) env.s[b][0] = R(0);
+      else if (act[b][0] == R(2)) env.s[b][0] = R(1);
+      else if (act[b][0] == R(3)) env.s[b][0] = R(2);
+      co[b] = R(1); si[b] = R(0);
+      bb[b] = aabb_of(body.sbox);
+    } else {
+      const DevType<R>& k = body.k;
+      R snapped;
+      body_step(k, env.s[b], act[b][0], act[b][1], dt, co[b], si[b], snapped);
+      if (b == 0) ego_steer = snapped;
+      Quad<R> q;
+      make_box(k.length, k.width, env.s[b][3], co[b], si[b], env.s[b][0], env.s[b][1], q);
+      bb[b] = aabb_of(q);
+    }
+  }
+  // Rebuilds body b's corners on demand (deterministic, so identical to the ones the AABB came from);
+  // keeping only the AABB live keeps register pressure flat in M.
+  auto box_of = [&](int b, Quad<R>& q) {
+    const DevBody<R>& body = sc.bodies[b];
+    if (body.kind == CAV_BODY_PELICAN) { q = body.sbox; return; }
+    const DevType<R>& k = body.k;
+    make_box(k.length, k.width, env.s[b][3], co[b], si[b], env.s[b][0], env.s[b][1], q);
+  };
+
+  // ---- rewards and liveness
+  const R c = sc.cost_step, W = sc.W;
+  const R ego_rel = rmax(R(0), rmin(R(1), (W - env.s[0][0]) / W));
+  const R voff = rabs(env.s[0][2] - sc.v_maint) / sc.v_off;
+  R r0 = R(0);
+  r0 -= voff * c;
+  r0 += (R(1) - ego_rel) * c;
+  out.reward[0] = r0;
+#pragma unroll
+  for (int b = 1; b < M; ++b) {
+    const bool is_static = sc.bodies[b].kind == CAV_BODY_PELICAN;
+    R p = R(0);
+    bool near = false;
+#pragma unroll
+    for (int r = 0; r < CAV_MAX_ROADS; ++r) {
+      if (r >= sc.n_roads) break;
+      R q = R(0);
+      if (!(aabb_gap(bb[b], sc.road_bb[r]) > tau)) {  // otherwise disjoint: percentage 0
+        Quad<R> mine;
+        box_of(b, mine);
+        q = percentage_intersects(mine, sc.roads[r], tau, near);
+      }
+      if (r == 0 || q > p) p = q;
+    }
+    R rb = R(0);
+    rb -= p * c;
+    rb += ego_rel * c;
+    out.reward[b] = rb;
+    if (!is_static) {
+      if (near || rabs(p - R(0.5)) < tau) tangent = true;
+    }
+    if (p > R(0.5)) buf.liveness[(int64_t)b * buf.n + e] += 1;
+  }
+
+  // ---- termination cascade
+  bool terminate = false, win_ego = false;
+  int win_tester = -1;
+  {
+    const R margin = bb[0].x0 - W;  // all four ego corners x > viewer_width  <=>  min corner x > W
+    if (rabs(margin) < tau) tangent = true;
+    if (margin > R(0)) { terminate = true; win_ego = true; }
+  }
+  if (!terminate && sc.collisions == CAV_COLLISIONS_ALL) {
+    bool hit = false;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      if (sc.bodies[i].kind == CAV_BODY_PELICAN) continue;
+#pragma unroll
+      for (int j = i + 1; j < M; ++j) {
+        if (sc.bodies[j].kind == CAV_BODY_PELICAN) continue;
+        if (!(aabb_gap(bb[i], bb[j]) > tau)) {
+          Quad<R> qi, qj;
+          box_of(i, qi);
+          box_of(j, qj);
+          hit |= sat_intersects(qi, qj, tau, tangent);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < CAV_MAX_STATICS; ++s) {
+        if (s >= sc.n_statics) break;
+        if (!(aabb_gap(bb[i], sc.static_bb[s]) > tau)) {
+          Quad<R> qi;
+          box_of(i, qi);
+          hit |= sat_intersects(qi, sc.statics[s], tau, tangent);
+        }
+      }
+    }
+    terminate = hit;
+  }
+  if (!terminate && sc.offroad) {
+    bool on_road = false;
+#pragma unroll
+    for (int r = 0; r < CAV_MAX_ROADS; ++r) {
+      if (r >= sc.n_roads) break;
+      if (!(aabb_gap(bb[0], sc.road_bb[r]) > tau)) {
+        Quad<R> q0;
+        box_of(0, q0);
+        on_road |= sat_intersects(q0, sc.roads[r], tau, tangent);
+      }
+    }
+    terminate = !on_road;
+  }
+  if (!terminate && (sc.collisions == CAV_COLLISIONS_EGO || sc.zones)) {
+    Quad<R> braking, reaction;
+    Aabb<R> braking_bb, reaction_bb;
+    const DevType<R>& k0 = sc.bodies[0].k;
+    const bool have_zones = stopping_zones(k0, env.s[0][0], env.s[0][1], env.s[0][2], env.s[0][3], co[0], si[0], ego_steer,
+                                           braking, reaction);
+    if (have_zones) { braking_bb = aabb_of(braking); reaction_bb = aabb_of(reaction); }
+    if (sc.collisions == CAV_COLLISIONS_EGO) {
+      bool hit = false;
+#pragma unroll
+      for (int b = 1; b < M; ++b) {
+        if (!(sc.bodies[b].flags & CAV_FLAG_PEDESTRIAN)) continue;
+        const bool near_ego = !(aabb_gap(bb[b], bb[0]) > tau);
+        const bool near_brake = have_zones && !(aabb_gap(bb[b], braking_bb) > tau);
+        if (near_ego || near_brake) {
+          Quad<R> qb;
+          box_of(b, qb);
+          bool h = false;
+          if (near_ego) {
+            Quad<R> q0;
+            box_of(0, q0);
+            h = sat_intersects(qb, q0, tau, tangent);
+          }
+          if (!h && near_brake) h = sat_intersects(qb, braking, tau, tangent);
+          hit |= h;
+        }
+      }
+      terminate = hit;
+    }
+    if (!terminate && sc.zones) {
+      if (have_zones) {
+#pragma unroll
+        for (int b = 1; b < M; ++b) {
+          if (!(sc.bodies[b].flags & CAV_FLAG_PEDESTRIAN) || win_tester >= 0) continue;
+          if (!(aabb_gap(bb[b], reaction_bb) > tau)) {
+            Quad<R> qb;
+            box_of(b, qb);
+            if (sat_intersects(qb, reaction, tau, tangent)) win_tester = b;
+          }
+        }
+      }
+      terminate = win_tester >= 0;
+    }
+  }
+
+  // ---- terminal rewards and winner
+  if (terminate || t_global == sc.max_timesteps - 1) {
+    out.reward[0] += win_ego ? sc.reward_win : (win_tester >= 0 ? -sc.reward_win : sc.reward_draw);
+#pragma unroll
+    for (int b = 1; b < M; ++b)
+      out.reward[b] += win_ego ? -sc.reward_win : (win_tester < 0 ? sc.reward_draw : (win_tester == b ? sc.reward_win : sc.reward_draw));
+    if (win_ego) out.winner = 0;
+    else if (win_tester >= 0) out.winner = win_tester;
+  }
+
+  // ---- crossing agents' process_feedback on the new state
+  if (AGENTS) {
+#pragma unroll
+    for (int b = 0; b < M; ++b) {
+      if (uses_agent_state<R, M>(sc, b)) {
+        bool dirty = false;
+        crossing_feedback(sc, env.s[b], env.ag[b], dirty);
+        if (dirty) env.ag_dirty |= 1u << b;
+      }
+    }
+  }
+
+  env.t_ep += 1;
+  env.winner = out.winner;
+  if (terminate) env.done = 1;
+  else if (env.t_ep >= sc.max_timesteps) env.done = 2;  // cut off by Simulation.run (simulation.py:69-70), not `done`
+  out.terminate = terminate;
+  out.tangent = tangent;
+}
+
+// reporting.analyse_episode (reporting.py:227-243) for an env whose episode just ended.
+template <typename R, int M>
+__device__ __forceinline__ void score_episode(const EnvBuffers<R>& buf, int64_t e, const EnvRegs<R, M>& env, LocalStats& ls) {
+  const long long t = env.t_ep;
+  ls.episodes += 1;
+  ls.sum_t += t;
+  ls.sum_t2 += t * t;
+  if (env.winner > 0) {
+    long long score = 0;
+#pragma unroll
+    for (int b = 1; b < M; ++b) score -= buf.liveness[(int64_t)b * buf.n + e];
+    ls.interesting += 1;
+    ls.sum_score += score;
+    ls.sum_score2 += score * score;
+  }
+}
+
+// CAVEnv.reset for one env (environment.py:225-229): bodies back to init_state (SpawnPedestrians re-drawn),
+// liveness zeroed, agents reset, on-device noop action.  `init` (nullable) replays given initial states.
+template <typename R, int M>
+__device__ __forceinline__ void reset_env(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const R* init, int64_t e,
+                                          EnvRegs<R, M>& env) {
+  env.episode += 1;
+#pragma unroll
+  for (int b = 0; b < M; ++b) {
+    const DevBody<R>& body = sc.bodies[b];
+    R st[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) st[c] = body.init[c];
+    if (init) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) st[c] = init[((int64_t)b * 4 + c) * buf.n + e];
+    } else if ((body.flags & CAV_FLAG_SPAWN) && body.spawn_id >= 0) {
+      double u[5];
+      if (buf.spawn_override) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) u[c] = buf.spawn_override[((int64_t)b * 5 + c) * buf.n + e];
+      } else {
+        double w[2];
+        const uint64_t g = (uint64_t)(buf.shard + e);
+        draw_block(buf.seed, g, b, KIND_SPAWN0, (uint32_t)env.episode, 0u, w); u[0] = w[0]; u[1] = w[1];
+        draw_block(buf.seed, g, b, KIND_SPAWN1, (uint32_t)env.episode, 0u, w); u[2] = w[0]; u[3] = w[1];
+        draw_block(buf.seed, g, b, KIND_SPAWN2, (uint32_t)env.episode, 0u, w); u[4] = w[0];
+      }
+      spawn_body(buf.spawns[body.spawn_id], u, st);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) env.s[b][c] = st[c];
+    env.held[b][0] = R(0); env.held[b][1] = R(0);
+#pragma unroll
+    for (int w = 0; w < CAV_AGENT_WORDS; ++w) env.ag[b][w] = nan_<R>();
+    buf.liveness[(int64_t)b * buf.n + e] = 0;
+  }
+  env.t_ep = 0;
+  env.done = 0;
+  env.winner = -1;
+  env.ag_dirty = 0xFFFFFFFFu;  // everything must be written back
+}
+
+}  // namespace cav

@@ -1,0 +1,232 @@
+"""BatchedCAVEnv — tensor API over N parallel CAV-Gym environments on one B200.
+
+Host side of the drop-in boundary: the same constructor vocabulary as the reference's
+`CAVEnv(bodies, constants, env_config, np_random)` (library/environment.py:59) plus
+`num_envs / device / dtype / agents`; `reset()` / `step(actions)` exchange torch tensors in the
+engine's SoA layout ([M, 4, N] state, [M, 2, N] actions, [M, N] reward, [N] done / winner).
+PyTorch is only plumbing here (device memory, streams); every transition runs in the
+hand-written CUDA kernels behind the C-ABI of include/cavgym.h, called through ctypes.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi, _native
+from .scenario import AgentSpec, compile_scenario
+
+_DTYPES = {"float64": (_abi.CAV_F64, torch.float64), "float32": (_abi.CAV_F32, torch.float32),
+           torch.float64: (_abi.CAV_F64, torch.float64), torch.float32: (_abi.CAV_F32, torch.float32)}
+
+
+class _DeviceArray:
+    """Exposes an engine-owned device buffer through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner
+
+
+def _ptr(tensor):
+    return None if tensor is None else C.c_void_p(tensor.data_ptr())
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("cavgym_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"cavgym_b200 runs on CUDA devices only, not {device}")
+    return torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+
+
+class BatchedCAVEnv:
+    def __init__(self, bodies, constants, env_config, num_envs=1, agents=None, device=None, dtype="float64", seed=0,
+                 env_offset=0, compiled=None):
+        self._lib = _native.load()
+        self.device = _require_cuda(device)
+        self.code, self.dtype = _DTYPES[dtype]
+        self.bodies, self.constants, self.env_config = bodies, constants, env_config
+        self.compiled = compiled if compiled is not None else compile_scenario(bodies, constants, env_config, agents)
+        self.num_envs, self.num_bodies = int(num_envs), self.compiled.n_bodies
+        self.frequency = 60
+        self.time_resolution = 1.0 / self.frequency
+        self._handle = C.c_void_p()
+        _native.check(self._lib.cavgym_create(self.compiled.pointer(), self.num_envs, self.code, self.device.index,
+                                              int(seed), C.byref(self._handle)))
+        if env_offset:
+            _native.check(self._lib.cavgym_set_shard(self._handle, int(env_offset)))
+        n, m = self.num_envs, self.num_bodies
+        real = "<f8" if self.code == _abi.CAV_F64 else "<f4"
+        self.state = self._view(self._lib.cavgym_state_ptr, (m, 4, n), real)
+        self.actions_taken = self._view(self._lib.cavgym_action_ptr, (m, 2, n), real)
+        self.agent_state = self._view(self._lib.cavgym_agent_state_ptr, (m, _abi.CAV_AGENT_WORDS, n), real)
+        self.episode_liveness = self._view(self._lib.cavgym_liveness_ptr, (m, n), "<i4")
+        self.timestep = self._view(self._lib.cavgym_timestep_ptr, (n,), "<i4")
+        self.done_latch = self._view(self._lib.cavgym_done_ptr, (n,), "|u1")
+        self.winner_latch = self._view(self._lib.cavgym_winner_ptr, (n,), "<i4")
+        self.error = self._view(self._lib.cavgym_error_ptr, (n,), "|u1")
+        self.reward = torch.zeros((m, n), dtype=self.dtype, device=self.device)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        self.winner = torch.full((n,), -1, dtype=torch.int32, device=self.device)
+        self.tangent = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        self._keep = {}
+
+    # ---- plumbing ----------------------------------------------------------------------
+    def _view(self, getter, shape, typestr):
+        return torch.as_tensor(_DeviceArray(getter(self._handle), shape, typestr, self), device=self.device)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _as_real(self, value, shape, name):
+        if value is None:
+            return None
+        tensor = torch.as_tensor(value, dtype=self.dtype, device=self.device).contiguous()
+        if tuple(tensor.shape) != tuple(shape):
+            raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(tensor.shape)}")
+        return tensor
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.cavgym_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- reference protocol, batched ------------------------------------------------------
+    def reset(self, mask=None, init_state=None):
+        """CAVEnv.reset for the envs selected by `mask` (all when None).  `init_state` [M,4,N] replays
+        given initial states instead of drawing SpawnPedestrians on the device."""
+        n, m = self.num_envs, self.num_bodies
+        mask_t = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        init_t = self._as_real(init_state, (m, 4, n), "init_state")
+        _native.check(self._lib.cavgym_reset(self._handle, _ptr(mask_t), _ptr(init_t), self._stream()))
+        return self.state
+
+    def step(self, actions=None, copy_state=None):
+        """CAVEnv.step over all envs.  Returns (state, reward, done, winner, tangent) tensors; `state` is the
+        engine's own buffer (zero copy) unless `copy_state` is a [M,4,N] tensor to receive a snapshot."""
+        n, m = self.num_envs, self.num_bodies
+        actions_t = self._as_real(actions, (m, 2, n), "actions")
+        _native.check(self._lib.cavgym_step(self._handle, _ptr(actions_t), _ptr(copy_state), _ptr(self.reward), _ptr(self.done),
+                                            _ptr(self.winner), _ptr(self.tangent), self._stream()))
+        return (self.state if copy_state is None else copy_state), self.reward, self.done, self.winner, self.tangent
+
+    def rollout(self, n_steps, auto_reset=True):
+        """Simulation.run's timestep loop with the on-device agents: n_steps fused transitions per launch."""
+        _native.check(self._lib.cavgym_rollout(self._handle, int(n_steps), int(bool(auto_reset)), self._stream()))
+
+    def replay(self, actions, record=("state", "reward", "done", "winner", "tangent")):
+        """Replay joint actions [T,M,2,N] in one launch; returns the recorded trajectories as a dict."""
+        n, m = self.num_envs, self.num_bodies
+        actions_t = torch.as_tensor(actions, dtype=self.dtype, device=self.device).contiguous()
+        t = actions_t.shape[0]
+        if tuple(actions_t.shape) != (t, m, 2, n):
+            raise ValueError(f"actions must have shape (T, {m}, 2, {n})")
+        out = {
+            "state": torch.empty((t, m, 4, n), dtype=self.dtype, device=self.device) if "state" in record else None,
+            "reward": torch.empty((t, m, n), dtype=self.dtype, device=self.device) if "reward" in record else None,
+            "done": torch.empty((t, n), dtype=torch.uint8, device=self.device) if "done" in record else None,
+            "winner": torch.empty((t, n), dtype=torch.int32, device=self.device) if "winner" in record else None,
+            "tangent": torch.empty((t, n), dtype=torch.uint8, device=self.device) if "tangent" in record else None,
+        }
+        _native.check(self._lib.cavgym_replay(self._handle, t, _ptr(actions_t), _ptr(out["state"]), _ptr(out["reward"]),
+                                              _ptr(out["done"]), _ptr(out["winner"]), _ptr(out["tangent"]), self._stream()))
+        return out
+
+    def step_host(self, actions, state_out=None, reward_out=None, done_out=None, winner_out=None, tangent_out=None):
+        """cavgym_step_host: numpy (ideally pinned) host buffers in and out, copies pipelined with the kernel."""
+        def hp(a):
+            return None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
+        _native.check(self._lib.cavgym_step_host(self._handle, hp(actions), hp(state_out), hp(reward_out), hp(done_out),
+                                                 hp(winner_out), hp(tangent_out)))
+
+    # ---- accounting and knobs ------------------------------------------------------------
+    def stats(self):
+        out = (C.c_int64 * _abi.CAV_N_STATS)()
+        _native.check(self._lib.cavgym_stats(self._handle, out))
+        return dict(zip(_abi.STAT_NAMES, [int(v) for v in out]))
+
+    def launch_count(self):
+        out = C.c_int64()
+        _native.check(self._lib.cavgym_launch_count(self._handle, C.byref(out)))
+        return int(out.value)
+
+    def set_global_timestep(self, t):
+        _native.check(self._lib.cavgym_set_global_timestep(self._handle, int(t)))
+
+    def set_tangent_tolerance(self, tau):
+        _native.check(self._lib.cavgym_set_tangent_tolerance(self._handle, float(tau)))
+
+    def set_action_logging(self, enabled=True):
+        _native.check(self._lib.cavgym_set_action_logging(self._handle, int(bool(enabled))))
+
+    def set_uniform_override(self, uniforms):
+        self._keep["uniforms"] = None if uniforms is None else torch.as_tensor(
+            uniforms, dtype=torch.float64, device=self.device).contiguous()
+        _native.check(self._lib.cavgym_set_uniform_override(self._handle, _ptr(self._keep["uniforms"])))
+
+    def set_spawn_override(self, draws):
+        self._keep["spawn"] = None if draws is None else torch.as_tensor(draws, dtype=torch.float64, device=self.device).contiguous()
+        _native.check(self._lib.cavgym_set_spawn_override(self._handle, _ptr(self._keep["spawn"])))
+
+    # ---- single-environment helpers for the compat view (library/environment.py) ----------------
+    def reset_to(self, rows):
+        init = torch.tensor(rows, dtype=self.dtype).reshape(self.num_bodies, 4, 1).expand(-1, -1, self.num_envs)
+        self.reset(init_state=init.contiguous())
+
+    def step_single(self, joint_action):
+        rows = [[float(a[0]), float(a[1])] if isinstance(a, (list, tuple, np.ndarray)) else [float(int(a)), 0.0] for a in joint_action]
+        actions = torch.tensor(rows, dtype=self.dtype).reshape(self.num_bodies, 2, 1)
+        state, reward, done, winner, _ = self.step(actions)
+        packed = torch.cat([state[:, :, 0].reshape(-1).double(), reward[:, 0].double(), done[:1].double(), winner[:1].double(),
+                            self.episode_liveness[:, 0].double()]).cpu().tolist()
+        m = self.num_bodies
+        state_rows = [packed[4 * b:4 * b + 4] for b in range(m)]
+        rewards = packed[4 * m:5 * m]
+        done_flag, winner_index = bool(packed[5 * m]), int(packed[5 * m + 1])
+        liveness = [int(v) for v in packed[5 * m + 2:6 * m + 2]]
+        taken = [[r[0], 0.0 if abs(r[1]) < 0.0000000000001 else r[1]] for r in rows]
+        return state_rows, rewards, done_flag, winner_index, liveness, taken
+
+
+def bodies_step(constants, states, actions, time_resolution, dtype="float64", device=None):
+    """DynamicBody.step (reference library/bodies.py:214-275) for a list of independent bodies of one type,
+    run by the stand-alone CUDA kinematics kernel.  states [n][4], actions [n][2] -> new states [n][4]."""
+    lib = _native.load()
+    device = _require_cuda(device)
+    code, tdtype = _DTYPES[dtype]
+    state_t = torch.tensor(states, dtype=tdtype, device=device).t().contiguous()
+    action_t = torch.tensor(actions, dtype=tdtype, device=device).t().contiguous()
+    k = _abi.CavBodyType(*[float(v) for v in (constants.length, constants.width, constants.wheelbase, constants.min_velocity,
+                                               constants.max_velocity, constants.min_throttle, constants.max_throttle,
+                                               constants.min_steering_angle, constants.max_steering_angle)])
+    with torch.cuda.device(device):
+        _native.check(lib.cavgym_bodies_step(C.byref(k), _ptr(state_t), _ptr(action_t), state_t.shape[1], float(time_resolution),
+                                             code, C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+    return state_t.t().cpu().tolist()
+
+
+def geometry_probe(quads_a, quads_b, dtype="float64", device=None):
+    """Shape.intersects / contains / percentage_intersects (reference library/geometry.py:74-87) on n quad pairs,
+    run by the CUDA geometry code.  quads [n][4][2] -> array [n][4]: intersects, b.contains(a), share, tangent."""
+    lib = _native.load()
+    device = _require_cuda(device)
+    code, tdtype = _DTYPES[dtype]
+
+    def pack(quads):
+        arr = np.asarray(quads, dtype=np.float64)  # [n, 4, 2]
+        return torch.tensor(np.concatenate([arr[:, :, 0].T, arr[:, :, 1].T], axis=0), dtype=tdtype, device=device).contiguous()
+
+    a, b = pack(quads_a), pack(quads_b)
+    out = torch.empty((4, a.shape[1]), dtype=tdtype, device=device)
+    with torch.cuda.device(device):
+        _native.check(lib.cavgym_geometry_probe(_ptr(a), _ptr(b), _ptr(out), a.shape[1], code,
+                                                C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+    return out.t().double().cpu().numpy()

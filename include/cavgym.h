@@ -211,6 +211,10 @@ int cavgym_set_uniform_override(CavEngine* engine, const double* uniforms);
  * SpawnPedestrian by caller-provided [0,1) numbers: device f64[M][5][N], NULL restores Philox. */
 int cavgym_set_spawn_override(CavEngine* engine, const double* draws);
 
+/* cavgym_action_ptr normally holds only what a RandomAgent must remember; with logging on,
+ * every on-device agent's chosen action is stored there each step (parity tests, compat view). */
+int cavgym_set_action_logging(CavEngine* engine, int enabled);
+
 /* CAVEnv.current_timestep (environment.py:90,222) is never reset by the reference;
  * the engine keeps ONE counter of step calls for the whole batch. */
 int cavgym_set_global_timestep(CavEngine* engine, int64_t t);

@@ -1,0 +1,155 @@
+"""CUDA engine vs the reference traces and vs the CPU oracle on replayed joint actions (through the C-ABI).
+
+Bar (north star): body state within 1e-9 relative in fp64 mode and 1e-4 in fp32 mode; done-step, winner and
+liveness identical except on steps the engine flags as near-tangent.
+"""
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_CASES, compile_from_meta, load_golden, soa
+
+pytestmark = pytest.mark.gpu
+
+REL = {"float64": 1e-9, "float32": 1e-4}
+
+
+def rel_err(got, want):
+    return float(np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want)))) if got.size else 0.0
+
+
+def make_env(meta, n, dtype, mode="external", **kw):
+    from cavgym_b200 import BatchedCAVEnv
+    comp = compile_from_meta(meta, mode=mode)
+    return BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=comp, **kw)
+
+
+def check_episode(traj, ep, col, dtype, liveness=None):
+    """Compare one env column of a recorded trajectory with a golden episode; returns #flagged steps."""
+    t_len = ep["actions"].shape[0]
+    state = traj["state"][:t_len, :, :, col]
+    reward = traj["reward"][:t_len, :, col]
+    done = traj["done"][:t_len, col]
+    winner = traj["winner"][:t_len, col]
+    tangent = traj["tangent"][:t_len, col].astype(bool)
+    mismatch = (done != ep["done"]) | (winner != ep["winner"])
+    assert not np.any(mismatch & ~tangent), f"unflagged event mismatch at steps {np.nonzero(mismatch & ~tangent)[0][:5]}"
+    if np.any(mismatch):  # a flagged near-tangent divergence: compare only up to it
+        t_len = int(np.nonzero(mismatch)[0][0])
+    assert rel_err(state[:t_len], ep["state"][:t_len]) < REL[dtype]
+    reward_tol = 1e-9 if dtype == "float64" else 2e-3  # terminal rewards are +-6000: relative to max(1,|r|)
+    assert rel_err(reward[:t_len], ep["reward"][:t_len]) < reward_tol
+    if liveness is not None and not np.any(mismatch):
+        want = ep["liveness"][-1]
+        if dtype == "float64":
+            assert np.array_equal(liveness, want) or tangent.any()
+    return int(tangent.sum())
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_step_by_step_matches_reference_fp64(name):
+    """cavgym_step once per timestep, one env per golden episode (ragged lengths, zero-padded actions)."""
+    import torch
+    meta, episodes = load_golden(name)
+    n, m = len(episodes), meta["n_bodies"]
+    t_max = max(ep["actions"].shape[0] for ep in episodes)
+    env = make_env(meta, n, "float64")
+    init = np.stack([ep["init_state"] for ep in episodes])           # [N, M, 4]
+    env.reset(init_state=soa(init))
+    actions = np.zeros((t_max, m, 2, n))
+    for e, ep in enumerate(episodes):
+        actions[:ep["actions"].shape[0], :, :, e] = ep["actions"]
+    # CAVEnv.current_timestep is per env object in the reference; replay each episode's own counter via the
+    # engine-wide counter only when all episodes share it, else check the time-out reward separately below.
+    starts = {int(ep["t_global_start"]) for ep in episodes}
+    traj = {k: [] for k in ("state", "reward", "done", "winner", "tangent")}
+    single_start = len(starts) == 1
+    env.set_global_timestep(starts.pop() if single_start else -10 ** 9)
+    actions_t = torch.tensor(actions, device=env.device)
+    for t in range(t_max):
+        state, reward, done, winner, tangent = env.step(actions_t[t])
+        for k, v in zip(traj, (state, reward, done, winner, tangent)):
+            traj[k].append(v.cpu().numpy().copy())
+    traj = {k: np.stack(v) for k, v in traj.items()}
+    live = env.episode_liveness.cpu().numpy()
+    for e, ep in enumerate(episodes):
+        want = dict(ep)
+        if not single_start:  # remove the one-off time-out reward the reference adds at global step max_timesteps-1
+            t_hit = meta["config"]["max_timesteps"] - 1 - int(ep["t_global_start"])
+            if 0 <= t_hit < ep["reward"].shape[0] and not ep["done"][t_hit]:
+                want["reward"] = ep["reward"].copy()
+                want["reward"][t_hit] -= meta["config"]["reward_draw"]
+        check_episode(traj, want, e, "float64", live[:, e])
+    # frozen after the episode ended: reward 0, state unchanged
+    for e, ep in enumerate(episodes):
+        t_len = ep["actions"].shape[0]
+        if t_len < t_max and ep["done"][-1]:
+            assert np.all(traj["reward"][t_len:, :, e] == 0.0)
+            assert np.array_equal(traj["state"][t_len, :, :, e], traj["state"][t_len - 1, :, :, e])
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", ["pedestrians_rc_seed0", "pedestrians3_rc_seed2", "busstop_random_all_seed8",
+                                  "pelican_random_all_seed10", "crossroads_random_ego_seed7"])
+def test_fused_replay_matches_reference(name, dtype):
+    """cavgym_replay (T steps in one launch) per golden episode with the reference's own time-out counter."""
+    meta, episodes = load_golden(name)
+    env = make_env(meta, 1, dtype)
+    flagged = 0
+    for ep in episodes:
+        env.reset(init_state=soa(ep["init_state"][None]))
+        env.set_global_timestep(int(ep["t_global_start"]))
+        out = env.replay(ep["actions"][..., None])
+        traj = {k: v.double().cpu().numpy() if v.dtype.is_floating_point else v.cpu().numpy() for k, v in out.items()}
+        flagged += check_episode(traj, ep, 0, dtype, env.episode_liveness.cpu().numpy()[:, 0])
+    assert flagged < sum(ep["actions"].shape[0] for ep in episodes) * (0.02 if dtype == "float64" else 0.2)
+
+
+def test_batched_replay_matches_oracle_65536_envs():
+    """BASELINE config C2 shape: 65,536 envs, env e replays golden episode e mod K; engine vs CPU oracle over the
+    whole batch (state 1e-9, events exact off flagged steps)."""
+    from oracle.oracle import Oracle
+    meta, episodes = load_golden("pedestrians_rc_seed0")
+    n, m, t_len = 65536, meta["n_bodies"], 256
+    k = len(episodes)
+    init = np.stack([episodes[e % k]["init_state"] for e in range(k)])
+    init = soa(init[np.arange(n) % k])
+    actions = np.zeros((t_len, m, 2, n))
+    for j, ep in enumerate(episodes):
+        a = ep["actions"][:t_len]
+        actions[:a.shape[0], :, :, j::k] = a[..., None]
+    env = make_env(meta, n, "float64")
+    env.reset(init_state=init)
+    out = env.replay(actions, record=("state", "done", "winner", "tangent"))
+    oracle = Oracle(compile_from_meta(meta), n, threads=8)
+    oracle.reset(init_state=init)
+    want_state, _, want_done, want_winner, _ = oracle.replay(actions)
+    got_state = out["state"].cpu().numpy()
+    assert rel_err(got_state, want_state) < 1e-9
+    tangent = out["tangent"].cpu().numpy().astype(bool)
+    mismatch = (out["done"].cpu().numpy() != want_done) | (out["winner"].cpu().numpy() != want_winner)
+    assert not np.any(mismatch & ~tangent)
+    assert np.array_equal(env.episode_liveness.cpu().numpy(), oracle.liveness)
+
+
+def test_invalid_action_sets_error_flag_and_leaves_state():
+    meta, episodes = load_golden("pedestrians_rc_seed0")
+    env = make_env(meta, 4, "float64")
+    env.reset(init_state=soa(np.stack([episodes[0]["init_state"]] * 4)))
+    before = env.state.clone()
+    actions = np.zeros((2, 2, 4))
+    actions[0, 0, 1] = 1e6          # throttle out of Box bounds (environment.py:120)
+    actions[1, 1, 3] = float("nan")
+    state, reward, done, winner, _ = env.step(actions)
+    err = env.error.cpu().numpy()
+    assert err.tolist() == [0, 1, 0, 1]
+    assert np.array_equal(state[:, :, 1].cpu().numpy(), before[:, :, 1].cpu().numpy())
+    assert not np.array_equal(state[:, :, 0].cpu().numpy(), before[:, :, 0].cpu().numpy())
+    assert env.stats()["errors"] == 2
+
+
+def test_missing_actions_is_an_error():
+    from cavgym_b200._native import CavgymError
+    meta, _ = load_golden("pedestrians_rc_seed0")
+    env = make_env(meta, 2, "float64")
+    with pytest.raises(CavgymError):
+        env.step(None)
