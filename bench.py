@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the CAV-Gym stepping hot path on B200 (driver contract in the task prompt).
+
+    python bench.py --gpus 1 --steps 1000 --warmup 100             # our arm
+    python bench.py --impl reference --gpus 1 --steps 200 --warmup 10   # CPU arm (oracle port, all host threads)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "C2"): the stock pedestrians scenario (Car + SpawnPedestrian) batched to
+65,536 parallel envs per GPU, replayed joint actions, fp64.  A "step" is one CAVEnv.step over the whole batch.
+The joint actions are synthetic: a RandomConstrainedAgent(eps=0.01) trace generated ON DEVICE before the timed
+region (untimed) for every env, then replayed.  `value` counts only LIVE env-steps (frozen, finished envs do not
+count), inputs resident in HBM, trajectories (state, reward, done, winner, tangent) recorded to HBM slabs larger
+than L2.  `e2e` is the same metric through cavgym_step_host with pinned HOST buffers (H2D actions, D2H results
+inside the timed region).  `hbm_config` repeats the per-step kernel at 4,194,304 envs, where the working set is
+far beyond L2, for the HBM-roofline fraction (do not call the 65,536-env figure an HBM fraction).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_ENVS = 65536          # per GPU (weak scaling)
+SEGMENT = 500           # steps replayed from a fresh reset before resetting again (ego finishes at step 901)
+CHUNK = 50              # steps fused per cavgym_replay launch
+HBM_ENVS = 4 * 1024 * 1024
+EPSILON = 0.01
+BYTES_PER_BODY_STEP = {"float64": 88, "float32": 44}   # 4w state in + 2w action + 4w state out + 1w reward
+BYTES_PER_ENV_STEP_EXTRA = 5                            # 1 B done + 4 B winner
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            names = {pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self._halt.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.reasons.update(name for bit, name in names.items() if mask & bit)
+                time.sleep(0.02)
+        except Exception as exc:  # NVML missing: report nothing rather than guess
+            self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        samples = sorted(self.samples)
+        return {"sm_mhz": samples[len(samples) // 2] if samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def scenario(mode):
+    from helpers import compile_from_meta, load_golden
+    meta, _ = load_golden("pedestrians_rc_seed0")   # the stock config.json scenario (ego noop, tester random-constrained)
+    meta["config"]["tester_config"]["epsilon"] = EPSILON
+    return compile_from_meta(meta, mode=mode)
+
+
+def make_trace(torch, device, n_envs, n_steps, dtype, env_offset):
+    """Untimed set-up: run the on-device agents once and log every joint action -> (init_state, actions[T,M,2,N])."""
+    from cavgym_b200 import BatchedCAVEnv
+    gen = BatchedCAVEnv(None, None, None, num_envs=n_envs, dtype=dtype, compiled=scenario("device"), device=device, seed=0,
+                        env_offset=env_offset)
+    gen.set_action_logging(True)
+    gen.reset()
+    init = gen.state.clone()
+    actions = torch.empty((n_steps, gen.num_bodies, 2, n_envs), dtype=gen.dtype, device=device)
+    for t in range(n_steps):
+        gen.step(None)
+        actions[t].copy_(gen.actions_taken)
+    torch.cuda.synchronize(device)
+    gen.close()
+    return init, actions
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cavgym_b200 import BatchedCAVEnv
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    dtype, n, m = args.dtype, N_ENVS, 2
+    bytes_env_step = m * BYTES_PER_BODY_STEP[dtype] + BYTES_PER_ENV_STEP_EXTRA
+    peak_gbs, peak_src = peaks()
+
+    init, actions = make_trace(torch, device, n, SEGMENT, dtype, env_offset=rank * n)
+    env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=scenario("external"), device=device,
+                        env_offset=rank * n)
+    slab = {"state": torch.empty((CHUNK, m, 4, n), dtype=env.dtype, device=device),
+            "reward": torch.empty((CHUNK, m, n), dtype=env.dtype, device=device),
+            "done": torch.empty((CHUNK, n), dtype=torch.uint8, device=device),
+            "winner": torch.empty((CHUNK, n), dtype=torch.int32, device=device),
+            "tangent": torch.empty((CHUNK, n), dtype=torch.uint8, device=device)}
+    lib, handle, stream = env._lib, env._handle, env._stream()
+    from cavgym_b200._native import check
+    import ctypes as C
+
+    def ptr(t):
+        return C.c_void_p(t.data_ptr())
+
+    kernel_events = []
+
+    def advance(n_steps, cursor, timed):
+        """Replay n_steps starting at trace position `cursor` (resetting every SEGMENT steps); returns new cursor."""
+        done = 0
+        while done < n_steps:
+            if cursor == 0:
+                env.reset(init_state=init)
+            take = min(CHUNK, n_steps - done, SEGMENT - cursor)
+            if timed:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            check(lib.cavgym_replay(handle, take, ptr(actions[cursor]), ptr(slab["state"]), ptr(slab["reward"]),
+                                    ptr(slab["done"]), ptr(slab["winner"]), ptr(slab["tangent"]), stream))
+            if timed:
+                b.record()
+                kernel_events.append((a, b, take))
+            done += take
+            cursor = (cursor + take) % SEGMENT
+        return cursor
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- device-resident throughput (value) -------------------------------------------------
+    cursor = advance(args.warmup, 0, False)
+    barrier()
+    before, launches_before = env.stats(), env.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    cursor = advance(args.steps, cursor, True)
+    stop.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = start.elapsed_time(stop)
+    after, launches_after = env.stats(), env.launch_count()
+    live_env_steps = after["env_steps"] - before["env_steps"]
+    # stats() itself launches one reduction kernel per call: not part of the timed region
+    gpu_launches = launches_after - launches_before - 1
+    kernel_ms = sum(a.elapsed_time(b) for a, b, _ in kernel_events)
+    kernel_steps = sum(k for _, _, k in kernel_events)
+    replay_launches = len(kernel_events)
+
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+    total = torch.tensor([float(live_env_steps)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    elapsed_ms, total_env_steps = float(t.item()), float(total.item())
+    value = total_env_steps / (elapsed_ms * 1e-3)
+
+    # roofline of the dominant kernel (replay_kernel): algorithmic bytes per launch / mean launch duration
+    live_fraction = live_env_steps / float(n * args.steps)
+    bytes_per_launch = bytes_env_step * n * (kernel_steps / replay_launches) * live_fraction
+    achieved = bytes_per_launch / (kernel_ms / replay_launches * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"replay_kernel<{'double' if dtype == 'float64' else 'float'},2>",
+                "achieved": round(achieved, 1), "peak": peak_gbs, "peak_source": peak_src, "unit": "GB/s",
+                "frac": round(achieved / peak_gbs, 4), "traffic": None,
+                "algorithmic_bytes_per_env_step": bytes_env_step, "launches": replay_launches,
+                "avg_launch_ms": round(kernel_ms / replay_launches, 4),
+                "note": "65,536 envs: state (4 MiB) stays in L2/registers, only actions and trajectories stream"}
+
+    out = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic",
+           "body_steps_per_sec": value * m,
+           "config": {"workload": "C2: pedestrians scenario (Car + SpawnPedestrian) x 65,536 envs per GPU, replayed joint "
+                                  "actions (on-device RandomConstrained eps=0.01 trace), cavgym_replay 50 steps/launch, "
+                                  "trajectories recorded", "envs_per_gpu": n, "bodies": m, "segment": SEGMENT,
+                      "l2": "trajectory slabs (262 MB) and action trace (1 GB) exceed L2; state is L2/register resident",
+                      "live_fraction": round(live_fraction, 4)},
+           "roofline": roofline, "gpu_launches": int(gpu_launches), "clocks": clocks}
+
+    if rank == 0 or world > 1:
+        # ---- end to end through the host-buffer API (every rank; max over ranks) -------------
+        e2e_steps = max(3, min(args.steps, args.e2e_steps))
+        np_dtype = "float64" if dtype == "float64" else "float32"
+        import numpy as np
+        h_actions = torch.empty((SEGMENT, m, 2, n), dtype=env.dtype).pin_memory()
+        h_actions.copy_(actions)
+        h_state = torch.empty((m, 4, n), dtype=env.dtype).pin_memory()
+        h_reward = torch.empty((m, n), dtype=env.dtype).pin_memory()
+        h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+        h_winner = torch.empty(n, dtype=torch.int32).pin_memory()
+        h_tangent = torch.empty(n, dtype=torch.uint8).pin_memory()
+        env.reset(init_state=init)
+        for t_ in range(3):
+            env.step_host(h_actions[t_], h_state, h_reward, h_done, h_winner, h_tangent)
+        barrier()
+        s0 = env.stats()
+        t0 = time.perf_counter()
+        for t_ in range(e2e_steps):
+            env.step_host(h_actions[3 + t_], h_state, h_reward, h_done, h_winner, h_tangent)
+        torch.cuda.synchronize(device)
+        e2e_s = time.perf_counter() - t0
+        s1 = env.stats()
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        tot = torch.tensor([float(s1["env_steps"] - s0["env_steps"])], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        rs = 8 if dtype == "float64" else 4
+        out["e2e"] = {"value": float(tot.item()) / float(tt.item()), "unit": "env-steps/s",
+                      "h2d_bytes_per_step": m * 2 * n * rs, "d2h_bytes_per_step": m * 4 * n * rs + m * n * rs + n * 6,
+                      "steps": e2e_steps, "api": "cavgym_step_host (pinned host buffers, 8 env-chunks over 3 streams)"}
+
+    # ---- episode statistics: the single NCCL reduce over NVLink ---------------------
+    stats = env.stats()
+    vec = torch.tensor([stats[k] for k in ("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2",
+                                           "env_steps", "body_steps", "tangent", "errors")], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+    out["episode_stats"] = dict(zip(("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2", "env_steps",
+                                     "body_steps", "tangent", "errors"), [int(v) for v in vec.tolist()]))
+    env.close()
+
+    if rank == 0:
+        if not args.skip_hbm:
+            out["hbm_config"] = hbm_config(torch, device, dtype, peak_gbs)
+        if not args.skip_cpu:
+            out["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_seconds)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def hbm_config(torch, device, dtype, peak_gbs):
+    """The per-step kernel (cavgym_step) at 4,194,304 envs: 268 MB of state, 0.77 GB algorithmic bytes per launch."""
+    from cavgym_b200 import BatchedCAVEnv
+    n, m, t_len = HBM_ENVS, 2, 6
+    init, actions = make_trace(torch, device, n, t_len, dtype, env_offset=0)
+    env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=scenario("external"), device=device)
+    env.reset(init_state=init)
+    for t in range(3):
+        env.step(actions[t])
+    torch.cuda.synchronize(device)
+    times = []
+    for rep in range(5):
+        for t in range(t_len):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            env.step(actions[t])
+            b.record()
+            times.append((a, b))
+    torch.cuda.synchronize(device)
+    ms = sorted(a.elapsed_time(b) for a, b in times)
+    mean_ms = sum(ms) / len(ms)
+    bytes_launch = n * (m * BYTES_PER_BODY_STEP[dtype] + BYTES_PER_ENV_STEP_EXTRA)
+    achieved = bytes_launch / (mean_ms * 1e-3) / 1e9
+    env.close()
+    return {"workload": "pedestrians x 4,194,304 envs, cavgym_step (one launch per step), replayed actions, working set >> L2",
+            "kernel": f"step_kernel<{'double' if dtype == 'float64' else 'float'},2,false>", "envs": n,
+            "env_steps_per_sec": n / (mean_ms * 1e-3), "body_steps_per_sec": n * m / (mean_ms * 1e-3),
+            "avg_launch_ms": round(mean_ms, 4), "min_launch_ms": round(ms[0], 4), "algorithmic_bytes_per_launch": bytes_launch,
+            "achieved_gbs": round(achieved, 1), "peak_gbs": peak_gbs, "frac": round(achieved / peak_gbs, 4)}
+
+
+def oracle_trace(n_envs, n_steps, threads):
+    """Joint-action trace for the CPU arm, produced by the oracle's own RandomConstrained agents (untimed)."""
+    import numpy as np
+    from oracle.oracle import Oracle
+    gen = Oracle(scenario("device"), n_envs, seed=0, threads=threads)
+    gen.reset()
+    init = gen.state.copy()
+    actions = np.empty((n_steps, 2, 2, n_envs))
+    for t in range(n_steps):
+        gen.step(None)
+        actions[t] = gen.actions_taken
+    gen.close()
+    return init, actions
+
+
+def cpu_baseline(budget_s=15.0, threads=None):
+    """The oracle port of the reference's step timed on this host's cores, on a bounded sample of the C2 workload."""
+    from oracle.oracle import Oracle
+    threads = threads or os.cpu_count() or 1
+    n, t_len = 8192, 100
+    init, actions = oracle_trace(n, t_len, threads)
+    results = {}
+    for label, nt in (("all", threads), ("one", 1)):
+        sim = Oracle(scenario("external"), n, threads=nt)
+        sim.reset(init_state=init)
+        sim.replay(actions[:5], outputs=False)
+        steps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget_s / 2 and steps + 5 < t_len:
+            take = min(10 if nt > 1 else 2, t_len - 5 - steps)
+            sim.replay(actions[5 + steps:5 + steps + take], outputs=True)
+            steps += take
+        results[label] = n * steps / (time.perf_counter() - t0)
+        sim.close()
+    return {"value": results["all"], "unit": "env-steps/s", "cores": threads, "kind": "port",
+            "single_thread_value": results["one"],
+            "sample": f"{n} envs of the C2 scenario, replayed joint actions, oracle/cavgym_oracle.c (exact predicates), "
+                      f"~{budget_s:.0f} s of CPU work",
+            "note": "the reference itself is Python (README.md:27: 2,557 env-steps/s with real Shapely/GEOS); the port is C"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path (oracle port; the Python reference cannot travel to the
+    GPU box and has no compiled form), all host threads, same workload / metric / unit."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle.oracle import Oracle
+    threads = os.cpu_count() or 1
+    n = N_ENVS
+    t_len = min(SEGMENT, args.warmup + args.steps)
+    init, actions = oracle_trace(n, t_len, threads)
+    sim = Oracle(scenario("external"), n, threads=threads)
+    sim.reset(init_state=init)
+    cursor = 0
+
+    def advance(k, cursor):
+        while k > 0:
+            if cursor == 0:
+                sim.reset(init_state=init)
+            take = min(k, t_len - cursor, 10)
+            sim.replay(actions[cursor:cursor + take], outputs=True)
+            cursor = (cursor + take) % t_len
+            k -= take
+        return cursor
+
+    cursor = advance(args.warmup, cursor)
+    before = sim.stats()["env_steps"]
+    t0 = time.perf_counter()
+    cursor = advance(args.steps, cursor)
+    elapsed = time.perf_counter() - t0
+    live = sim.stats()["env_steps"] - before
+    value = live / elapsed
+    print(json.dumps({
+        "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed * 1e3 / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "body_steps_per_sec": value * 2,
+        "config": {"workload": "C2: pedestrians scenario x 65,536 envs, replayed joint actions, CPU", "envs": n, "bodies": 2},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps of the full 65,536-env batch, oracle/cavgym_oracle.c on {threads} threads"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=1000)
+    parser.add_argument("--warmup", type=int, default=100)
+    parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    parser.add_argument("--dtype", default="float64", choices=["float64", "float32"])
+    parser.add_argument("--e2e-steps", type=int, default=200)
+    parser.add_argument("--cpu-seconds", type=float, default=15.0)
+    parser.add_argument("--skip-hbm", action="store_true")
+    parser.add_argument("--skip-cpu", action="store_true")
+    args = parser.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        if args.steps > 200:
+            args.steps = 200   # bounded: 200 steps of 65,536 envs is ~13 M env-steps of CPU work
+        args.warmup = min(args.warmup, 10)
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

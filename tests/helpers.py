@@ -68,3 +68,24 @@ def compile_from_meta(meta, mode="external"):
 def soa(per_env):
     """[N][M][C] -> [M][C][N] contiguous."""
     return np.ascontiguousarray(np.transpose(np.asarray(per_env), (1, 2, 0)))
+
+
+def rel_err(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    return float(np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want)))) if got.size else 0.0
+
+
+def state_err(got, want, dynamic=None):
+    """Relative error of body state [..., M, 4] (component axis last): position as a vector,
+    |dp| / max(1, |p|) (a coordinate that crosses zero has no meaningful scalar relative error), velocity
+    |dv| / max(1, |v|), orientation as an angle modulo 2*pi — atan2(sin(t), cos(t)) may land on +pi in one
+    libm and -pi in another for the same heading."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    if not got.size:
+        return 0.0
+    pos = np.hypot(got[..., 0] - want[..., 0], got[..., 1] - want[..., 1]) / np.maximum(1.0, np.hypot(want[..., 0], want[..., 1]))
+    vel = np.abs(got[..., 2] - want[..., 2]) / np.maximum(1.0, np.abs(want[..., 2]))
+    d = got[..., 3] - want[..., 3]
+    plain = np.abs(d) / np.maximum(1.0, np.abs(want[..., 3]))
+    ang = np.minimum(plain, np.abs(np.arctan2(np.sin(d), np.cos(d))) / np.maximum(1.0, np.abs(want[..., 3])))
+    return float(max(pos.max(), vel.max(), ang.max()))
