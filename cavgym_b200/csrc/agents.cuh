@@ -26,39 +26,56 @@ template <typename R> __device__ __forceinline__ R nan_() { return R(NAN); }
 // ---------------------------------------------------------------- kinematics
 // st = x, y, v, theta in/out.  On return c, s = cos/sin of the NEW orientation (what the
 // bounding box needs); `snapped` is the steering angle after the 1e-13 snap (bodies.py:217-218).
+// cos/sin of a heading: exact for 0, looked up (host libm values) for the headings bodies are created with,
+// device sincos otherwise.
 template <typename R>
-__device__ __forceinline__ void body_step(const DevType<R>& k, R st[4], R throttle, R steer, R dt, R& c, R& s, R& snapped) {
+__device__ __forceinline__ void heading_cs(const DevScenario<R>& sc, R th, R& c, R& s) {
+  if (th == R(0)) { c = R(1); s = th; return; }  // cos(+-0) = 1, sin(+-0) = +-0
+  bool hit = false;
+#pragma unroll
+  for (int i = 0; i < CAV_HEADING_CACHE; ++i) {
+    if (i < sc.hc_n && th == sc.hc_theta[i]) { c = sc.hc_cos[i]; s = sc.hc_sin[i]; hit = true; }
+  }
+  if (!hit) sincos_(th, &s, &c);
+}
+
+// c, s: cos/sin of the CURRENT heading on entry (cached in EnvBuffers::cs, refreshed only when the heading
+// changes), cos/sin of the NEW heading on return.  Returns true if the heading changed.
+template <typename R>
+__device__ __forceinline__ bool body_step(const DevType<R>& k, R st[4], R throttle, R steer, R dt, R& c, R& s, R& snapped) {
   if (rabs(steer) < R(0.0000000000001)) steer = R(0);
   snapped = steer;
   const R x = st[0], y = st[1], v = st[2], th = st[3];
   const R v1 = rmax(k.vmin, rmin(k.vmax, v + (throttle * dt)));
   const R d = v * dt;
-  if (th == R(0)) { c = R(1); s = th; }  // cos(+-0) = 1, sin(+-0) = +-0
-  else sincos_(th, &s, &c);
   st[2] = v1;
   if (steer == R(0)) {
     st[0] = x + d * c;
     st[1] = y + d * s;
-  } else {
-    const R wbo = k.wheelbase / R(2);
-    const R rx = x - wbo * c, ry = y - wbo * s;
-    const R kk = k.wheelbase / tan_(steer);
-    const R cx = rx - kk * s, cy = ry + kk * c;
-    const R dx = x - cx, dy = y - cy;
-    const R q = d / rsqrt_(dx * dx + dy * dy);
-    const R theta = steer < R(0) ? -q : q;
-    R ct, sn;
-    sincos_(theta, &sn, &ct);
-    st[0] = cx + dx * ct - dy * sn;
-    st[1] = cy + dx * sn + dy * ct;
-    const R ot = th + theta;
-    R so, co;
-    sincos_(ot, &so, &co);
-    const R th1 = atan2_(so, co);
-    st[3] = th1;
-    if (th1 == R(0)) { c = R(1); s = th1; }
-    else sincos_(th1, &s, &c);
+    return false;
   }
+  const R wbo = k.wheelbase / R(2);
+  const R rx = x - wbo * c, ry = y - wbo * s;
+  // wheelbase / tan(steer): at full lock (what a crossing agent commands for all but the last step of a turn)
+  // the host-computed value is used, which is also the reference's own libm value
+  R kk;
+  if (steer == k.smax) kk = k.kk_smax;
+  else if (steer == k.smin) kk = k.kk_smin;
+  else kk = k.wheelbase / tan_(steer);
+  const R cx = rx - kk * s, cy = ry + kk * c;
+  const R dx = x - cx, dy = y - cy;
+  const R q = d / rsqrt_(dx * dx + dy * dy);
+  const R theta = steer < R(0) ? -q : q;
+  R ct, sn;
+  sincos_(theta, &sn, &ct);
+  st[0] = cx + dx * ct - dy * sn;
+  st[1] = cy + dx * sn + dy * ct;
+  // sin/cos(th + theta) by angle addition from the two sincos in hand (the reference evaluates sin and cos of
+  // the rounded sum; the difference is a few ulp).  They are also cos/sin of the new heading atan2(so, co).
+  const R so = s * ct + c * sn, co = c * ct - s * sn;
+  st[3] = atan2_(so, co);
+  c = co; s = so;
+  return true;
 }
 
 // ---------------------------------------------------------------- Philox4x32-10

@@ -30,12 +30,17 @@ def headers_mtime():
     return max(os.path.getmtime(p) for p in paths)
 
 
+ONLY_M = [int(v) for v in os.environ.get("CAVGYM_ONLY_M", "").split(",") if v]   # development: compile these body counts only
+EXTRA = os.environ.get("CAVGYM_NVCC_FLAGS", "").split()
+
+
 def compile_one(src, force, verbose):
-    obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+    stub = bool(ONLY_M) and src.startswith("small_m") and int(src[len("small_m"):-3]) not in ONLY_M
+    obj = os.path.join(OBJ_DIR, src[:-3] + (".stub.o" if stub else ".o"))
     src_path = os.path.join(HERE, src)
-    if not force and os.path.isfile(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src_path), headers_mtime()):
+    if not force and not EXTRA and os.path.isfile(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src_path), headers_mtime()):
         return obj, ""
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src_path, "-o", obj]
+    cmd = [NVCC] + FLAGS + EXTRA + (["-DCAV_STUB"] if stub else []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src_path, "-o", obj]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{proc.stdout}\n{proc.stderr}")
@@ -51,7 +56,7 @@ def build(force=False, jobs=None, verbose=False):
         results = list(pool.map(lambda s: compile_one(s, force, verbose), srcs))
     objs = [obj for obj, _ in results]
     logs = [log for _, log in results if log]
-    if force or not os.path.isfile(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(o) for o in objs):
+    if True:
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"]
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:

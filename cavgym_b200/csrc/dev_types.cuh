@@ -17,9 +17,13 @@ struct Quad {
   R x[4], y[4];  // rear_left, front_left, front_right, rear_right — clockwise (y up)
 };
 
+#define CAV_HEADING_CACHE 4
+
 template <typename R>
 struct DevType {
   R length, width, wheelbase, vmin, vmax, amin, amax, smin, smax;
+  R inv_2brake;  // 1 / (2 * -min_throttle): braking distance = v*v * inv_2brake (bodies.py:123)
+  R kk_smin, kk_smax;  // wheelbase / tan(steering limit), host libm: full-lock turns skip tan and one division
 };
 
 template <typename R>
@@ -52,11 +56,18 @@ struct DevScenario {
   int32_t collisions, zones, offroad;
   int64_t max_timesteps;
   R reward_win, reward_draw, cost_step, W, dt, v_maint, v_off;
+  R inv_W, inv_v_off;  // reciprocals of the two constant divisors on the always-executed path
   R tau;         // near-tangent tolerance (px)
   R target_err;  // TARGET_ERROR (dynamic_body.py:8); widened for float
   R cl[4];       // centre line start x,y end x,y
+  // Headings bodies are created with (spawn orientations, init orientations): cos/sin evaluated ON THE HOST
+  // with the C library the reference's math.cos/math.sin use, so the common straight-walking case needs no
+  // device sincos and is bit-equal to the reference.
+  int32_t hc_n, hc_pad;
+  R hc_theta[CAV_HEADING_CACHE], hc_cos[CAV_HEADING_CACHE], hc_sin[CAV_HEADING_CACHE];
   Quad<R> roads[CAV_MAX_ROADS];
   Aabb<R> road_bb[CAV_MAX_ROADS];
+  int32_t road_axis[CAV_MAX_ROADS];  // 1 if the road rectangle is exactly axis-aligned (road == its AABB)
   Quad<R> statics[CAV_MAX_STATICS];
   Aabb<R> static_bb[CAV_MAX_STATICS];
   DevBody<R> bodies[CAV_SMALL_M];
@@ -72,6 +83,7 @@ struct EnvBuffers {
   R* state;             // [M][4][N]
   R* action;            // [M][2][N] last joint action (RandomAgent's held action)
   R* agent;             // [M][5][N] crossing-agent state, NaN = None
+  R* cs;                // [M][2][N] cos/sin of each body's heading; refreshed only when the heading changes
   int32_t* liveness;    // [M][N]
   int32_t* t_ep;        // [N]
   int32_t* episode;     // [N]

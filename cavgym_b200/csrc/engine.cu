@@ -81,7 +81,8 @@ static Aabb<R> host_aabb(const Quad<R>& q) {
 template <typename R>
 static DevType<R> to_type(const CavBodyType& t) {
   return {(R)t.length, (R)t.width, (R)t.wheelbase, (R)t.min_velocity, (R)t.max_velocity, (R)t.min_throttle,
-          (R)t.max_throttle, (R)t.min_steering_angle, (R)t.max_steering_angle};
+          (R)t.max_throttle, (R)t.min_steering_angle, (R)t.max_steering_angle, (R)(1.0 / (2.0 * -t.min_throttle)),
+          (R)(t.wheelbase / std::tan((double)(R)t.min_steering_angle)), (R)(t.wheelbase / std::tan((double)(R)t.max_steering_angle))};
 }
 
 template <typename R>
@@ -94,10 +95,19 @@ static void convert(const CavScenario& in, double tau, DevScenario<R>& out) {
   out.reward_win = (R)in.reward_win; out.reward_draw = (R)in.reward_draw; out.cost_step = (R)in.cost_step;
   out.W = (R)in.viewer_width; out.dt = (R)in.time_resolution;
   out.v_maint = (R)in.ego_maintenance_velocity; out.v_off = (R)in.ego_max_velocity_offset;
+  out.inv_W = (R)(1.0 / in.viewer_width); out.inv_v_off = (R)(1.0 / in.ego_max_velocity_offset);
   out.tau = (R)tau;
   out.target_err = sizeof(R) == 8 ? (R)0.000000000000001 : (R)1e-6;  // dynamic_body.py:8; one float ulp at pi/2 is 1.2e-7
   for (int i = 0; i < 4; ++i) out.cl[i] = (R)in.centre_line[i];
-  for (int i = 0; i < in.n_roads; ++i) { out.roads[i] = to_quad<R>(in.roads[i]); out.road_bb[i] = host_aabb(out.roads[i]); }
+  for (int i = 0; i < in.n_roads; ++i) {
+    out.roads[i] = to_quad<R>(in.roads[i]);
+    out.road_bb[i] = host_aabb(out.roads[i]);
+    bool axis = true;  // every corner lies on a corner of the AABB
+    for (int c = 0; c < 4; ++c)
+      axis = axis && (out.roads[i].x[c] == out.road_bb[i].x0 || out.roads[i].x[c] == out.road_bb[i].x1) &&
+             (out.roads[i].y[c] == out.road_bb[i].y0 || out.roads[i].y[c] == out.road_bb[i].y1);
+    out.road_axis[i] = axis ? 1 : 0;
+  }
   for (int i = 0; i < in.n_statics; ++i) { out.statics[i] = to_quad<R>(in.statics[i]); out.static_bb[i] = host_aabb(out.statics[i]); }
   for (int b = 0; b < in.n_bodies && b < CAV_SMALL_M; ++b) {
     const CavBody& src = in.bodies[b];
@@ -108,6 +118,20 @@ static void convert(const CavScenario& in, double tau, DevScenario<R>& out) {
     if (src.kind == CAV_BODY_DYNAMIC) dst.k = to_type<R>(in.types[src.type_id]);
     dst.sbox = to_quad<R>(src.static_box);
   }
+  // heading cache: orientations bodies start with, cos/sin from the host C library (what math.cos/math.sin call)
+  auto remember = [&out](double theta) {
+    const R th = (R)theta;
+    if (th == (R)0 || out.hc_n >= CAV_HEADING_CACHE) return;
+    for (int i = 0; i < out.hc_n; ++i) if (out.hc_theta[i] == th) return;
+    out.hc_theta[out.hc_n] = th;
+    out.hc_cos[out.hc_n] = (R)std::cos((double)th);
+    out.hc_sin[out.hc_n] = (R)std::sin((double)th);
+    out.hc_n += 1;
+  };
+  for (int s = 0; s < in.n_spawns; ++s)
+    for (int i = 0; i < in.spawns[s].n_orientations; ++i) remember(in.spawns[s].orientations[i]);
+  for (int b = 0; b < in.n_bodies && b < CAV_SMALL_M; ++b)
+    if (in.bodies[b].kind == CAV_BODY_DYNAMIC) remember(in.bodies[b].init_state[3]);
 }
 
 template <typename R>
@@ -144,7 +168,8 @@ __global__ void bodies_step_kernel(const __grid_constant__ DevType<R> k, R* stat
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   R st[4] = {state[i], state[n + i], state[2 * n + i], state[3 * n + i]};
-  R c, s, snapped;
+  R c = R(1), s = st[3], snapped;
+  if (!(st[3] == R(0))) sincos_(st[3], &s, &c);
   body_step(k, st, actions[i], actions[n + i], dt, c, s, snapped);
 #pragma unroll
   for (int j = 0; j < 4; ++j) state[j * n + i] = st[j];
@@ -177,7 +202,11 @@ __global__ void geometry_probe_kernel(const R* qa, const R* qb, R* out, int64_t 
   bool inside = false;
   R share = R(0);
   if (hit) inside = contains(B, A, tau, tangent);
-  if (!(aabb_gap(aabb_of(A), aabb_of(B)) > tau)) share = percentage_intersects(A, B, tau, tangent);
+  if (!(aabb_gap(aabb_of(A), aabb_of(B)) > tau)) {
+    const Share<R> sh = percentage_intersects(A, B, tau);
+    share = sh.value;
+    tangent |= sh.tangent != 0;
+  }
   out[i] = hit ? R(1) : R(0);
   out[n + i] = inside ? R(1) : R(0);
   out[2 * n + i] = share;
@@ -233,6 +262,7 @@ static int setup_buffers(CavEngine* eng, EnvBuffers<R>& buf) {
   if ((rc = dev_alloc(eng, &buf.state, (size_t)m * 4 * n))) return rc;
   if ((rc = dev_alloc(eng, &buf.action, (size_t)m * 2 * n))) return rc;
   if ((rc = dev_alloc(eng, &buf.agent, (size_t)m * CAV_AGENT_WORDS * n))) return rc;
+  if ((rc = dev_alloc(eng, &buf.cs, (size_t)m * 2 * n))) return rc;
   if ((rc = dev_alloc(eng, &buf.liveness, (size_t)m * n))) return rc;
   if ((rc = dev_alloc(eng, &buf.t_ep, (size_t)n))) return rc;
   if ((rc = dev_alloc(eng, &buf.episode, (size_t)n))) return rc;
@@ -287,6 +317,8 @@ int cavgym_create(const CavScenario* tables, int64_t n_envs, int dtype, int devi
   if (tables->n_bodies < 1 || !tables->bodies) return fail(CAV_EINVAL, "scenario has no bodies");
   if (tables->n_bodies > CAV_SMALL_M)
     return fail(CAV_EINVAL, "more than CAV_SMALL_M bodies: the dense block-per-environment path is not built in this library");
+  if ((dtype == CAV_F64 ? (const void*)small_launchers<double>(tables->n_bodies)->step : (const void*)small_launchers<float>(tables->n_bodies)->step) == nullptr)
+    return fail(CAV_EINVAL, "this development build of the library was compiled without this body count (CAVGYM_ONLY_M)");
   if (tables->n_roads < 1 || tables->n_roads > CAV_MAX_ROADS || tables->n_statics < 0 || tables->n_statics > CAV_MAX_STATICS ||
       tables->n_types < 0 || tables->n_types > CAV_MAX_TYPES)
     return fail(CAV_EINVAL, "road/static/type counts out of range");
@@ -478,7 +510,8 @@ int cavgym_stats(CavEngine* eng, int64_t* out10) {
   CUDA_TRY(cudaMemcpy(raw, stats, sizeof(raw), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(extra, eng->d_scratch, sizeof(extra), cudaMemcpyDeviceToHost));
   for (int i = 0; i < CAV_N_STATS; ++i) out10[i] = (int64_t)raw[i];
-  out10[CAV_STAT_ENV_STEPS] = (int64_t)(raw[CAV_STAT_SUM_T] + extra[0]);  // finished episodes + episodes in flight
+  // finished episodes + episodes abandoned by a reset + episodes in flight
+  out10[CAV_STAT_ENV_STEPS] = (int64_t)(raw[CAV_STAT_SUM_T] + raw[CAV_STAT_ENV_STEPS] + extra[0]);
   out10[CAV_STAT_BODY_STEPS] = out10[CAV_STAT_ENV_STEPS] * eng->m;
   out10[CAV_STAT_ERRORS] = (int64_t)extra[1];
   return CAV_OK;

@@ -13,6 +13,17 @@
 
 namespace cav {
 
+// a / b to ~2 ulp with a float reciprocal seed and two Newton steps (10 instructions instead of the ~60 of the
+// IEEE division subroutine).  Used only for quantities that feed rewards and flagged predicates, never body state;
+// |b| must be a normal float (here: pixel distances).
+__device__ __forceinline__ double fast_div(double a, double b) {
+  double r = (double)__frcp_rn((float)b);
+  r = r * (2.0 - b * r);
+  r = r * (2.0 - b * r);
+  return a * r;
+}
+__device__ __forceinline__ float fast_div(float a, float b) { return a / b; }
+
 template <typename R> __device__ __forceinline__ R rmin(R a, R b) { return b < a ? b : a; }
 template <typename R> __device__ __forceinline__ R rmax(R a, R b) { return b > a ? b : a; }
 __device__ __forceinline__ double rsqrt_(double v) { return sqrt(v); }
@@ -36,6 +47,28 @@ __device__ __forceinline__ R aabb_gap(const Aabb<R>& a, const Aabb<R>& b) {
   return rmax(rmax(a.x0 - b.x1, b.x0 - a.x1), rmax(a.y0 - b.y1, b.y0 - a.y1));
 }
 
+// aabb_gap(a, b) > tau without the max tree: four subtractions and compares.  True means the polygons inside the
+// boxes are certainly disjoint, with a safety margin of tau >> rounding error (so no near-tangent flag is needed).
+template <typename R>
+__device__ __forceinline__ bool aabb_apart(const Aabb<R>& a, const Aabb<R>& b, R tau) {
+  return (a.x0 - b.x1 > tau) || (b.x0 - a.x1 > tau) || (a.y0 - b.y1 > tau) || (b.y0 - a.y1 > tau);
+}
+
+// AABB of make_rectangle(length, width).transform(theta, p) from the half extents |c|hl + |s|hw, |s|hl + |c|hw
+// (no corner min/max tree).  For theta == 0 it equals the corner AABB bit for bit; otherwise within a few ulp,
+// far inside the tau margin every consumer applies.
+template <typename R>
+__device__ __forceinline__ Aabb<R> box_aabb(R length, R width, R theta, R c, R s, R px, R py) {
+  const R hl = length * R(0.5), hw = width * R(0.5);
+  R ex = hl, ey = hw;
+  if (!(theta == R(0))) {
+    const R ac = rabs(c), as = rabs(s);
+    ex = ac * hl + as * hw;
+    ey = as * hl + ac * hw;
+  }
+  return {px - ex, px + ex, py - ey, py + ey};
+}
+
 // make_rectangle(length, width) . transform(theta, (px, py)); c, s = cos/sin(theta).
 // theta == 0 takes the reference's translate-only path (geometry.py:118-119) bit for bit.
 template <typename R>
@@ -56,50 +89,64 @@ __device__ __forceinline__ void make_box(R length, R width, R theta, R c, R s, R
 }
 
 // DynamicBody.stopping_zones + split_longitudinally (bodies.py:122-135, geometry.py:176-191).
+// The braking/reaction split is built directly (rectangles of length bd and rd laid end to end from the
+// front-centre anchor) instead of by interpolating with p = bd / td: algebraically identical, no division on the
+// always-executed path, corners within a few ulp of the reference's.  The oracle keeps the reference's form.
 template <typename R>
-__device__ __forceinline__ bool stopping_zones(const DevType<R>& k, R x, R y, R v, R theta, R c, R s, R steer,
-                                               Quad<R>& braking, Quad<R>& reaction) {
-  const R bd = (v * v) / (R(2) * -k.amin);
-  const R rd = v * R(0.675);
-  const R td = bd + rd;
-  if (td == R(0) || !(steer == R(0))) return false;
-  const R hx = k.length * R(0.5), hw = k.width * R(0.5);
-  R ax, ay;
-  if (theta == R(0)) { ax = x + hx; ay = y + R(0); }
-  else { ax = x + ((c * hx) - (s * R(0))); ay = y + ((s * hx) + (c * R(0))); }
-  // make_rectangle(td, width, rear_offset=0): rear = 0, front = td, left = +hw, right = -hw
-  const R lx[4] = {R(0), td, td, R(0)};
-  const R ly[4] = {hw, hw, -hw, -hw};
-  R zx[4], zy[4];
+struct ZoneFrame {
+  bool have;
+  R ax, ay, bd, td, hw;  // anchor (front centre), braking and total distance, half width
+};
+
+template <typename R>
+__device__ __forceinline__ ZoneFrame<R> zone_frame(const DevType<R>& k, R x, R y, R v, R theta, R c, R s, R steer) {
+  ZoneFrame<R> z;
+  z.bd = (v * v) * k.inv_2brake;
+  z.td = z.bd + v * R(0.675);
+  z.have = !(z.td == R(0)) && (steer == R(0));
+  const R hx = k.length * R(0.5);
+  z.hw = k.width * R(0.5);
+  if (theta == R(0)) { z.ax = x + hx; z.ay = y; }
+  else { z.ax = x + c * hx; z.ay = y + s * hx; }
+  return z;
+}
+
+// Rectangle spanning local x in [x0, x1], y in [-hw, +hw] of the zone frame, corners RL, FL, FR, RR.
+template <typename R>
+__device__ __forceinline__ void zone_quad(const ZoneFrame<R>& z, R theta, R c, R s, R x0, R x1, Quad<R>& q) {
+  const R lx[4] = {x0, x1, x1, x0};
+  const R ly[4] = {z.hw, z.hw, -z.hw, -z.hw};
   if (theta == R(0)) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { zx[i] = ax + lx[i]; zy[i] = ay + ly[i]; }
+    for (int i = 0; i < 4; ++i) { q.x[i] = z.ax + lx[i]; q.y[i] = z.ay + ly[i]; }
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      zx[i] = ax + ((c * lx[i]) - (s * ly[i]));
-      zy[i] = ay + ((s * lx[i]) + (c * ly[i]));
+      q.x[i] = z.ax + ((c * lx[i]) - (s * ly[i]));
+      q.y[i] = z.ay + ((s * lx[i]) + (c * ly[i]));
     }
   }
-  const R p = bd / td, q = R(1) - p;
-  const R lsx = (zx[0] * q) + (zx[1] * p), lsy = (zy[0] * q) + (zy[1] * p);
-  const R rsx = (zx[3] * q) + (zx[2] * p), rsy = (zy[3] * q) + (zy[2] * p);
-  braking.x[0] = zx[0]; braking.y[0] = zy[0];
-  braking.x[1] = lsx;   braking.y[1] = lsy;
-  braking.x[2] = rsx;   braking.y[2] = rsy;
-  braking.x[3] = zx[3]; braking.y[3] = zy[3];
-  reaction.x[0] = lsx;   reaction.y[0] = lsy;
-  reaction.x[1] = zx[1]; reaction.y[1] = zy[1];
-  reaction.x[2] = zx[2]; reaction.y[2] = zy[2];
-  reaction.x[3] = rsx;   reaction.y[3] = rsy;
-  return true;
 }
 
-// max over the edges of A of (min over the vertices of B of the signed outside distance).
-// > 0  <=>  some edge line of A has all of B strictly outside (a separating axis).
 template <typename R>
-__device__ __forceinline__ R separation(const Quad<R>& A, const Quad<R>& B) {
-  R best = -INFINITY;
+__device__ __forceinline__ Aabb<R> zone_aabb(const ZoneFrame<R>& z, R theta, R c, R s, R x0, R x1) {
+  if (theta == R(0)) return {z.ax + x0, z.ax + x1, z.ay - z.hw, z.ay + z.hw};
+  Quad<R> q;
+  zone_quad(z, theta, c, s, x0, x1, q);
+  return aabb_of(q);
+}
+
+// Separating-axis bookkeeping without square roots or divisions.  For edge i of A let m_i be the smallest
+// cross(e_i, p - a_i) over the vertices p of B (> 0 means all of B strictly outside that edge line) and
+// near_i <=> |m_i| < tau * |e_i|  <=>  m_i^2 < tau^2 |e_i|^2.
+//   bit 0 (SEP_CLEAR)   some edge separates with margin >= tau
+//   bit 1 (SEP_ANY)     some edge separates (m_i > 0)
+//   bit 2 (NEAR_ANY)    some edge has |margin| < tau
+enum { SEP_CLEAR = 1, SEP_ANY = 2, NEAR_ANY = 4 };
+
+template <typename R>
+__device__ __forceinline__ int separation_bits(const Quad<R>& A, const Quad<R>& B, R tau2) {
+  int bits = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int j = (i + 1) & 3;
@@ -108,17 +155,28 @@ __device__ __forceinline__ R separation(const Quad<R>& A, const Quad<R>& B) {
     R m = INFINITY;
 #pragma unroll
     for (int k = 0; k < 4; ++k) m = rmin(m, ex * (B.y[k] - ay) - ey * (B.x[k] - ax));
-    if (len2 > R(0)) best = rmax(best, m / rsqrt_(len2));
+    if (len2 > R(0)) {
+      const bool near = m * m < tau2 * len2;
+      if (m > R(0)) bits |= near ? SEP_ANY : (SEP_ANY | SEP_CLEAR);
+      if (near) bits |= NEAR_ANY;
+    }
   }
-  return best;
+  return bits;
 }
 
-// Full separating-axis test (8 edge normals).  Rare path: called only when the AABBs overlap.
+// Result of a rare-path predicate: bit 0 = predicate holds, bit 1 = decision margin within tau (near-tangent).
+enum { GEO_HIT = 1, GEO_TANGENT = 2 };
+
+// Full separating-axis test (8 edge normals).  Rare path, called only when the AABBs overlap.  Quads are passed
+// BY VALUE so that the caller's copies are never address-taken and stay in registers on the common path.
+// Near-tangent <=> the largest normalised margin lies in (-tau, tau) <=> no edge separates clearly and
+// some edge is within tau of touching.
 template <typename R>
-__device__ __noinline__ bool sat_intersects(const Quad<R>& A, const Quad<R>& B, R tau, bool& tangent) {
-  const R m = rmax(separation(A, B), separation(B, A));
-  if (rabs(m) < tau) tangent = true;
-  return m <= R(0);
+__device__ __noinline__ int sat_intersects(Quad<R> A, Quad<R> B, R tau) {
+  const int bits = separation_bits(A, B, tau * tau) | separation_bits(B, A, tau * tau);
+  const bool hit = !(bits & SEP_ANY);
+  const bool tangent = !(bits & SEP_CLEAR) && (bits & NEAR_ANY);
+  return (hit ? GEO_HIT : 0) | (tangent ? GEO_TANGENT : 0);
 }
 
 // Shape.intersects for two convex quads.  AABB rejection first: exact and conservative.
@@ -126,13 +184,17 @@ template <typename R>
 __device__ __forceinline__ bool intersects(const Quad<R>& A, const Aabb<R>& a, const Quad<R>& B, const Aabb<R>& b, R tau,
                                            bool& tangent) {
   if (aabb_gap(a, b) > tau) return false;
-  return sat_intersects(A, B, tau, tangent);
+  const int r = sat_intersects(A, B, tau);
+  if (r & GEO_TANGENT) tangent = true;
+  return (r & GEO_HIT) != 0;
 }
 
-// outer.contains(inner): every vertex of inner inside or on every edge of outer.
+// outer.contains(inner): every vertex of inner inside or on every edge of outer.  Near-tangent when the
+// worst vertex is within tau of some edge line (compared without sqrt: m^2 < tau^2 |e|^2).
 template <typename R>
 __device__ __forceinline__ bool contains(const Quad<R>& outer, const Quad<R>& inner, R tau, bool& tangent) {
-  R worst = -INFINITY;
+  bool inside = true, clear_out = false, near = false;
+  const R tau2 = tau * tau;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int j = (i + 1) & 3;
@@ -141,10 +203,14 @@ __device__ __forceinline__ bool contains(const Quad<R>& outer, const Quad<R>& in
     R m = -INFINITY;
 #pragma unroll
     for (int k = 0; k < 4; ++k) m = rmax(m, ex * (inner.y[k] - ay) - ey * (inner.x[k] - ax));
-    if (len2 > R(0)) worst = rmax(worst, m / rsqrt_(len2));
+    if (len2 > R(0)) {
+      const bool close = m * m < tau2 * len2;
+      if (m > R(0)) { inside = false; if (!close) clear_out = true; }
+      if (close) near = true;
+    }
   }
-  if (rabs(worst) < tau) tangent = true;
-  return worst <= R(0);
+  if (near && !clear_out) tangent = true;
+  return inside;
 }
 
 template <typename R>
@@ -196,14 +262,75 @@ __device__ __noinline__ R clip_area(const Quad<R>& subject, const Quad<R>& clip)
 }
 
 // Shape.percentage_intersects (geometry.py:80-87): share of `self` lying on `other`.
-// Callers reject AABB-disjoint pairs first, so this is the rare path.
+// Callers reject AABB-disjoint pairs first, so this is the rare path (by-value arguments, see sat_intersects).
 template <typename R>
-__device__ __noinline__ R percentage_intersects(const Quad<R>& self, const Quad<R>& other, R tau, bool& tangent) {
-  const R m = rmax(separation(self, other), separation(other, self));
-  if (rabs(m) < tau) tangent = true;
-  if (!(m <= R(0))) return R(0);
-  if (contains(other, self, tau, tangent)) return R(1);
-  return clip_area(self, other) / quad_area(self);
+struct Share {
+  R value;
+  int tangent;
+};
+
+template <typename R>
+__device__ __noinline__ Share<R> percentage_intersects(Quad<R> self, Quad<R> other, R tau) {
+  Share<R> out;
+  bool tangent = false;
+  const int bits = separation_bits(self, other, tau * tau) | separation_bits(other, self, tau * tau);
+  if (!(bits & SEP_CLEAR) && (bits & NEAR_ANY)) tangent = true;
+  if (bits & SEP_ANY) out.value = R(0);
+  else if (contains(other, self, tau, tangent)) out.value = R(1);
+  else out.value = clip_area(self, other) / quad_area(self);
+  out.tangent = tangent ? 1 : 0;
+  return out;
+}
+
+// Area of the part of a convex quad on the inner side of ONE axis-aligned line, by a single Sutherland–Hodgman
+// stage with a running shoelace sum (no vertex list, registers only).  inside(p) <=> sign * (coord(p) - bound) <= 0.
+// This is the kerb-crossing case: a body box straddling exactly one edge of an axis-aligned road rectangle.
+template <typename R>
+__device__ __forceinline__ R halfplane_area(const Quad<R>& q, bool vertical_line, R bound, R sign) {
+  R d[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d[i] = sign * (bound - (vertical_line ? q.x[i] : q.y[i]));  // >= 0 inside
+  R acc = R(0), fx = R(0), fy = R(0), px = R(0), py = R(0);
+  bool have = false;
+  auto emit = [&](R x, R y) {
+    if (have) acc += px * y - x * py;
+    else { fx = x; fy = y; have = true; }
+    px = x; py = y;
+  };
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = (i + 1) & 3;
+    if (d[i] >= R(0)) emit(q.x[i], q.y[i]);
+    if ((d[i] > R(0) && d[j] < R(0)) || (d[i] < R(0) && d[j] > R(0))) {
+      const R t = fast_div(d[i], d[i] - d[j]);
+      emit(q.x[i] + t * (q.x[j] - q.x[i]), q.y[i] + t * (q.y[j] - q.y[i]));
+    }
+  }
+  if (have) acc += px * fy - fx * py;
+  return rabs(acc) * R(0.5);
+}
+
+// Share of a body box lying on an EXACTLY axis-aligned road rectangle (road == road_bb), given the box AABB:
+//   clearly inside            -> 1
+//   straddles exactly one edge -> single half-plane clip, registers only (the kerb crossing, common)
+//   anything else             -> general path (returns -1: caller falls back to percentage_intersects)
+// Callers have already rejected boxes that are clearly apart.
+template <typename R>
+__device__ __forceinline__ R axis_road_share(const Quad<R>& box, const Aabb<R>& bb, R box_area, const Aabb<R>& road, R tau,
+                                             bool& tangent) {
+  const R m0 = bb.x0 - road.x0, m1 = road.x1 - bb.x1, m2 = bb.y0 - road.y0, m3 = road.y1 - bb.y1;  // >= 0: inside that edge
+  const int out = (m0 < tau) + (m1 < tau) + (m2 < tau) + (m3 < tau);
+  if (out == 0) return R(1);
+  const bool straddle = (m0 <= -tau) + (m1 <= -tau) + (m2 <= -tau) + (m3 <= -tau) == 1;
+  if (out != 1 || !straddle) return R(-1);
+  // exactly one edge is crossed, clearly; the box is clearly inside the other three
+  R area;
+  if (m0 < tau) area = halfplane_area(box, true, road.x0, R(-1));       // inside: x >= x0
+  else if (m1 < tau) area = halfplane_area(box, true, road.x1, R(1));   // inside: x <= x1
+  else if (m2 < tau) area = halfplane_area(box, false, road.y0, R(-1));
+  else area = halfplane_area(box, false, road.y1, R(1));
+  (void)tangent;
+  return fast_div(area, box_area);
 }
 
 }  // namespace cav

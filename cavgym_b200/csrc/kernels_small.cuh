@@ -17,6 +17,12 @@
 namespace cav {
 
 constexpr int kThreads = 128;
+#ifndef CAV_MIN_BLOCKS_STEP
+#define CAV_MIN_BLOCKS_STEP 3
+#endif
+#ifndef CAV_MIN_BLOCKS_LOOP
+#define CAV_MIN_BLOCKS_LOOP 2
+#endif
 
 template <typename R, int M, bool AGENTS>
 __device__ __forceinline__ void load_env(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, EnvRegs<R, M>& env) {
@@ -25,12 +31,18 @@ __device__ __forceinline__ void load_env(const DevScenario<R>& sc, const EnvBuff
   env.t_ep = buf.t_ep[e];
   env.winner = env.done ? buf.winner[e] : -1;
   env.ag_dirty = 0;
+  env.cs_dirty = 0;
   env.episode = AGENTS ? buf.episode[e] : 0;
 #pragma unroll
   for (int b = 0; b < M; ++b) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) env.s[b][c] = buf.state[((int64_t)b * 4 + c) * n + e];
     env.held[b][0] = R(0); env.held[b][1] = R(0);
+    env.cs[b][0] = R(1); env.cs[b][1] = R(0);
+    if (sc.bodies[b].kind == CAV_BODY_DYNAMIC) {
+      env.cs[b][0] = buf.cs[((int64_t)b * 2 + 0) * n + e];
+      env.cs[b][1] = buf.cs[((int64_t)b * 2 + 1) * n + e];
+    }
     if (AGENTS && sc.bodies[b].agent == CAV_AGENT_RANDOM) {
       env.held[b][0] = buf.action[((int64_t)b * 2 + 0) * n + e];
       env.held[b][1] = buf.action[((int64_t)b * 2 + 1) * n + e];
@@ -54,6 +66,10 @@ __device__ __forceinline__ void store_env(const DevScenario<R>& sc, const EnvBuf
     if (all || (AGENTS && sc.bodies[b].agent != CAV_AGENT_EXTERNAL && (buf.log_actions || sc.bodies[b].agent == CAV_AGENT_RANDOM))) {
       buf.action[((int64_t)b * 2 + 0) * n + e] = env.held[b][0];
       buf.action[((int64_t)b * 2 + 1) * n + e] = env.held[b][1];
+    }
+    if (all || (env.cs_dirty >> b & 1u)) {
+      buf.cs[((int64_t)b * 2 + 0) * n + e] = env.cs[b][0];
+      buf.cs[((int64_t)b * 2 + 1) * n + e] = env.cs[b][1];
     }
     if (all || (AGENTS && uses_agent_state<R, M>(sc, b) && (env.ag_dirty >> b & 1u))) {
 #pragma unroll
@@ -117,7 +133,7 @@ __device__ __forceinline__ void load_actions(const R* actions, int64_t n, int64_
 }
 
 template <typename R, int M, bool AGENTS>
-__global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ DevScenario<R> sc,
+__global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_STEP) step_kernel(const __grid_constant__ DevScenario<R> sc,
                                                         const __grid_constant__ EnvBuffers<R> buf,
                                                         const __grid_constant__ StepIO<R> io, int64_t t_global) {
   const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -136,7 +152,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
 
 // Trajectory outputs are [T][...] slabs of the per-step shapes; io.* point at step 0.
 template <typename R, int M>
-__global__ void __launch_bounds__(kThreads) replay_kernel(const __grid_constant__ DevScenario<R> sc,
+__global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) replay_kernel(const __grid_constant__ DevScenario<R> sc,
                                                           const __grid_constant__ EnvBuffers<R> buf,
                                                           const __grid_constant__ StepIO<R> io, int64_t t_global, int n_steps) {
   const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -168,7 +184,7 @@ __global__ void __launch_bounds__(kThreads) replay_kernel(const __grid_constant_
 }
 
 template <typename R, int M>
-__global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant__ DevScenario<R> sc,
+__global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) rollout_kernel(const __grid_constant__ DevScenario<R> sc,
                                                            const __grid_constant__ EnvBuffers<R> buf, int64_t t_global,
                                                            int n_steps, int auto_reset) {
   const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -202,6 +218,10 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__
   if (e >= buf.hi || (mask && !mask[e])) return;
   EnvRegs<R, M> env;
   env.episode = first_time ? -1 : buf.episode[e];
+  if (!first_time && !buf.done[e]) {  // an unfinished episode is abandoned: keep its steps in the env-step total
+    const int32_t t = buf.t_ep[e];
+    if (t > 0) atomicAdd(&buf.stats[CAV_STAT_ENV_STEPS], (unsigned long long)t);
+  }
   reset_env<R, M>(sc, buf, init, e, env);
   store_env<R, M, true>(sc, buf, e, env, true);
   if (first_time) buf.err[e] = 0;

@@ -22,7 +22,9 @@ struct EnvRegs {
   R s[M][4];         // x, y, v, theta (PelicanCrossing: light state in [0])
   R held[M][2];      // last action of on-device agents (RandomAgent holds it)
   R ag[M][CAV_AGENT_WORDS];
+  R cs[M][2];        // cos, sin of the heading (EnvBuffers::cs)
   int32_t t_ep, episode, winner;
+  uint32_t cs_dirty;  // bit b: cs[b] changed since it was loaded
   uint32_t ag_dirty;  // bit b: ag[b] changed since it was loaded
   uint8_t done;
 };
@@ -59,6 +61,22 @@ __device__ __forceinline__ void flush_stats(const LocalStats& ls, unsigned long 
 template <typename R, int M>
 __device__ __forceinline__ bool uses_agent_state(const DevScenario<R>& sc, int b) {
   return sc.bodies[b].agent == CAV_AGENT_RANDOM_CONSTRAINED || sc.bodies[b].agent == CAV_AGENT_PROXIMITY;
+}
+
+template <typename R>
+__device__ __forceinline__ bool sat_hit(const Quad<R>& a, const Quad<R>& b, R tau, bool& tangent) {
+  const int r = sat_intersects(a, b, tau);
+  if (r & GEO_TANGENT) tangent = true;
+  return (r & GEO_HIT) != 0;
+}
+
+// Corners of body b from its post-step state; b must be a compile-time constant at the call site (unrolled loops).
+template <typename R, int M>
+__device__ __forceinline__ void body_quad(const DevScenario<R>& sc, const EnvRegs<R, M>& env, const R (&co)[M], const R (&si)[M],
+                                          const int b, Quad<R>& q) {
+  const DevBody<R>& body = sc.bodies[b];
+  if (body.kind == CAV_BODY_PELICAN) q = body.sbox;
+  else make_box(body.k.length, body.k.width, env.s[b][3], co[b], si[b], env.s[b][0], env.s[b][1], q);
 }
 
 // Result of one transition besides the updated EnvRegs.
@@ -141,6 +159,7 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
   }
 
   // ---- body.step, then what every later test needs per body: cos/sin of the new heading and the AABB
+  R (&co_si)[M][2] = env.cs;
   R co[M], si[M];
   Aabb<R> bb[M];
   R ego_steer = R(0);
@@ -157,26 +176,21 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
     } else {
       const DevType<R>& k = body.k;
       R snapped;
-      body_step(k, env.s[b], act[b][0], act[b][1], dt, co[b], si[b], snapped);
+      if (body_step(k, env.s[b], act[b][0], act[b][1], dt, co_si[b][0], co_si[b][1], snapped)) env.cs_dirty |= 1u << b;
+      co[b] = co_si[b][0]; si[b] = co_si[b][1];
       if (b == 0) ego_steer = snapped;
-      Quad<R> q;
-      make_box(k.length, k.width, env.s[b][3], co[b], si[b], env.s[b][0], env.s[b][1], q);
-      bb[b] = aabb_of(q);
+      bb[b] = box_aabb(k.length, k.width, env.s[b][3], co[b], si[b], env.s[b][0], env.s[b][1]);
     }
   }
-  // Rebuilds body b's corners on demand (deterministic, so identical to the ones the AABB came from);
-  // keeping only the AABB live keeps register pressure flat in M.
-  auto box_of = [&](int b, Quad<R>& q) {
-    const DevBody<R>& body = sc.bodies[b];
-    if (body.kind == CAV_BODY_PELICAN) { q = body.sbox; return; }
-    const DevType<R>& k = body.k;
-    make_box(k.length, k.width, env.s[b][3], co[b], si[b], env.s[b][0], env.s[b][1], q);
-  };
+  // Body b's corners are rebuilt on demand by body_quad() (deterministic, so identical to the ones the AABB came
+  // from); keeping only the AABB live keeps register pressure flat in M.
+#define CAV_BOX(b, q) body_quad<R, M>(sc, env, co, si, b, q)
 
   // ---- rewards and liveness
   const R c = sc.cost_step, W = sc.W;
-  const R ego_rel = rmax(R(0), rmin(R(1), (W - env.s[0][0]) / W));
-  const R voff = rabs(env.s[0][2] - sc.v_maint) / sc.v_off;
+  // Both divisors are scenario constants: multiply by the host-computed reciprocal (<= 1 ulp from the division).
+  const R ego_rel = rmax(R(0), rmin(R(1), (W - env.s[0][0]) * sc.inv_W));
+  const R voff = rabs(env.s[0][2] - sc.v_maint) * sc.inv_v_off;
   R r0 = R(0);
   r0 -= voff * c;
   r0 += (R(1) - ego_rel) * c;
@@ -190,10 +204,17 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
     for (int r = 0; r < CAV_MAX_ROADS; ++r) {
       if (r >= sc.n_roads) break;
       R q = R(0);
-      if (!(aabb_gap(bb[b], sc.road_bb[r]) > tau)) {  // otherwise disjoint: percentage 0
+      if (!aabb_apart(bb[b], sc.road_bb[r], tau)) {  // otherwise disjoint: percentage 0
         Quad<R> mine;
-        box_of(b, mine);
-        q = percentage_intersects(mine, sc.roads[r], tau, near);
+        CAV_BOX(b, mine);
+        if (sc.road_axis[r] && !is_static)
+          q = axis_road_share(mine, bb[b], sc.bodies[b].k.length * sc.bodies[b].k.width, sc.road_bb[r], tau, near);
+        else q = R(-1);
+        if (q < R(0)) {  // rotated road, road corner or near-tangent: the general predicates
+          const Share<R> share = percentage_intersects(mine, sc.roads[r], tau);
+          q = share.value;
+          near |= share.tangent != 0;
+        }
       }
       if (r == 0 || q > p) p = q;
     }
@@ -223,20 +244,20 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
 #pragma unroll
       for (int j = i + 1; j < M; ++j) {
         if (sc.bodies[j].kind == CAV_BODY_PELICAN) continue;
-        if (!(aabb_gap(bb[i], bb[j]) > tau)) {
+        if (!aabb_apart(bb[i], bb[j], tau)) {
           Quad<R> qi, qj;
-          box_of(i, qi);
-          box_of(j, qj);
-          hit |= sat_intersects(qi, qj, tau, tangent);
+          CAV_BOX(i, qi);
+          CAV_BOX(j, qj);
+          hit |= sat_hit(qi, qj, tau, tangent);
         }
       }
 #pragma unroll
       for (int s = 0; s < CAV_MAX_STATICS; ++s) {
         if (s >= sc.n_statics) break;
-        if (!(aabb_gap(bb[i], sc.static_bb[s]) > tau)) {
+        if (!aabb_apart(bb[i], sc.static_bb[s], tau)) {
           Quad<R> qi;
-          box_of(i, qi);
-          hit |= sat_intersects(qi, sc.statics[s], tau, tangent);
+          CAV_BOX(i, qi);
+          hit |= sat_hit(qi, sc.statics[s], tau, tangent);
         }
       }
     }
@@ -247,38 +268,45 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
 #pragma unroll
     for (int r = 0; r < CAV_MAX_ROADS; ++r) {
       if (r >= sc.n_roads) break;
-      if (!(aabb_gap(bb[0], sc.road_bb[r]) > tau)) {
+      if (!aabb_apart(bb[0], sc.road_bb[r], tau)) {
         Quad<R> q0;
-        box_of(0, q0);
-        on_road |= sat_intersects(q0, sc.roads[r], tau, tangent);
+        CAV_BOX(0, q0);
+        on_road |= sat_hit(q0, sc.roads[r], tau, tangent);
       }
     }
     terminate = !on_road;
   }
   if (!terminate && (sc.collisions == CAV_COLLISIONS_EGO || sc.zones)) {
-    Quad<R> braking, reaction;
-    Aabb<R> braking_bb, reaction_bb;
     const DevType<R>& k0 = sc.bodies[0].k;
-    const bool have_zones = stopping_zones(k0, env.s[0][0], env.s[0][1], env.s[0][2], env.s[0][3], co[0], si[0], ego_steer,
-                                           braking, reaction);
-    if (have_zones) { braking_bb = aabb_of(braking); reaction_bb = aabb_of(reaction); }
+    const R th0 = env.s[0][3];
+    const ZoneFrame<R> zf = zone_frame(k0, env.s[0][0], env.s[0][1], env.s[0][2], th0, co[0], si[0], ego_steer);
+    const bool have_zones = zf.have;
+    Aabb<R> braking_bb = {R(0), R(0), R(0), R(0)}, reaction_bb = braking_bb;
+    if (have_zones) {
+      braking_bb = zone_aabb(zf, th0, co[0], si[0], R(0), zf.bd);
+      reaction_bb = zone_aabb(zf, th0, co[0], si[0], zf.bd, zf.td);
+    }
     if (sc.collisions == CAV_COLLISIONS_EGO) {
       bool hit = false;
 #pragma unroll
       for (int b = 1; b < M; ++b) {
         if (!(sc.bodies[b].flags & CAV_FLAG_PEDESTRIAN)) continue;
-        const bool near_ego = !(aabb_gap(bb[b], bb[0]) > tau);
-        const bool near_brake = have_zones && !(aabb_gap(bb[b], braking_bb) > tau);
+        const bool near_ego = !aabb_apart(bb[b], bb[0], tau);
+        const bool near_brake = have_zones && !aabb_apart(bb[b], braking_bb, tau);
         if (near_ego || near_brake) {
           Quad<R> qb;
-          box_of(b, qb);
+          CAV_BOX(b, qb);
           bool h = false;
           if (near_ego) {
             Quad<R> q0;
-            box_of(0, q0);
-            h = sat_intersects(qb, q0, tau, tangent);
+            CAV_BOX(0, q0);
+            h = sat_hit(qb, q0, tau, tangent);
           }
-          if (!h && near_brake) h = sat_intersects(qb, braking, tau, tangent);
+          if (!h && near_brake) {
+            Quad<R> braking;
+            zone_quad(zf, th0, co[0], si[0], R(0), zf.bd, braking);
+            h = sat_hit(qb, braking, tau, tangent);
+          }
           hit |= h;
         }
       }
@@ -289,10 +317,11 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
 #pragma unroll
         for (int b = 1; b < M; ++b) {
           if (!(sc.bodies[b].flags & CAV_FLAG_PEDESTRIAN) || win_tester >= 0) continue;
-          if (!(aabb_gap(bb[b], reaction_bb) > tau)) {
-            Quad<R> qb;
-            box_of(b, qb);
-            if (sat_intersects(qb, reaction, tau, tangent)) win_tester = b;
+          if (!aabb_apart(bb[b], reaction_bb, tau)) {
+            Quad<R> qb, reaction;
+            CAV_BOX(b, qb);
+            zone_quad(zf, th0, co[0], si[0], zf.bd, zf.td, reaction);
+            if (sat_hit(qb, reaction, tau, tangent)) win_tester = b;
           }
         }
       }
@@ -328,6 +357,7 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
   else if (env.t_ep >= sc.max_timesteps) env.done = 2;  // cut off by Simulation.run (simulation.py:69-70), not `done`
   out.terminate = terminate;
   out.tangent = tangent;
+#undef CAV_BOX
 }
 
 // reporting.analyse_episode (reporting.py:227-243) for an env whose episode just ended.
@@ -379,6 +409,8 @@ __device__ __forceinline__ void reset_env(const DevScenario<R>& sc, const EnvBuf
 #pragma unroll
     for (int c = 0; c < 4; ++c) env.s[b][c] = st[c];
     env.held[b][0] = R(0); env.held[b][1] = R(0);
+    env.cs[b][0] = R(1); env.cs[b][1] = R(0);
+    if (body.kind == CAV_BODY_DYNAMIC) heading_cs(sc, st[3], env.cs[b][0], env.cs[b][1]);
 #pragma unroll
     for (int w = 0; w < CAV_AGENT_WORDS; ++w) env.ag[b][w] = nan_<R>();
     buf.liveness[(int64_t)b * buf.n + e] = 0;
@@ -387,6 +419,7 @@ __device__ __forceinline__ void reset_env(const DevScenario<R>& sc, const EnvBuf
   env.done = 0;
   env.winner = -1;
   env.ag_dirty = 0xFFFFFFFFu;  // everything must be written back
+  env.cs_dirty = 0xFFFFFFFFu;
 }
 
 }  // namespace cav
