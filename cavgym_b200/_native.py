@@ -9,7 +9,7 @@ import os
 from . import _abi
 
 LIB_NAME = "libcavgym_sm100.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+LIB_PATH = os.environ.get("CAVGYM_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)  # CAVGYM_LIB: tuning builds
 _lib = None
 
 

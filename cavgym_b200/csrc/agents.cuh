@@ -11,14 +11,15 @@
 
 namespace cav {
 
-__device__ __forceinline__ void sincos_(double a, double* s, double* c) { sincos(a, s, c); }
-__device__ __forceinline__ void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
-__device__ __forceinline__ double tan_(double a) { return tan(a); }
-__device__ __forceinline__ float tan_(float a) { return tanf(a); }
-__device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
-__device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
-__device__ __forceinline__ double atan_(double a) { return atan(a); }
-__device__ __forceinline__ float atan_(float a) { return atanf(a); }
+// The fp64 libm routines are ~100-instruction sequences: one out-of-line copy each keeps the kernels' hot path small.
+static __device__ __noinline__ void sincos_(double a, double* s, double* c) { sincos(a, s, c); }
+static __device__ __noinline__ void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
+static __device__ __noinline__ double tan_(double a) { return tan(a); }
+static __device__ __noinline__ float tan_(float a) { return tanf(a); }
+static __device__ __noinline__ double atan2_(double y, double x) { return atan2(y, x); }
+static __device__ __noinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+static __device__ __noinline__ double atan_(double a) { return atan(a); }
+static __device__ __noinline__ float atan_(float a) { return atanf(a); }
 __device__ __forceinline__ bool isnan_(double a) { return isnan(a); }
 __device__ __forceinline__ bool isnan_(float a) { return isnan(a); }
 template <typename R> __device__ __forceinline__ R nan_() { return R(NAN); }
@@ -39,42 +40,57 @@ __device__ __forceinline__ void heading_cs(const DevScenario<R>& sc, R th, R& c,
   if (!hit) sincos_(th, &s, &c);
 }
 
-// c, s: cos/sin of the CURRENT heading on entry (cached in EnvBuffers::cs, refreshed only when the heading
-// changes), cos/sin of the NEW heading on return.  Returns true if the heading changed.
+// The turning branch of DynamicBody.step (bodies.py:241-275): rotation about the instantaneous centre.  Out of line:
+// only a few percent of the lanes turn in any step.
 template <typename R>
-__device__ __forceinline__ bool body_step(const DevType<R>& k, R st[4], R throttle, R steer, R dt, R& c, R& s, R& snapped) {
-  if (rabs(steer) < R(0.0000000000001)) steer = R(0);
-  snapped = steer;
-  const R x = st[0], y = st[1], v = st[2], th = st[3];
-  const R v1 = rmax(k.vmin, rmin(k.vmax, v + (throttle * dt)));
-  const R d = v * dt;
-  st[2] = v1;
-  if (steer == R(0)) {
-    st[0] = x + d * c;
-    st[1] = y + d * s;
-    return false;
-  }
-  const R wbo = k.wheelbase / R(2);
+struct Turned {
+  R x, y, theta, c, s;
+};
+
+template <typename R>
+__device__ __noinline__ Turned<R> turn_step(R wheelbase, R kk_smin, R kk_smax, R smin, R smax, R x, R y, R th, R c, R s, R d, R steer) {
+  const R wbo = wheelbase / R(2);
   const R rx = x - wbo * c, ry = y - wbo * s;
   // wheelbase / tan(steer): at full lock (what a crossing agent commands for all but the last step of a turn)
   // the host-computed value is used, which is also the reference's own libm value
   R kk;
-  if (steer == k.smax) kk = k.kk_smax;
-  else if (steer == k.smin) kk = k.kk_smin;
-  else kk = k.wheelbase / tan_(steer);
+  if (steer == smax) kk = kk_smax;
+  else if (steer == smin) kk = kk_smin;
+  else kk = wheelbase / tan_(steer);
   const R cx = rx - kk * s, cy = ry + kk * c;
   const R dx = x - cx, dy = y - cy;
   const R q = d / rsqrt_(dx * dx + dy * dy);
   const R theta = steer < R(0) ? -q : q;
   R ct, sn;
   sincos_(theta, &sn, &ct);
-  st[0] = cx + dx * ct - dy * sn;
-  st[1] = cy + dx * sn + dy * ct;
+  Turned<R> out;
+  out.x = cx + dx * ct - dy * sn;
+  out.y = cy + dx * sn + dy * ct;
   // sin/cos(th + theta) by angle addition from the two sincos in hand (the reference evaluates sin and cos of
   // the rounded sum; the difference is a few ulp).  They are also cos/sin of the new heading atan2(so, co).
-  const R so = s * ct + c * sn, co = c * ct - s * sn;
-  st[3] = atan2_(so, co);
-  c = co; s = so;
+  out.s = s * ct + c * sn;
+  out.c = c * ct - s * sn;
+  out.theta = atan2_(out.s, out.c);
+  return out;
+}
+
+// c, s: cos/sin of the CURRENT heading on entry (cached in EnvBuffers::cs, refreshed only when the heading
+// changes), cos/sin of the NEW heading on return.  Returns true if the heading changed.
+template <typename R>
+__device__ __forceinline__ bool body_step(const DevType<R>& k, R st[4], R throttle, R steer, R dt, R& c, R& s, R& snapped) {
+  if (rabs(steer) < R(0.0000000000001)) steer = R(0);
+  snapped = steer;
+  const R v = st[2];
+  const R d = v * dt;
+  st[2] = rmax(k.vmin, rmin(k.vmax, v + (throttle * dt)));
+  if (steer == R(0)) {
+    st[0] = st[0] + d * c;
+    st[1] = st[1] + d * s;
+    return false;
+  }
+  const Turned<R> t = turn_step(k.wheelbase, k.kk_smin, k.kk_smax, k.smin, k.smax, st[0], st[1], st[3], c, s, d, steer);
+  st[0] = t.x; st[1] = t.y; st[3] = t.theta;
+  c = t.c; s = t.s;
   return true;
 }
 

@@ -39,6 +39,7 @@ struct DevBody {
   R init[4];       // init_state (bodies.py:27); PelicanCrossing: light state in [0]
   DevType<R> k;    // this body's DynamicBodyConstants row, resolved on the host
   Quad<R> sbox;    // PelicanCrossing static box
+  Aabb<R> sbox_bb;
 };
 
 template <typename R>

@@ -117,6 +117,7 @@ static void convert(const CavScenario& in, double tau, DevScenario<R>& out) {
     for (int c = 0; c < 4; ++c) dst.init[c] = (R)src.init_state[c];
     if (src.kind == CAV_BODY_DYNAMIC) dst.k = to_type<R>(in.types[src.type_id]);
     dst.sbox = to_quad<R>(src.static_box);
+    dst.sbox_bb = host_aabb(dst.sbox);
   }
   // heading cache: orientations bodies start with, cos/sin from the host C library (what math.cos/math.sin call)
   auto remember = [&out](double theta) {

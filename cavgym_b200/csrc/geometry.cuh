@@ -282,14 +282,15 @@ __device__ __noinline__ Share<R> percentage_intersects(Quad<R> self, Quad<R> oth
   return out;
 }
 
-// Area of the part of a convex quad on the inner side of ONE axis-aligned line, by a single Sutherland–Hodgman
-// stage with a running shoelace sum (no vertex list, registers only).  inside(p) <=> sign * (coord(p) - bound) <= 0.
-// This is the kerb-crossing case: a body box straddling exactly one edge of an axis-aligned road rectangle.
+// Area of the part of a convex quad inside ONE half-plane {p : nx*x + ny*y <= bound}, by a single
+// Sutherland–Hodgman stage with a running shoelace sum (no vertex list, registers only).  This is the
+// kerb-crossing case: a body box straddling exactly one edge of an axis-aligned road rectangle, where (nx, ny) is
+// (+-1, 0) or (0, +-1) and the products are exact.
 template <typename R>
-__device__ __forceinline__ R halfplane_area(const Quad<R>& q, bool vertical_line, R bound, R sign) {
+__device__ __forceinline__ R halfplane_area(const Quad<R>& q, R nx, R ny, R bound) {
   R d[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) d[i] = sign * (bound - (vertical_line ? q.x[i] : q.y[i]));  // >= 0 inside
+  for (int i = 0; i < 4; ++i) d[i] = bound - (nx * q.x[i] + ny * q.y[i]);  // >= 0 inside
   R acc = R(0), fx = R(0), fy = R(0), px = R(0), py = R(0);
   bool have = false;
   auto emit = [&](R x, R y) {
@@ -310,27 +311,95 @@ __device__ __forceinline__ R halfplane_area(const Quad<R>& q, bool vertical_line
   return rabs(acc) * R(0.5);
 }
 
-// Share of a body box lying on an EXACTLY axis-aligned road rectangle (road == road_bb), given the box AABB:
-//   clearly inside            -> 1
-//   straddles exactly one edge -> single half-plane clip, registers only (the kerb crossing, common)
-//   anything else             -> general path (returns -1: caller falls back to percentage_intersects)
-// Callers have already rejected boxes that are clearly apart.
+// How a body-box AABB sits on an EXACTLY axis-aligned road rectangle (road == road_bb); callers have already
+// rejected boxes that are clearly apart.  Margins m >= tau mean "clearly inside that edge".
+//   AXIS_INSIDE    clearly inside all four edges                       -> share 1
+//   AXIS_ONE_EDGE  clearly across exactly one edge, inside the others  -> single half-plane clip (the kerb)
+//   AXIS_GENERAL   road corner or within tau of an edge                -> general predicates
+enum { AXIS_INSIDE = 0, AXIS_ONE_EDGE = 1, AXIS_GENERAL = 2 };
+
 template <typename R>
-__device__ __forceinline__ R axis_road_share(const Quad<R>& box, const Aabb<R>& bb, R box_area, const Aabb<R>& road, R tau,
-                                             bool& tangent) {
-  const R m0 = bb.x0 - road.x0, m1 = road.x1 - bb.x1, m2 = bb.y0 - road.y0, m3 = road.y1 - bb.y1;  // >= 0: inside that edge
+__device__ __forceinline__ int axis_case(const Aabb<R>& bb, const Aabb<R>& road, R tau) {
+  const R m0 = bb.x0 - road.x0, m1 = road.x1 - bb.x1, m2 = bb.y0 - road.y0, m3 = road.y1 - bb.y1;
   const int out = (m0 < tau) + (m1 < tau) + (m2 < tau) + (m3 < tau);
-  if (out == 0) return R(1);
-  const bool straddle = (m0 <= -tau) + (m1 <= -tau) + (m2 <= -tau) + (m3 <= -tau) == 1;
-  if (out != 1 || !straddle) return R(-1);
-  // exactly one edge is crossed, clearly; the box is clearly inside the other three
-  R area;
-  if (m0 < tau) area = halfplane_area(box, true, road.x0, R(-1));       // inside: x >= x0
-  else if (m1 < tau) area = halfplane_area(box, true, road.x1, R(1));   // inside: x <= x1
-  else if (m2 < tau) area = halfplane_area(box, false, road.y0, R(-1));
-  else area = halfplane_area(box, false, road.y1, R(1));
-  (void)tangent;
-  return fast_div(area, box_area);
+  if (out == 0) return AXIS_INSIDE;
+  const int across = (m0 <= -tau) + (m1 <= -tau) + (m2 <= -tau) + (m3 <= -tau);
+  return (out == 1 && across == 1) ? AXIS_ONE_EDGE : AXIS_GENERAL;
+}
+
+// ---------------------------------------------------------------- out-of-line rare paths
+// Everything below is __noinline__ and takes small by-value arguments: the always-executed path of a step stays a
+// few KB of straight-line code (it must fit the instruction caches), and the rare geometry lives once per kernel.
+
+template <typename R>
+struct Pose {  // what is needed to rebuild a body's corners: make_rectangle(length, width).transform(theta, (x, y))
+  R x, y, theta, c, s, length, width;
+};
+
+template <typename R>
+__device__ __forceinline__ void pose_quad(const Pose<R>& p, Quad<R>& q) {
+  make_box(p.length, p.width, p.theta, p.c, p.s, p.x, p.y, q);
+}
+
+// body box vs body box
+template <typename R>
+__device__ __noinline__ int sat_pose_pose(Pose<R> a, Pose<R> b, R tau) {
+  Quad<R> qa, qb;
+  pose_quad(a, qa);
+  pose_quad(b, qb);
+  const int bits = separation_bits(qa, qb, tau * tau) | separation_bits(qb, qa, tau * tau);
+  return (!(bits & SEP_ANY) ? GEO_HIT : 0) | ((!(bits & SEP_CLEAR) && (bits & NEAR_ANY)) ? GEO_TANGENT : 0);
+}
+
+// body box vs a static quad of the scenario tables (road, traffic light, obstacle, crossing box)
+template <typename R>
+__device__ __noinline__ int sat_pose_quad(Pose<R> a, const Quad<R>* other, R tau) {
+  Quad<R> qa, qb = *other;
+  pose_quad(a, qa);
+  const int bits = separation_bits(qa, qb, tau * tau) | separation_bits(qb, qa, tau * tau);
+  return (!(bits & SEP_ANY) ? GEO_HIT : 0) | ((!(bits & SEP_CLEAR) && (bits & NEAR_ANY)) ? GEO_TANGENT : 0);
+}
+
+// body box vs the part [x0, x1] of the ego's stopping-zone frame (braking or reaction zone)
+template <typename R>
+__device__ __noinline__ int sat_pose_zone(Pose<R> a, ZoneFrame<R> z, R theta, R c, R s, R x0, R x1, R tau) {
+  Quad<R> qa, qz;
+  pose_quad(a, qa);
+  zone_quad(z, theta, c, s, x0, x1, qz);
+  const int bits = separation_bits(qa, qz, tau * tau) | separation_bits(qz, qa, tau * tau);
+  return (!(bits & SEP_ANY) ? GEO_HIT : 0) | ((!(bits & SEP_CLEAR) && (bits & NEAR_ANY)) ? GEO_TANGENT : 0);
+}
+
+// The kerb crossing: share of a body box lying on an axis-aligned road when its AABB is clearly across exactly
+// one road edge (axis_case == AXIS_ONE_EDGE).  One compact out-of-line instance.
+template <typename R>
+__device__ __noinline__ R kerb_share(Pose<R> a, Aabb<R> bb, Aabb<R> road, R tau) {
+  Quad<R> box;
+  pose_quad(a, box);
+  R nx = R(0), ny = R(0), bound;
+  if (bb.x0 - road.x0 < tau) { nx = R(-1); bound = -road.x0; }        // inside: x >= x0
+  else if (road.x1 - bb.x1 < tau) { nx = R(1); bound = road.x1; }     // inside: x <= x1
+  else if (bb.y0 - road.y0 < tau) { ny = R(-1); bound = -road.y0; }
+  else { ny = R(1); bound = road.y1; }
+  return fast_div(halfplane_area(box, nx, ny, bound), a.length * a.width);
+}
+
+// Share of a body box lying on a road by the general predicates (Shape.percentage_intersects, geometry.py:80-87):
+// rotated roads, road corners, near-tangent configurations.  Cold.
+template <typename R>
+__device__ __noinline__ Share<R> road_share_general(Pose<R> a, const Quad<R>* road, R tau) {
+  Quad<R> box;
+  pose_quad(a, box);
+  const Quad<R> other = *road;
+  Share<R> out;
+  bool tangent = false;
+  const int bits = separation_bits(box, other, tau * tau) | separation_bits(other, box, tau * tau);
+  if (!(bits & SEP_CLEAR) && (bits & NEAR_ANY)) tangent = true;
+  if (bits & SEP_ANY) out.value = R(0);
+  else if (contains(other, box, tau, tangent)) out.value = R(1);
+  else out.value = clip_area(box, other) / quad_area(box);
+  out.tangent = tangent ? 1 : 0;
+  return out;
 }
 
 }  // namespace cav

@@ -63,20 +63,16 @@ __device__ __forceinline__ bool uses_agent_state(const DevScenario<R>& sc, int b
   return sc.bodies[b].agent == CAV_AGENT_RANDOM_CONSTRAINED || sc.bodies[b].agent == CAV_AGENT_PROXIMITY;
 }
 
-template <typename R>
-__device__ __forceinline__ bool sat_hit(const Quad<R>& a, const Quad<R>& b, R tau, bool& tangent) {
-  const int r = sat_intersects(a, b, tau);
-  if (r & GEO_TANGENT) tangent = true;
-  return (r & GEO_HIT) != 0;
+// Pose of body b from its post-step state; b must be a compile-time constant at the call site (unrolled loops).
+template <typename R, int M>
+__device__ __forceinline__ Pose<R> body_pose(const DevScenario<R>& sc, const EnvRegs<R, M>& env, const int b) {
+  const DevBody<R>& body = sc.bodies[b];
+  return {env.s[b][0], env.s[b][1], env.s[b][3], env.cs[b][0], env.cs[b][1], body.k.length, body.k.width};
 }
 
-// Corners of body b from its post-step state; b must be a compile-time constant at the call site (unrolled loops).
-template <typename R, int M>
-__device__ __forceinline__ void body_quad(const DevScenario<R>& sc, const EnvRegs<R, M>& env, const R (&co)[M], const R (&si)[M],
-                                          const int b, Quad<R>& q) {
-  const DevBody<R>& body = sc.bodies[b];
-  if (body.kind == CAV_BODY_PELICAN) q = body.sbox;
-  else make_box(body.k.length, body.k.width, env.s[b][3], co[b], si[b], env.s[b][0], env.s[b][1], q);
+__device__ __forceinline__ bool geo_hit(int r, bool& tangent) {
+  if (r & GEO_TANGENT) tangent = true;
+  return (r & GEO_HIT) != 0;
 }
 
 // Result of one transition besides the updated EnvRegs.
@@ -158,9 +154,7 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
     return;
   }
 
-  // ---- body.step, then what every later test needs per body: cos/sin of the new heading and the AABB
-  R (&co_si)[M][2] = env.cs;
-  R co[M], si[M];
+  // ---- body.step, then the AABB of every body (all later tests start from it)
   Aabb<R> bb[M];
   R ego_steer = R(0);
 #pragma unroll
@@ -171,20 +165,15 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
       if (act[b][0] == R(1)) env.s[b][0] = R(0);
       else if (act[b][0] == R(2)) env.s[b][0] = R(1);
       else if (act[b][0] == R(3)) env.s[b][0] = R(2);
-      co[b] = R(1); si[b] = R(0);
-      bb[b] = aabb_of(body.sbox);
+      bb[b] = body.sbox_bb;
     } else {
       const DevType<R>& k = body.k;
       R snapped;
-      if (body_step(k, env.s[b], act[b][0], act[b][1], dt, co_si[b][0], co_si[b][1], snapped)) env.cs_dirty |= 1u << b;
-      co[b] = co_si[b][0]; si[b] = co_si[b][1];
+      if (body_step(k, env.s[b], act[b][0], act[b][1], dt, env.cs[b][0], env.cs[b][1], snapped)) env.cs_dirty |= 1u << b;
       if (b == 0) ego_steer = snapped;
-      bb[b] = box_aabb(k.length, k.width, env.s[b][3], co[b], si[b], env.s[b][0], env.s[b][1]);
+      bb[b] = box_aabb(k.length, k.width, env.s[b][3], env.cs[b][0], env.cs[b][1], env.s[b][0], env.s[b][1]);
     }
   }
-  // Body b's corners are rebuilt on demand by body_quad() (deterministic, so identical to the ones the AABB came
-  // from); keeping only the AABB live keeps register pressure flat in M.
-#define CAV_BOX(b, q) body_quad<R, M>(sc, env, co, si, b, q)
 
   // ---- rewards and liveness
   const R c = sc.cost_step, W = sc.W;
@@ -200,20 +189,22 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
     const bool is_static = sc.bodies[b].kind == CAV_BODY_PELICAN;
     R p = R(0);
     bool near = false;
-#pragma unroll
-    for (int r = 0; r < CAV_MAX_ROADS; ++r) {
-      if (r >= sc.n_roads) break;
+#pragma unroll 1
+    for (int r = 0; r < sc.n_roads; ++r) {  // max over roads (environment.py:141)
       R q = R(0);
       if (!aabb_apart(bb[b], sc.road_bb[r], tau)) {  // otherwise disjoint: percentage 0
-        Quad<R> mine;
-        CAV_BOX(b, mine);
-        if (sc.road_axis[r] && !is_static)
-          q = axis_road_share(mine, bb[b], sc.bodies[b].k.length * sc.bodies[b].k.width, sc.road_bb[r], tau, near);
-        else q = R(-1);
-        if (q < R(0)) {  // rotated road, road corner or near-tangent: the general predicates
-          const Share<R> share = percentage_intersects(mine, sc.roads[r], tau);
-          q = share.value;
-          near |= share.tangent != 0;
+        if (is_static) {
+          const Quad<R> mine = sc.bodies[b].sbox;
+          q = percentage_intersects(mine, sc.roads[r], tau).value;  // static vs static: never tangent-flagged
+        } else {
+          const int how = sc.road_axis[r] ? axis_case(bb[b], sc.road_bb[r], tau) : AXIS_GENERAL;
+          if (how == AXIS_INSIDE) q = R(1);
+          else if (how == AXIS_ONE_EDGE) q = kerb_share(body_pose<R, M>(sc, env, b), bb[b], sc.road_bb[r], tau);
+          else {
+            const Share<R> share = road_share_general(body_pose<R, M>(sc, env, b), &sc.roads[r], tau);
+            q = share.value;
+            near |= share.tangent != 0;
+          }
         }
       }
       if (r == 0 || q > p) p = q;
@@ -244,71 +235,47 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
 #pragma unroll
       for (int j = i + 1; j < M; ++j) {
         if (sc.bodies[j].kind == CAV_BODY_PELICAN) continue;
-        if (!aabb_apart(bb[i], bb[j], tau)) {
-          Quad<R> qi, qj;
-          CAV_BOX(i, qi);
-          CAV_BOX(j, qj);
-          hit |= sat_hit(qi, qj, tau, tangent);
-        }
+        if (!aabb_apart(bb[i], bb[j], tau))
+          hit |= geo_hit(sat_pose_pose(body_pose<R, M>(sc, env, i), body_pose<R, M>(sc, env, j), tau), tangent);
       }
-#pragma unroll
-      for (int s = 0; s < CAV_MAX_STATICS; ++s) {
-        if (s >= sc.n_statics) break;
-        if (!aabb_apart(bb[i], sc.static_bb[s], tau)) {
-          Quad<R> qi;
-          CAV_BOX(i, qi);
-          hit |= sat_hit(qi, sc.statics[s], tau, tangent);
-        }
+#pragma unroll 1
+      for (int s = 0; s < sc.n_statics; ++s) {
+        if (!aabb_apart(bb[i], sc.static_bb[s], tau))
+          hit |= geo_hit(sat_pose_quad(body_pose<R, M>(sc, env, i), &sc.statics[s], tau), tangent);
       }
     }
     terminate = hit;
   }
   if (!terminate && sc.offroad) {
     bool on_road = false;
-#pragma unroll
-    for (int r = 0; r < CAV_MAX_ROADS; ++r) {
-      if (r >= sc.n_roads) break;
-      if (!aabb_apart(bb[0], sc.road_bb[r], tau)) {
-        Quad<R> q0;
-        CAV_BOX(0, q0);
-        on_road |= sat_hit(q0, sc.roads[r], tau, tangent);
-      }
+#pragma unroll 1
+    for (int r = 0; r < sc.n_roads; ++r) {
+      if (!aabb_apart(bb[0], sc.road_bb[r], tau))
+        on_road |= geo_hit(sat_pose_quad(body_pose<R, M>(sc, env, 0), &sc.roads[r], tau), tangent);
     }
     terminate = !on_road;
   }
   if (!terminate && (sc.collisions == CAV_COLLISIONS_EGO || sc.zones)) {
     const DevType<R>& k0 = sc.bodies[0].k;
-    const R th0 = env.s[0][3];
-    const ZoneFrame<R> zf = zone_frame(k0, env.s[0][0], env.s[0][1], env.s[0][2], th0, co[0], si[0], ego_steer);
+    const R th0 = env.s[0][3], c0 = env.cs[0][0], s0 = env.cs[0][1];
+    const ZoneFrame<R> zf = zone_frame(k0, env.s[0][0], env.s[0][1], env.s[0][2], th0, c0, s0, ego_steer);
     const bool have_zones = zf.have;
     Aabb<R> braking_bb = {R(0), R(0), R(0), R(0)}, reaction_bb = braking_bb;
     if (have_zones) {
-      braking_bb = zone_aabb(zf, th0, co[0], si[0], R(0), zf.bd);
-      reaction_bb = zone_aabb(zf, th0, co[0], si[0], zf.bd, zf.td);
+      braking_bb = zone_aabb(zf, th0, c0, s0, R(0), zf.bd);
+      reaction_bb = zone_aabb(zf, th0, c0, s0, zf.bd, zf.td);
     }
     if (sc.collisions == CAV_COLLISIONS_EGO) {
       bool hit = false;
 #pragma unroll
       for (int b = 1; b < M; ++b) {
         if (!(sc.bodies[b].flags & CAV_FLAG_PEDESTRIAN)) continue;
-        const bool near_ego = !aabb_apart(bb[b], bb[0], tau);
-        const bool near_brake = have_zones && !aabb_apart(bb[b], braking_bb, tau);
-        if (near_ego || near_brake) {
-          Quad<R> qb;
-          CAV_BOX(b, qb);
-          bool h = false;
-          if (near_ego) {
-            Quad<R> q0;
-            CAV_BOX(0, q0);
-            h = sat_hit(qb, q0, tau, tangent);
-          }
-          if (!h && near_brake) {
-            Quad<R> braking;
-            zone_quad(zf, th0, co[0], si[0], R(0), zf.bd, braking);
-            h = sat_hit(qb, braking, tau, tangent);
-          }
-          hit |= h;
-        }
+        bool h = false;
+        if (!aabb_apart(bb[b], bb[0], tau))
+          h = geo_hit(sat_pose_pose(body_pose<R, M>(sc, env, b), body_pose<R, M>(sc, env, 0), tau), tangent);
+        if (!h && have_zones && !aabb_apart(bb[b], braking_bb, tau))
+          h = geo_hit(sat_pose_zone(body_pose<R, M>(sc, env, b), zf, th0, c0, s0, R(0), zf.bd, tau), tangent);
+        hit |= h;
       }
       terminate = hit;
     }
@@ -318,10 +285,7 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
         for (int b = 1; b < M; ++b) {
           if (!(sc.bodies[b].flags & CAV_FLAG_PEDESTRIAN) || win_tester >= 0) continue;
           if (!aabb_apart(bb[b], reaction_bb, tau)) {
-            Quad<R> qb, reaction;
-            CAV_BOX(b, qb);
-            zone_quad(zf, th0, co[0], si[0], zf.bd, zf.td, reaction);
-            if (sat_hit(qb, reaction, tau, tangent)) win_tester = b;
+            if (geo_hit(sat_pose_zone(body_pose<R, M>(sc, env, b), zf, th0, c0, s0, zf.bd, zf.td, tau), tangent)) win_tester = b;
           }
         }
       }
@@ -357,7 +321,6 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
   else if (env.t_ep >= sc.max_timesteps) env.done = 2;  // cut off by Simulation.run (simulation.py:69-70), not `done`
   out.terminate = terminate;
   out.tangent = tangent;
-#undef CAV_BOX
 }
 
 // reporting.analyse_episode (reporting.py:227-243) for an env whose episode just ended.
