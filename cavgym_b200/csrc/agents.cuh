@@ -14,6 +14,8 @@ namespace cav {
 // The fp64 libm routines are ~100-instruction sequences: one out-of-line copy each keeps the kernels' hot path small.
 static __device__ __noinline__ void sincos_(double a, double* s, double* c) { sincos(a, s, c); }
 static __device__ __noinline__ void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
+static __device__ __noinline__ double sin_(double a) { return sin(a); }
+static __device__ __noinline__ double cos_(double a) { return cos(a); }
 static __device__ __noinline__ double tan_(double a) { return tan(a); }
 static __device__ __noinline__ float tan_(float a) { return tanf(a); }
 static __device__ __noinline__ double atan2_(double y, double x) { return atan2(y, x); }
@@ -24,9 +26,82 @@ __device__ __forceinline__ bool isnan_(double a) { return isnan(a); }
 __device__ __forceinline__ bool isnan_(float a) { return isnan(a); }
 template <typename R> __device__ __forceinline__ R nan_() { return R(NAN); }
 
+// ---------------------------------------------------------------- trigonometry for the kinematics
+// sin x and cos x - 1 for |x| <= pi/4 (fdlibm kernel polynomials, < 1 ulp), explicit FMAs.  cos x - 1 is returned
+// instead of cos x because the turn below multiplies it by the turn radius (up to 1e14 px for a near-zero steering
+// angle): forming cos x first would lose every digit of the product.
+// Coefficients live in the constant bank (one LDCU.128 per pair) instead of being materialised as immediates.
+static __constant__ double kSinPoly[6] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+                                          -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01};
+static __constant__ double kCosPoly[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+                                          2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+
+__device__ __forceinline__ void sin_cosm1_poly(double x, double& sn, double& cm1) {
+  const double z = x * x;
+  double ps = fma(z, kSinPoly[0], kSinPoly[1]);
+  ps = fma(z, ps, kSinPoly[2]);
+  ps = fma(z, ps, kSinPoly[3]);
+  ps = fma(z, ps, kSinPoly[4]);
+  ps = fma(z, ps, kSinPoly[5]);
+  sn = fma(x * z, ps, x);
+  double pc = fma(z, kCosPoly[0], kCosPoly[1]);
+  pc = fma(z, pc, kCosPoly[2]);
+  pc = fma(z, pc, kCosPoly[3]);
+  pc = fma(z, pc, kCosPoly[4]);
+  pc = fma(z, pc, kCosPoly[5]);
+  cm1 = fma(z * z, pc, -0.5 * z);
+}
+
+static __device__ __noinline__ void sin_cosm1_wide(double x, double* sn, double* cm1) {  // |x| > pi/4: never in practice
+  double h, unused;
+  sincos(x, sn, &unused);
+  h = sin(0.5 * x);
+  *cm1 = -2.0 * h * h;
+}
+
+__device__ __forceinline__ void sin_cosm1(double x, double& sn, double& cm1) {
+  if (fabs(x) <= 0.78539816339744830962) sin_cosm1_poly(x, sn, cm1);
+  else sin_cosm1_wide(x, &sn, &cm1);
+}
+// wheelbase / tan(steer) and 1 / turn radius of the body centre for an arbitrary steering angle
+// (bodies.py:248 tan, :256-262 radius).  The radius is |centre - ICR| = sqrt((wb/2)^2 + (wb/tan)^2) whatever the
+// heading, so no square root of position differences is needed.
+__device__ __forceinline__ void steer_geometry(double wheelbase, double half_wb, double steer, double& kk, double& inv_r) {
+  double sn, cm1, cs;
+  const double a = fabs(steer);
+  if (a <= 0.78539816339744830962) {
+    sin_cosm1_poly(steer, sn, cm1);
+    cs = 1.0 + cm1;
+  } else if (a <= 2.3561944901923448) {  // one quadrant of Cody-Waite reduction: steer = +-pi/2 + r
+    const double k = steer < 0.0 ? -1.0 : 1.0;
+    const double r = fma(-k, 6.123233995736766036e-17, fma(-k, 1.57079632679489655800e+00, steer));
+    double sr, cr1;
+    sin_cosm1_poly(r, sr, cr1);
+    sn = k * (1.0 + cr1);   // sin(k pi/2 + r) = k cos r
+    cs = -k * sr;           // cos(k pi/2 + r) = -k sin r
+  } else {
+    sn = sin_(steer);
+    cs = cos_(steer);
+  }
+  kk = wheelbase * fast_div(cs, sn);
+  inv_r = rsqrt(fma(kk, kk, half_wb * half_wb));
+}
+// atan2(sin(a), cos(a)) (bodies.py:274): a wrapped into [-pi, pi].  One conditional +-2 pi instead of three libm calls;
+// the result is the value the reference's composition approximates to a few ulp.
+template <typename R>
+__device__ __forceinline__ R wrap_angle(R a) {
+  const R pi = R(3.14159265358979323846), two_pi = R(6.28318530717958647692);
+  if (rabs(a) > R(3) * pi) {  // bodies created with headings beyond +-2 pi: general formula
+    R sa, ca;
+    sincos_(a, &sa, &ca);
+    return atan2_(sa, ca);
+  }
+  if (a > pi) return a - two_pi;
+  if (a < -pi) return a + two_pi;
+  return a;
+}
+
 // ---------------------------------------------------------------- kinematics
-// st = x, y, v, theta in/out.  On return c, s = cos/sin of the NEW orientation (what the
-// bounding box needs); `snapped` is the steering angle after the 1e-13 snap (bodies.py:217-218).
 // cos/sin of a heading: exact for 0, looked up (host libm values) for the headings bodies are created with,
 // device sincos otherwise.
 template <typename R>
@@ -40,42 +115,18 @@ __device__ __forceinline__ void heading_cs(const DevScenario<R>& sc, R th, R& c,
   if (!hit) sincos_(th, &s, &c);
 }
 
-// The turning branch of DynamicBody.step (bodies.py:241-275): rotation about the instantaneous centre.  Out of line:
-// only a few percent of the lanes turn in any step.
-template <typename R>
-struct Turned {
-  R x, y, theta, c, s;
-};
-
-template <typename R>
-__device__ __noinline__ Turned<R> turn_step(R wheelbase, R kk_smin, R kk_smax, R smin, R smax, R x, R y, R th, R c, R s, R d, R steer) {
-  const R wbo = wheelbase / R(2);
-  const R rx = x - wbo * c, ry = y - wbo * s;
-  // wheelbase / tan(steer): at full lock (what a crossing agent commands for all but the last step of a turn)
-  // the host-computed value is used, which is also the reference's own libm value
-  R kk;
-  if (steer == smax) kk = kk_smax;
-  else if (steer == smin) kk = kk_smin;
-  else kk = wheelbase / tan_(steer);
-  const R cx = rx - kk * s, cy = ry + kk * c;
-  const R dx = x - cx, dy = y - cy;
-  const R q = d / rsqrt_(dx * dx + dy * dy);
-  const R theta = steer < R(0) ? -q : q;
-  R ct, sn;
-  sincos_(theta, &sn, &ct);
-  Turned<R> out;
-  out.x = cx + dx * ct - dy * sn;
-  out.y = cy + dx * sn + dy * ct;
-  // sin/cos(th + theta) by angle addition from the two sincos in hand (the reference evaluates sin and cos of
-  // the rounded sum; the difference is a few ulp).  They are also cos/sin of the new heading atan2(so, co).
-  out.s = s * ct + c * sn;
-  out.c = c * ct - s * sn;
-  out.theta = atan2_(out.s, out.c);
-  return out;
-}
-
-// c, s: cos/sin of the CURRENT heading on entry (cached in EnvBuffers::cs, refreshed only when the heading
-// changes), cos/sin of the NEW heading on return.  Returns true if the heading changed.
+// DynamicBody.step (bodies.py:214-275).  st = x, y, v, theta in/out.  c, s: cos/sin of the CURRENT heading on entry
+// (cached in EnvBuffers::cs), of the NEW heading on return; `snapped` is the steering angle after the 1e-13 snap
+// (bodies.py:217-218).  Returns true if the heading changed.
+//
+// The turning branch (bodies.py:241-275) rotates the body centre about the instantaneous centre of rotation
+// ICR = rear axle + (wb / tan steer) * left normal by phi = +-distance / |centre - ICR|.  The reference forms the ICR in
+// world coordinates and rotates (centre - ICR); here the same rotation is applied to the body-frame offset
+//   d = centre - ICR = (wb/2) (c, s) + kk (s, -c),   kk = wb / tan steer,   |d|^2 = (wb/2)^2 + kk^2,
+//   centre' = centre + d (cos phi - 1) + d_perp sin phi,
+// which is the same map without the cancellation of two ~kk-sized world coordinates (that cancellation costs the
+// reference ~1e-11 px per step at small steering angles in fp64 and would cost whole pixels in fp32), and without
+// sqrt, division, or atan2: the new heading's cos/sin follow by the angle-addition formulas.
 template <typename R>
 __device__ __forceinline__ bool body_step(const DevType<R>& k, R st[4], R throttle, R steer, R dt, R& c, R& s, R& snapped) {
   if (rabs(steer) < R(0.0000000000001)) steer = R(0);
@@ -88,9 +139,23 @@ __device__ __forceinline__ bool body_step(const DevType<R>& k, R st[4], R thrott
     st[1] = st[1] + d * s;
     return false;
   }
-  const Turned<R> t = turn_step(k.wheelbase, k.kk_smin, k.kk_smax, k.smin, k.smax, st[0], st[1], st[3], c, s, d, steer);
-  st[0] = t.x; st[1] = t.y; st[3] = t.theta;
-  c = t.c; s = t.s;
+  // The turn increment is evaluated in double in BOTH modes: a steering angle is held for many steps, so a few-ulp
+  // float error in wb / tan(steer) would be a systematic heading drift (1e-5 rad over an episode), not a random one.
+  double kk, inv_r;
+  if (steer == k.smax) { kk = k.kk_smax; inv_r = k.inv_r_smax; }
+  else if (steer == k.smin) { kk = k.kk_smin; inv_r = k.inv_r_smin; }
+  else steer_geometry((double)k.wheelbase, (double)k.half_wb, (double)steer, kk, inv_r);
+  const double q = (double)d * inv_r;
+  const double phi = steer < R(0) ? -q : q;
+  double sn_, cm1_;
+  sin_cosm1(phi, sn_, cm1_);
+  const R sn = (R)sn_, cm1 = (R)cm1_;
+  const R dx = k.half_wb * c + (R)kk * s, dy = k.half_wb * s - (R)kk * c;
+  st[0] = st[0] + (dx * cm1 - dy * sn);
+  st[1] = st[1] + (dx * sn + dy * cm1);
+  const R c2 = c + (c * cm1 - s * sn), s2 = s + (s * cm1 + c * sn);
+  c = c2; s = s2;
+  st[3] = wrap_angle(st[3] + (R)phi);
   return true;
 }
 

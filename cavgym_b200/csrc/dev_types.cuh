@@ -4,6 +4,11 @@
 // DevScenario<R> in the engine's arithmetic type R and passed to every kernel BY VALUE
 // as a __grid_constant__ parameter: all threads read it through the constant bank
 // (uniform loads), no global traffic.
+//
+// Rectangles (body boxes, roads, traffic lights, the obstacle, stopping zones) are kept in
+// CENTRE-EXTENT form — centre, unit heading (c, s), half length, half width — because every
+// test of the step (separating axes, road share, finish line) is a handful of dot products in
+// that form; corner lists (Quad) exist only for the general-polygon fallbacks.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -17,13 +22,22 @@ struct Quad {
   R x[4], y[4];  // rear_left, front_left, front_right, rear_right — clockwise (y up)
 };
 
+template <typename R>
+struct Box {  // make_rectangle(2*hl, 2*hw).transform(theta, (px, py)) with c, s = cos/sin(theta)  (geometry.py:241-251)
+  R px, py, c, s, hl, hw;
+};
+
 #define CAV_HEADING_CACHE 4
 
 template <typename R>
 struct DevType {
   R length, width, wheelbase, vmin, vmax, amin, amax, smin, smax;
-  R inv_2brake;  // 1 / (2 * -min_throttle): braking distance = v*v * inv_2brake (bodies.py:123)
-  R kk_smin, kk_smax;  // wheelbase / tan(steering limit), host libm: full-lock turns skip tan and one division
+  R hl, hw;            // half length / half width
+  R half_wb;           // wheelbase / 2 (bodies.py:246: rear axle offset)
+  R inv_2brake;        // 1 / (2 * -min_throttle): braking distance = v*v * inv_2brake (bodies.py:123)
+  // Full-lock turns (what a crossing agent commands for all but the last step of a turn): wheelbase / tan(limit)
+  // and 1 / turn radius of the body centre, host libm values.
+  double kk_smin, kk_smax, inv_r_smin, inv_r_smax;  // double in both modes (see body_step)
 };
 
 template <typename R>
@@ -38,8 +52,7 @@ struct DevBody {
   R threshold;
   R init[4];       // init_state (bodies.py:27); PelicanCrossing: light state in [0]
   DevType<R> k;    // this body's DynamicBodyConstants row, resolved on the host
-  Quad<R> sbox;    // PelicanCrossing static box
-  Aabb<R> sbox_bb;
+  R static_share;  // PelicanCrossing: max over roads of percentage_intersects(static box, road) — a scenario constant
 };
 
 template <typename R>
@@ -55,6 +68,7 @@ template <typename R>
 struct DevScenario {
   int32_t n_bodies, n_types, n_roads, n_statics, n_spawns;
   int32_t collisions, zones, offroad;
+  int32_t homogeneous;  // no PelicanCrossing body, bodies 1.. all Pedestrians, roads axis-aligned: GENERIC = false kernels
   int64_t max_timesteps;
   R reward_win, reward_draw, cost_step, W, dt, v_maint, v_off;
   R inv_W, inv_v_off;  // reciprocals of the two constant divisors on the always-executed path
@@ -62,15 +76,17 @@ struct DevScenario {
   R target_err;  // TARGET_ERROR (dynamic_body.py:8); widened for float
   R cl[4];       // centre line start x,y end x,y
   // Headings bodies are created with (spawn orientations, init orientations): cos/sin evaluated ON THE HOST
-  // with the C library the reference's math.cos/math.sin use, so the common straight-walking case needs no
-  // device sincos and is bit-equal to the reference.
+  // with the C library the reference's math.cos/math.sin use.
   int32_t hc_n, hc_pad;
   R hc_theta[CAV_HEADING_CACHE], hc_cos[CAV_HEADING_CACHE], hc_sin[CAV_HEADING_CACHE];
-  Quad<R> roads[CAV_MAX_ROADS];
   Aabb<R> road_bb[CAV_MAX_ROADS];
-  int32_t road_axis[CAV_MAX_ROADS];  // 1 if the road rectangle is exactly axis-aligned (road == its AABB)
-  Quad<R> statics[CAV_MAX_STATICS];
+  Box<R> road_box[CAV_MAX_ROADS];
+  int32_t road_axis[CAV_MAX_ROADS];   // 1 if the road rectangle is exactly axis-aligned (road == its AABB)
+  int32_t road_rect[CAV_MAX_ROADS];   // 1 if the road quad is a rectangle (road_box valid)
   Aabb<R> static_bb[CAV_MAX_STATICS];
+  Box<R> static_box[CAV_MAX_STATICS];
+  int32_t static_rect[CAV_MAX_STATICS];
+  const Quad<R>* quads;  // device: roads[CAV_MAX_ROADS] then statics[CAV_MAX_STATICS] as corner lists (general fallbacks)
   DevBody<R> bodies[CAV_SMALL_M];
 };
 

@@ -80,9 +80,37 @@ static Aabb<R> host_aabb(const Quad<R>& q) {
 
 template <typename R>
 static DevType<R> to_type(const CavBodyType& t) {
-  return {(R)t.length, (R)t.width, (R)t.wheelbase, (R)t.min_velocity, (R)t.max_velocity, (R)t.min_throttle,
-          (R)t.max_throttle, (R)t.min_steering_angle, (R)t.max_steering_angle, (R)(1.0 / (2.0 * -t.min_throttle)),
-          (R)(t.wheelbase / std::tan((double)(R)t.min_steering_angle)), (R)(t.wheelbase / std::tan((double)(R)t.max_steering_angle))};
+  DevType<R> k;
+  k.length = (R)t.length; k.width = (R)t.width; k.wheelbase = (R)t.wheelbase;
+  k.vmin = (R)t.min_velocity; k.vmax = (R)t.max_velocity; k.amin = (R)t.min_throttle; k.amax = (R)t.max_throttle;
+  k.smin = (R)t.min_steering_angle; k.smax = (R)t.max_steering_angle;
+  k.hl = (R)(t.length * 0.5); k.hw = (R)(t.width * 0.5); k.half_wb = (R)(t.wheelbase / 2.0);
+  k.inv_2brake = (R)(1.0 / (2.0 * -t.min_throttle));
+  const double half_wb = t.wheelbase / 2.0;
+  const double kk_min = t.wheelbase / std::tan((double)k.smin), kk_max = t.wheelbase / std::tan((double)k.smax);
+  k.kk_smin = kk_min; k.kk_smax = kk_max;
+  k.inv_r_smin = 1.0 / std::sqrt(half_wb * half_wb + kk_min * kk_min);
+  k.inv_r_smax = 1.0 / std::sqrt(half_wb * half_wb + kk_max * kk_max);
+  return k;
+}
+
+// Centre-extent form of a quad that is a rectangle (every road, traffic light and obstacle of the reference is one:
+// make_rectangle(...).transform(...), assets.py / bodies.py); false for a general convex quad.
+template <typename R>
+static bool to_box(const Quad<R>& q, Box<R>& out) {
+  const double ux = (double)q.x[1] - q.x[0], uy = (double)q.y[1] - q.y[0];   // rear_left -> front_left: the heading
+  const double vx = (double)q.x[3] - q.x[0], vy = (double)q.y[3] - q.y[0];   // rear_left -> rear_right: across
+  const double lu = std::sqrt(ux * ux + uy * uy), lv = std::sqrt(vx * vx + vy * vy);
+  if (!(lu > 0.0) || !(lv > 0.0)) return false;
+  const double scale = lu + lv, eps = (sizeof(R) == 8 ? 1e-12 : 1e-5) * scale;
+  const double px = (double)q.x[0] + ux + vx - q.x[2], py = (double)q.y[0] + uy + vy - q.y[2];  // parallelogram closure
+  if (std::fabs(px) > eps || std::fabs(py) > eps) return false;
+  if (std::fabs(ux * vx + uy * vy) > eps * scale) return false;                                    // right angle
+  out.px = (R)(((double)q.x[0] + q.x[1] + q.x[2] + q.x[3]) * 0.25);
+  out.py = (R)(((double)q.y[0] + q.y[1] + q.y[2] + q.y[3]) * 0.25);
+  out.c = (R)(ux / lu); out.s = (R)(uy / lu);
+  out.hl = (R)(lu * 0.5); out.hw = (R)(lv * 0.5);
+  return true;
 }
 
 template <typename R>
@@ -99,16 +127,22 @@ static void convert(const CavScenario& in, double tau, DevScenario<R>& out) {
   out.tau = (R)tau;
   out.target_err = sizeof(R) == 8 ? (R)0.000000000000001 : (R)1e-6;  // dynamic_body.py:8; one float ulp at pi/2 is 1.2e-7
   for (int i = 0; i < 4; ++i) out.cl[i] = (R)in.centre_line[i];
+  Quad<R> roads[CAV_MAX_ROADS];
   for (int i = 0; i < in.n_roads; ++i) {
-    out.roads[i] = to_quad<R>(in.roads[i]);
-    out.road_bb[i] = host_aabb(out.roads[i]);
+    roads[i] = to_quad<R>(in.roads[i]);
+    out.road_bb[i] = host_aabb(roads[i]);
     bool axis = true;  // every corner lies on a corner of the AABB
     for (int c = 0; c < 4; ++c)
-      axis = axis && (out.roads[i].x[c] == out.road_bb[i].x0 || out.roads[i].x[c] == out.road_bb[i].x1) &&
-             (out.roads[i].y[c] == out.road_bb[i].y0 || out.roads[i].y[c] == out.road_bb[i].y1);
+      axis = axis && (roads[i].x[c] == out.road_bb[i].x0 || roads[i].x[c] == out.road_bb[i].x1) &&
+             (roads[i].y[c] == out.road_bb[i].y0 || roads[i].y[c] == out.road_bb[i].y1);
     out.road_axis[i] = axis ? 1 : 0;
+    out.road_rect[i] = to_box(roads[i], out.road_box[i]) ? 1 : 0;
   }
-  for (int i = 0; i < in.n_statics; ++i) { out.statics[i] = to_quad<R>(in.statics[i]); out.static_bb[i] = host_aabb(out.statics[i]); }
+  for (int i = 0; i < in.n_statics; ++i) {
+    const Quad<R> q = to_quad<R>(in.statics[i]);
+    out.static_bb[i] = host_aabb(q);
+    out.static_rect[i] = to_box(q, out.static_box[i]) ? 1 : 0;
+  }
   for (int b = 0; b < in.n_bodies && b < CAV_SMALL_M; ++b) {
     const CavBody& src = in.bodies[b];
     DevBody<R>& dst = out.bodies[b];
@@ -116,9 +150,23 @@ static void convert(const CavScenario& in, double tau, DevScenario<R>& out) {
     dst.epsilon = src.agent_epsilon; dst.threshold = (R)src.agent_threshold;
     for (int c = 0; c < 4; ++c) dst.init[c] = (R)src.init_state[c];
     if (src.kind == CAV_BODY_DYNAMIC) dst.k = to_type<R>(in.types[src.type_id]);
-    dst.sbox = to_quad<R>(src.static_box);
-    dst.sbox_bb = host_aabb(dst.sbox);
+    if (src.kind == CAV_BODY_PELICAN) {  // percentage_intersects(static box, road) never changes: environment.py:141
+      const Quad<R> box = to_quad<R>(src.static_box);
+      R share = (R)0;
+      for (int r = 0; r < in.n_roads; ++r) {
+        const R q = percentage_of(box, roads[r], (R)tau).value;
+        if (r == 0 || q > share) share = q;
+      }
+      dst.static_share = share;
+    }
   }
+  bool homogeneous = in.n_bodies <= CAV_SMALL_M;
+  for (int i = 0; i < in.n_roads; ++i) homogeneous = homogeneous && out.road_axis[i] && out.road_rect[i];
+  for (int b = 0; b < in.n_bodies && b < CAV_SMALL_M; ++b) {
+    homogeneous = homogeneous && in.bodies[b].kind == CAV_BODY_DYNAMIC;
+    if (b > 0) homogeneous = homogeneous && (in.bodies[b].flags & CAV_FLAG_PEDESTRIAN);
+  }
+  out.homogeneous = homogeneous ? 1 : 0;
   // heading cache: orientations bodies start with, cos/sin from the host C library (what math.cos/math.sin call)
   auto remember = [&out](double theta) {
     const R th = (R)theta;
@@ -204,7 +252,7 @@ __global__ void geometry_probe_kernel(const R* qa, const R* qb, R* out, int64_t 
   R share = R(0);
   if (hit) inside = contains(B, A, tau, tangent);
   if (!(aabb_gap(aabb_of(A), aabb_of(B)) > tau)) {
-    const Share<R> sh = percentage_intersects(A, B, tau);
+    const Share<R> sh = percentage_of(A, B, tau);
     share = sh.value;
     tangent |= sh.tangent != 0;
   }
@@ -240,6 +288,7 @@ struct CavEngine {
   uint8_t *d_done = nullptr, *d_tangent = nullptr;
   int32_t* d_winner = nullptr;
   unsigned long long* d_scratch = nullptr;
+  void* d_quads = nullptr;  // Quad<R>[CAV_MAX_ROADS + CAV_MAX_STATICS] in the engine's type: corner lists for the general fallbacks
 
   size_t real_size() const { return dtype == CAV_F64 ? 8 : 4; }
 };
@@ -277,12 +326,22 @@ static int setup_buffers(CavEngine* eng, EnvBuffers<R>& buf) {
   if ((rc = dev_alloc(eng, &d_spawns, spawns.size() ? spawns.size() : 1))) return rc;
   if (!spawns.empty()) CUDA_TRY(cudaMemcpy(d_spawns, spawns.data(), spawns.size() * sizeof(DevSpawn<R>), cudaMemcpyHostToDevice));
   buf.spawns = d_spawns;
+  Quad<R> quads[CAV_MAX_ROADS + CAV_MAX_STATICS];
+  std::memset(quads, 0, sizeof(quads));
+  for (int i = 0; i < eng->host.n_roads; ++i) quads[i] = to_quad<R>(eng->host.roads[i]);
+  for (int i = 0; i < eng->host.n_statics; ++i) quads[CAV_MAX_ROADS + i] = to_quad<R>(eng->host.statics[i]);
+  Quad<R>* d_quads = nullptr;
+  if ((rc = dev_alloc(eng, &d_quads, CAV_MAX_ROADS + CAV_MAX_STATICS))) return rc;
+  CUDA_TRY(cudaMemcpy(d_quads, quads, sizeof(quads), cudaMemcpyHostToDevice));
+  eng->d_quads = d_quads;
   return CAV_OK;
 }
 
 static void rebuild_tables(CavEngine* eng) {
   convert<double>(eng->host, eng->tau, eng->sc64);
   convert<float>(eng->host, eng->tau, eng->sc32);
+  eng->sc64.quads = (const Quad<double>*)eng->d_quads;  // only the table of the engine's own type is dereferenced
+  eng->sc32.quads = (const Quad<float>*)eng->d_quads;
 }
 
 static int check_engine(CavEngine* eng) {
@@ -350,7 +409,7 @@ int cavgym_create(const CavScenario* tables, int64_t n_envs, int dtype, int devi
   }
   rebuild_tables(eng);
   int rc = dtype == CAV_F64 ? setup_buffers(eng, eng->buf64) : setup_buffers(eng, eng->buf32);
-  if (rc == CAV_OK) rc = dev_alloc(eng, &eng->d_scratch, 2);
+  if (rc == CAV_OK) { rebuild_tables(eng); rc = dev_alloc(eng, &eng->d_scratch, 2); }
   if (rc == CAV_OK) rc = do_reset(eng, nullptr, nullptr, 1, nullptr);  // constructor-time spawn (bodies.py:296)
   if (rc == CAV_OK) {
     cudaError_t err = cudaDeviceSynchronize();

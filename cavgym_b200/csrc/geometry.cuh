@@ -1,38 +1,140 @@
-// geometry.cuh — oriented boxes, stopping zones, separating-axis test, containment and
-// convex clipping on device.  Replaces the Shapely bridge of the reference
+// geometry.cuh — oriented boxes, stopping zones, separating-axis tests, containment and
+// convex clipping.  Replaces the Shapely bridge of the reference
 // (library/geometry.py:74-87 Shape.intersects / contains / percentage_intersects),
 // make_rectangle + transform (geometry.py:241-251,117-126) and DynamicBody.stopping_zones
 // (library/bodies.py:122-135).
 //
-// All quads are clockwise (rear_left, front_left, front_right, rear_right with x forward,
-// y left), so a point is OUTSIDE edge i->j when cross(e, p - a) > 0.  Predicates are closed:
-// touching counts as intersecting (Shapely semantics).  Every predicate also reports whether
-// its decision margin is within `tau` pixels of zero (near-tangent flag, north star).
+// Two representations:
+//  * Box<R> (centre, unit heading, half extents): every rectangle-vs-rectangle test of a step.
+//    The separating-axis test is four |T.L| - (ra + rb) margins, the share of a box lying on an
+//    axis-aligned road across one kerb is the closed-form area of a rectangle cut by a half-plane.
+//    Branch-free, registers only: this is the always-executed path.
+//  * Quad<R> (corner lists, clockwise): general convex quads — non-rectangular statics, rotated
+//    roads, road corners, the stand-alone geometry probe.  Out of line, rare.
+// Predicates are closed: touching counts as intersecting (Shapely semantics).  Every predicate
+// also reports whether its decision margin is within `tau` pixels of zero (near-tangent flag).
 #pragma once
+#include <cmath>
+
 #include "dev_types.cuh"
+
+#define CAV_HD __host__ __device__ __forceinline__
 
 namespace cav {
 
 // a / b to ~2 ulp with a float reciprocal seed and two Newton steps (10 instructions instead of the ~60 of the
-// IEEE division subroutine).  Used only for quantities that feed rewards and flagged predicates, never body state;
-// |b| must be a normal float (here: pixel distances).
+// IEEE division subroutine).  Used only where |b| is a normal float (pixel distances, sines of steering angles).
 __device__ __forceinline__ double fast_div(double a, double b) {
   double r = (double)__frcp_rn((float)b);
-  r = r * (2.0 - b * r);
-  r = r * (2.0 - b * r);
-  return a * r;
+  r = fma(r, fma(-b, r, 1.0), r);
+  r = fma(r, fma(-b, r, 1.0), r);
+  const double q = a * r;
+  return fma(r, fma(-b, q, a), q);  // one residual correction of the quotient: <= 1 ulp
 }
 __device__ __forceinline__ float fast_div(float a, float b) { return a / b; }
 
-template <typename R> __device__ __forceinline__ R rmin(R a, R b) { return b < a ? b : a; }
-template <typename R> __device__ __forceinline__ R rmax(R a, R b) { return b > a ? b : a; }
-__device__ __forceinline__ double rsqrt_(double v) { return sqrt(v); }
-__device__ __forceinline__ float rsqrt_(float v) { return sqrtf(v); }
-__device__ __forceinline__ double rabs(double v) { return fabs(v); }
-__device__ __forceinline__ float rabs(float v) { return fabsf(v); }
+template <typename R> CAV_HD R rmin(R a, R b) { return b < a ? b : a; }
+template <typename R> CAV_HD R rmax(R a, R b) { return b > a ? b : a; }
+CAV_HD double rsqrt_(double v) { return sqrt(v); }
+CAV_HD float rsqrt_(float v) { return sqrtf(v); }
+CAV_HD double rabs(double v) { return fabs(v); }
+CAV_HD float rabs(float v) { return fabsf(v); }
+
+// ================================================================ centre-extent boxes (hot path)
+
+// Half extents of the axis-aligned bounding box of a rotated rectangle: |c|hl + |s|hw, |s|hl + |c|hw.
+template <typename R>
+__device__ __forceinline__ void box_extents(R c, R s, R hl, R hw, R& ex, R& ey) {
+  const R ac = rabs(c), as = rabs(s);
+  ex = ac * hl + as * hw;
+  ey = as * hl + ac * hw;
+}
+
+// Largest separating-axis margin of two oriented rectangles over their four edge normals:
+//   margin_L = |T . L| - (radius_a(L) + radius_b(L)),   T = centre_b - centre_a.
+// > 0: some axis separates them (disjoint).  <= 0: they intersect (closed).  |margin| < tau: near-tangent.
+template <typename R>
+__device__ __forceinline__ R box_margin(const Box<R>& a, const Box<R>& b) {
+  const R tx = b.px - a.px, ty = b.py - a.py;
+  const R cd = a.c * b.c + a.s * b.s, sd = a.c * b.s - a.s * b.c;  // cos / sin of the relative heading
+  const R acd = rabs(cd), asd = rabs(sd);
+  const R m1 = rabs(tx * a.c + ty * a.s) - (a.hl + (acd * b.hl + asd * b.hw));
+  const R m2 = rabs(ty * a.c - tx * a.s) - (a.hw + (asd * b.hl + acd * b.hw));
+  const R m3 = rabs(tx * b.c + ty * b.s) - (b.hl + (acd * a.hl + asd * a.hw));
+  const R m4 = rabs(ty * b.c - tx * b.s) - (b.hw + (asd * a.hl + acd * a.hw));
+  return rmax(rmax(m1, m2), rmax(m3, m4));
+}
+
+// A pedestrian box against the ego's box and its two stopping zones in ONE pass.  The zones are rectangles in the
+// ego's frame laid end to end from the front-centre anchor (bodies.py:122-135, geometry.py:176-191): braking
+// [hl0, hl0 + bd], reaction [hl0 + bd, hl0 + td] along the heading, the ego's width across.  All three tests share the
+// relative pose; each costs three more margins.  (The reference interpolates the split corners with p = bd / td —
+// identical up to a few ulp, far inside tau.)
+template <typename R>
+struct EgoFrame {
+  R x, y, c, s, hl, hw;  // ego pose
+  R bd, td;              // braking and total stopping distance
+  bool have;             // zones exist: td != 0 and the ego is not steering (bodies.py:130-135)
+};
 
 template <typename R>
-__device__ __forceinline__ Aabb<R> aabb_of(const Quad<R>& q) {
+struct EgoMargins {
+  R ego, braking, reaction;  // largest separating-axis margin against each rectangle
+  bool all_clear;            // every rectangle is separated from the pedestrian by tau or more (the common case)
+};
+
+template <typename R>
+__device__ __forceinline__ EgoMargins<R> ego_margins(const EgoFrame<R>& f, R px, R py, R cb, R sb, R hlb, R hwb, R tau) {
+  const R tx = px - f.x, ty = py - f.y;
+  const R cd = f.c * cb + f.s * sb, sd = f.c * sb - f.s * cb;
+  const R acd = rabs(cd), asd = rabs(sd);
+  const R u = tx * f.c + ty * f.s, w = ty * f.c - tx * f.s;    // pedestrian centre in the ego frame
+  const R tp = tx * cb + ty * sb, tq = ty * cb - tx * sb;      // ego centre offset in the pedestrian frame
+  const R exb = acd * hlb + asd * hwb, eyb = asd * hlb + acd * hwb;
+  const R lateral = rabs(w) - (f.hw + eyb);                    // same for all three rectangles
+  const R rp = hlb + asd * f.hw, rq = hwb + acd * f.hw;        // pedestrian-axis radii without the length term
+  EgoMargins<R> out;
+  // The strip [-hl, hl + td] x [-hw, hw] contains all three rectangles: being clear of it laterally, or beyond either
+  // end along the heading, settles all three tests at once (f.td = 0 leaves the ego box alone).
+  const R reach = f.have ? f.td : R(0);
+  const R along = rmax(-f.hl - u, u - (f.hl + reach)) - exb;
+  out.all_clear = (lateral >= tau) || (along >= tau);
+  out.ego = out.braking = out.reaction = R(1);
+  if (!out.all_clear) {
+    auto margin = [&](R centre, R half) {
+      const R mx = rabs(u - centre) - (half + exb);
+      const R m3 = rabs(tp - centre * cd) - (rp + acd * half);
+      const R m4 = rabs(tq + centre * sd) - (rq + asd * half);
+      return rmax(rmax(lateral, mx), rmax(m3, m4));
+    };
+    out.ego = margin(R(0), f.hl);
+    const R hb = f.bd * R(0.5), hr = (f.td - f.bd) * R(0.5);
+    out.braking = margin(f.hl + hb, hb);
+    out.reaction = margin(f.hl + f.bd + hr, hr);
+  }
+  return out;
+}
+
+// Fraction of a rectangle on the inner side of a line, as a function of the signed distance t of its centre from
+// the line (t > 0 inside) and the projections u, w >= 0 of its two half-edge vectors on the line's normal.  The
+// signed distance of a uniformly distributed point of the rectangle is t + U(-u, u) + U(-w, w), so the fraction is the
+// CDF of a trapezoidal distribution: quadratic while only one corner has crossed, linear in between.
+// This is Shape.percentage_intersects (geometry.py:80-87) for a body box across ONE edge of an axis-aligned road.
+template <typename R>
+__device__ __forceinline__ R kerb_share(R t, R u, R w) {
+  const R A = rmax(u, w), B = rmin(u, w), D = A - B, S = A + B;
+  const bool corner = (rabs(t) > D) && (B > R(0));
+  const R q = rmax(R(0), S - rabs(t));
+  const R num = corner ? q * q : rmax(R(0), rmin(A + A, t + A));
+  const R den = corner ? R(8) * (A * B) : A + A;
+  const R f = fast_div(num, den);
+  return (corner && t > R(0)) ? R(1) - f : f;
+}
+
+// ================================================================ general convex quads (rare paths)
+
+template <typename R>
+CAV_HD Aabb<R> aabb_of(const Quad<R>& q) {
   Aabb<R> b;
   b.x0 = rmin(rmin(q.x[0], q.x[1]), rmin(q.x[2], q.x[3]));
   b.x1 = rmax(rmax(q.x[0], q.x[1]), rmax(q.x[2], q.x[3]));
@@ -43,36 +145,14 @@ __device__ __forceinline__ Aabb<R> aabb_of(const Quad<R>& q) {
 
 // Largest axis-aligned gap between two boxes (> 0 means disjoint along x or y).
 template <typename R>
-__device__ __forceinline__ R aabb_gap(const Aabb<R>& a, const Aabb<R>& b) {
+CAV_HD R aabb_gap(const Aabb<R>& a, const Aabb<R>& b) {
   return rmax(rmax(a.x0 - b.x1, b.x0 - a.x1), rmax(a.y0 - b.y1, b.y0 - a.y1));
-}
-
-// aabb_gap(a, b) > tau without the max tree: four subtractions and compares.  True means the polygons inside the
-// boxes are certainly disjoint, with a safety margin of tau >> rounding error (so no near-tangent flag is needed).
-template <typename R>
-__device__ __forceinline__ bool aabb_apart(const Aabb<R>& a, const Aabb<R>& b, R tau) {
-  return (a.x0 - b.x1 > tau) || (b.x0 - a.x1 > tau) || (a.y0 - b.y1 > tau) || (b.y0 - a.y1 > tau);
-}
-
-// AABB of make_rectangle(length, width).transform(theta, p) from the half extents |c|hl + |s|hw, |s|hl + |c|hw
-// (no corner min/max tree).  For theta == 0 it equals the corner AABB bit for bit; otherwise within a few ulp,
-// far inside the tau margin every consumer applies.
-template <typename R>
-__device__ __forceinline__ Aabb<R> box_aabb(R length, R width, R theta, R c, R s, R px, R py) {
-  const R hl = length * R(0.5), hw = width * R(0.5);
-  R ex = hl, ey = hw;
-  if (!(theta == R(0))) {
-    const R ac = rabs(c), as = rabs(s);
-    ex = ac * hl + as * hw;
-    ey = as * hl + ac * hw;
-  }
-  return {px - ex, px + ex, py - ey, py + ey};
 }
 
 // make_rectangle(length, width) . transform(theta, (px, py)); c, s = cos/sin(theta).
 // theta == 0 takes the reference's translate-only path (geometry.py:118-119) bit for bit.
 template <typename R>
-__device__ __forceinline__ void make_box(R length, R width, R theta, R c, R s, R px, R py, Quad<R>& q) {
+CAV_HD void make_box(R length, R width, R theta, R c, R s, R px, R py, Quad<R>& q) {
   const R hl = length * R(0.5), hw = width * R(0.5);
   const R lx[4] = {-hl, hl, hl, -hl};
   const R ly[4] = {hw, hw, -hw, -hw};
@@ -88,54 +168,6 @@ __device__ __forceinline__ void make_box(R length, R width, R theta, R c, R s, R
   }
 }
 
-// DynamicBody.stopping_zones + split_longitudinally (bodies.py:122-135, geometry.py:176-191).
-// The braking/reaction split is built directly (rectangles of length bd and rd laid end to end from the
-// front-centre anchor) instead of by interpolating with p = bd / td: algebraically identical, no division on the
-// always-executed path, corners within a few ulp of the reference's.  The oracle keeps the reference's form.
-template <typename R>
-struct ZoneFrame {
-  bool have;
-  R ax, ay, bd, td, hw;  // anchor (front centre), braking and total distance, half width
-};
-
-template <typename R>
-__device__ __forceinline__ ZoneFrame<R> zone_frame(const DevType<R>& k, R x, R y, R v, R theta, R c, R s, R steer) {
-  ZoneFrame<R> z;
-  z.bd = (v * v) * k.inv_2brake;
-  z.td = z.bd + v * R(0.675);
-  z.have = !(z.td == R(0)) && (steer == R(0));
-  const R hx = k.length * R(0.5);
-  z.hw = k.width * R(0.5);
-  if (theta == R(0)) { z.ax = x + hx; z.ay = y; }
-  else { z.ax = x + c * hx; z.ay = y + s * hx; }
-  return z;
-}
-
-// Rectangle spanning local x in [x0, x1], y in [-hw, +hw] of the zone frame, corners RL, FL, FR, RR.
-template <typename R>
-__device__ __forceinline__ void zone_quad(const ZoneFrame<R>& z, R theta, R c, R s, R x0, R x1, Quad<R>& q) {
-  const R lx[4] = {x0, x1, x1, x0};
-  const R ly[4] = {z.hw, z.hw, -z.hw, -z.hw};
-  if (theta == R(0)) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { q.x[i] = z.ax + lx[i]; q.y[i] = z.ay + ly[i]; }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      q.x[i] = z.ax + ((c * lx[i]) - (s * ly[i]));
-      q.y[i] = z.ay + ((s * lx[i]) + (c * ly[i]));
-    }
-  }
-}
-
-template <typename R>
-__device__ __forceinline__ Aabb<R> zone_aabb(const ZoneFrame<R>& z, R theta, R c, R s, R x0, R x1) {
-  if (theta == R(0)) return {z.ax + x0, z.ax + x1, z.ay - z.hw, z.ay + z.hw};
-  Quad<R> q;
-  zone_quad(z, theta, c, s, x0, x1, q);
-  return aabb_of(q);
-}
-
 // Separating-axis bookkeeping without square roots or divisions.  For edge i of A let m_i be the smallest
 // cross(e_i, p - a_i) over the vertices p of B (> 0 means all of B strictly outside that edge line) and
 // near_i <=> |m_i| < tau * |e_i|  <=>  m_i^2 < tau^2 |e_i|^2.
@@ -145,7 +177,7 @@ __device__ __forceinline__ Aabb<R> zone_aabb(const ZoneFrame<R>& z, R theta, R c
 enum { SEP_CLEAR = 1, SEP_ANY = 2, NEAR_ANY = 4 };
 
 template <typename R>
-__device__ __forceinline__ int separation_bits(const Quad<R>& A, const Quad<R>& B, R tau2) {
+CAV_HD int separation_bits(const Quad<R>& A, const Quad<R>& B, R tau2) {
   int bits = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -164,15 +196,13 @@ __device__ __forceinline__ int separation_bits(const Quad<R>& A, const Quad<R>& 
   return bits;
 }
 
-// Result of a rare-path predicate: bit 0 = predicate holds, bit 1 = decision margin within tau (near-tangent).
+// Result of a predicate: bit 0 = predicate holds, bit 1 = decision margin within tau (near-tangent).
 enum { GEO_HIT = 1, GEO_TANGENT = 2 };
 
-// Full separating-axis test (8 edge normals).  Rare path, called only when the AABBs overlap.  Quads are passed
-// BY VALUE so that the caller's copies are never address-taken and stay in registers on the common path.
-// Near-tangent <=> the largest normalised margin lies in (-tau, tau) <=> no edge separates clearly and
-// some edge is within tau of touching.
+// Full separating-axis test on corner lists (8 edge normals).  Near-tangent <=> the largest normalised margin lies
+// in (-tau, tau) <=> no edge separates clearly and some edge is within tau of touching.
 template <typename R>
-__device__ __noinline__ int sat_intersects(Quad<R> A, Quad<R> B, R tau) {
+CAV_HD int sat_bits(const Quad<R>& A, const Quad<R>& B, R tau) {
   const int bits = separation_bits(A, B, tau * tau) | separation_bits(B, A, tau * tau);
   const bool hit = !(bits & SEP_ANY);
   const bool tangent = !(bits & SEP_CLEAR) && (bits & NEAR_ANY);
@@ -181,10 +211,9 @@ __device__ __noinline__ int sat_intersects(Quad<R> A, Quad<R> B, R tau) {
 
 // Shape.intersects for two convex quads.  AABB rejection first: exact and conservative.
 template <typename R>
-__device__ __forceinline__ bool intersects(const Quad<R>& A, const Aabb<R>& a, const Quad<R>& B, const Aabb<R>& b, R tau,
-                                           bool& tangent) {
+CAV_HD bool intersects(const Quad<R>& A, const Aabb<R>& a, const Quad<R>& B, const Aabb<R>& b, R tau, bool& tangent) {
   if (aabb_gap(a, b) > tau) return false;
-  const int r = sat_intersects(A, B, tau);
+  const int r = sat_bits(A, B, tau);
   if (r & GEO_TANGENT) tangent = true;
   return (r & GEO_HIT) != 0;
 }
@@ -192,7 +221,7 @@ __device__ __forceinline__ bool intersects(const Quad<R>& A, const Aabb<R>& a, c
 // outer.contains(inner): every vertex of inner inside or on every edge of outer.  Near-tangent when the
 // worst vertex is within tau of some edge line (compared without sqrt: m^2 < tau^2 |e|^2).
 template <typename R>
-__device__ __forceinline__ bool contains(const Quad<R>& outer, const Quad<R>& inner, R tau, bool& tangent) {
+CAV_HD bool contains(const Quad<R>& outer, const Quad<R>& inner, R tau, bool& tangent) {
   bool inside = true, clear_out = false, near = false;
   const R tau2 = tau * tau;
 #pragma unroll
@@ -214,7 +243,7 @@ __device__ __forceinline__ bool contains(const Quad<R>& outer, const Quad<R>& in
 }
 
 template <typename R>
-__device__ __forceinline__ R quad_area(const Quad<R>& q) {
+CAV_HD R quad_area(const Quad<R>& q) {
   R a = R(0);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -225,9 +254,9 @@ __device__ __forceinline__ R quad_area(const Quad<R>& q) {
 }
 
 // area(subject ∩ clip) by Sutherland–Hodgman; stands for Shapely's intersection(...).area.
-// Rare path (a box straddling a road edge): vertex lists live in local memory.
+// Vertex lists live in local memory: rare path only.
 template <typename R>
-__device__ __noinline__ R clip_area(const Quad<R>& subject, const Quad<R>& clip) {
+__host__ __device__ inline R clip_area(const Quad<R>& subject, const Quad<R>& clip) {
   R sx[8], sy[8], ox[8], oy[8];
   int n = 4;
   for (int i = 0; i < 4; ++i) { sx[i] = subject.x[i]; sy[i] = subject.y[i]; }
@@ -262,7 +291,6 @@ __device__ __noinline__ R clip_area(const Quad<R>& subject, const Quad<R>& clip)
 }
 
 // Shape.percentage_intersects (geometry.py:80-87): share of `self` lying on `other`.
-// Callers reject AABB-disjoint pairs first, so this is the rare path (by-value arguments, see sat_intersects).
 template <typename R>
 struct Share {
   R value;
@@ -270,7 +298,7 @@ struct Share {
 };
 
 template <typename R>
-__device__ __noinline__ Share<R> percentage_intersects(Quad<R> self, Quad<R> other, R tau) {
+__host__ __device__ inline Share<R> percentage_of(const Quad<R>& self, const Quad<R>& other, R tau) {
   Share<R> out;
   bool tangent = false;
   const int bits = separation_bits(self, other, tau * tau) | separation_bits(other, self, tau * tau);
@@ -282,124 +310,32 @@ __device__ __noinline__ Share<R> percentage_intersects(Quad<R> self, Quad<R> oth
   return out;
 }
 
-// Area of the part of a convex quad inside ONE half-plane {p : nx*x + ny*y <= bound}, by a single
-// Sutherland–Hodgman stage with a running shoelace sum (no vertex list, registers only).  This is the
-// kerb-crossing case: a body box straddling exactly one edge of an axis-aligned road rectangle, where (nx, ny) is
-// (+-1, 0) or (0, +-1) and the products are exact.
-template <typename R>
-__device__ __forceinline__ R halfplane_area(const Quad<R>& q, R nx, R ny, R bound) {
-  R d[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) d[i] = bound - (nx * q.x[i] + ny * q.y[i]);  // >= 0 inside
-  R acc = R(0), fx = R(0), fy = R(0), px = R(0), py = R(0);
-  bool have = false;
-  auto emit = [&](R x, R y) {
-    if (have) acc += px * y - x * py;
-    else { fx = x; fy = y; have = true; }
-    px = x; py = y;
-  };
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int j = (i + 1) & 3;
-    if (d[i] >= R(0)) emit(q.x[i], q.y[i]);
-    if ((d[i] > R(0) && d[j] < R(0)) || (d[i] < R(0) && d[j] > R(0))) {
-      const R t = fast_div(d[i], d[i] - d[j]);
-      emit(q.x[i] + t * (q.x[j] - q.x[i]), q.y[i] + t * (q.y[j] - q.y[i]));
-    }
-  }
-  if (have) acc += px * fy - fx * py;
-  return rabs(acc) * R(0.5);
-}
-
-// How a body-box AABB sits on an EXACTLY axis-aligned road rectangle (road == road_bb); callers have already
-// rejected boxes that are clearly apart.  Margins m >= tau mean "clearly inside that edge".
-//   AXIS_INSIDE    clearly inside all four edges                       -> share 1
-//   AXIS_ONE_EDGE  clearly across exactly one edge, inside the others  -> single half-plane clip (the kerb)
-//   AXIS_GENERAL   road corner or within tau of an edge                -> general predicates
-enum { AXIS_INSIDE = 0, AXIS_ONE_EDGE = 1, AXIS_GENERAL = 2 };
-
-template <typename R>
-__device__ __forceinline__ int axis_case(const Aabb<R>& bb, const Aabb<R>& road, R tau) {
-  const R m0 = bb.x0 - road.x0, m1 = road.x1 - bb.x1, m2 = bb.y0 - road.y0, m3 = road.y1 - bb.y1;
-  const int out = (m0 < tau) + (m1 < tau) + (m2 < tau) + (m3 < tau);
-  if (out == 0) return AXIS_INSIDE;
-  const int across = (m0 <= -tau) + (m1 <= -tau) + (m2 <= -tau) + (m3 <= -tau);
-  return (out == 1 && across == 1) ? AXIS_ONE_EDGE : AXIS_GENERAL;
-}
-
-// ---------------------------------------------------------------- out-of-line rare paths
-// Everything below is __noinline__ and takes small by-value arguments: the always-executed path of a step stays a
-// few KB of straight-line code (it must fit the instruction caches), and the rare geometry lives once per kernel.
+// ---------------------------------------------------------------- out-of-line device entry points for the rare paths
+// __noinline__ with small by-value arguments: the always-executed path of a step stays compact straight-line code and
+// the general-polygon machinery exists once per kernel.
 
 template <typename R>
 struct Pose {  // what is needed to rebuild a body's corners: make_rectangle(length, width).transform(theta, (x, y))
   R x, y, theta, c, s, length, width;
 };
 
-template <typename R>
-__device__ __forceinline__ void pose_quad(const Pose<R>& p, Quad<R>& q) {
-  make_box(p.length, p.width, p.theta, p.c, p.s, p.x, p.y, q);
-}
-
-// body box vs body box
-template <typename R>
-__device__ __noinline__ int sat_pose_pose(Pose<R> a, Pose<R> b, R tau) {
-  Quad<R> qa, qb;
-  pose_quad(a, qa);
-  pose_quad(b, qb);
-  const int bits = separation_bits(qa, qb, tau * tau) | separation_bits(qb, qa, tau * tau);
-  return (!(bits & SEP_ANY) ? GEO_HIT : 0) | ((!(bits & SEP_CLEAR) && (bits & NEAR_ANY)) ? GEO_TANGENT : 0);
-}
-
-// body box vs a static quad of the scenario tables (road, traffic light, obstacle, crossing box)
+// body box vs a quad of the scenario tables that is not a rectangle
 template <typename R>
 __device__ __noinline__ int sat_pose_quad(Pose<R> a, const Quad<R>* other, R tau) {
-  Quad<R> qa, qb = *other;
-  pose_quad(a, qa);
-  const int bits = separation_bits(qa, qb, tau * tau) | separation_bits(qb, qa, tau * tau);
-  return (!(bits & SEP_ANY) ? GEO_HIT : 0) | ((!(bits & SEP_CLEAR) && (bits & NEAR_ANY)) ? GEO_TANGENT : 0);
+  Quad<R> qa;
+  const Quad<R> qb = *other;
+  make_box(a.length, a.width, a.theta, a.c, a.s, a.x, a.y, qa);
+  return sat_bits(qa, qb, tau);
 }
 
-// body box vs the part [x0, x1] of the ego's stopping-zone frame (braking or reaction zone)
-template <typename R>
-__device__ __noinline__ int sat_pose_zone(Pose<R> a, ZoneFrame<R> z, R theta, R c, R s, R x0, R x1, R tau) {
-  Quad<R> qa, qz;
-  pose_quad(a, qa);
-  zone_quad(z, theta, c, s, x0, x1, qz);
-  const int bits = separation_bits(qa, qz, tau * tau) | separation_bits(qz, qa, tau * tau);
-  return (!(bits & SEP_ANY) ? GEO_HIT : 0) | ((!(bits & SEP_CLEAR) && (bits & NEAR_ANY)) ? GEO_TANGENT : 0);
-}
-
-// The kerb crossing: share of a body box lying on an axis-aligned road when its AABB is clearly across exactly
-// one road edge (axis_case == AXIS_ONE_EDGE).  One compact out-of-line instance.
-template <typename R>
-__device__ __noinline__ R kerb_share(Pose<R> a, Aabb<R> bb, Aabb<R> road, R tau) {
-  Quad<R> box;
-  pose_quad(a, box);
-  R nx = R(0), ny = R(0), bound;
-  if (bb.x0 - road.x0 < tau) { nx = R(-1); bound = -road.x0; }        // inside: x >= x0
-  else if (road.x1 - bb.x1 < tau) { nx = R(1); bound = road.x1; }     // inside: x <= x1
-  else if (bb.y0 - road.y0 < tau) { ny = R(-1); bound = -road.y0; }
-  else { ny = R(1); bound = road.y1; }
-  return fast_div(halfplane_area(box, nx, ny, bound), a.length * a.width);
-}
-
-// Share of a body box lying on a road by the general predicates (Shape.percentage_intersects, geometry.py:80-87):
-// rotated roads, road corners, near-tangent configurations.  Cold.
+// Share of a body box lying on a road by the general predicates: rotated roads, road corners, near-tangent
+// configurations.
 template <typename R>
 __device__ __noinline__ Share<R> road_share_general(Pose<R> a, const Quad<R>* road, R tau) {
   Quad<R> box;
-  pose_quad(a, box);
+  make_box(a.length, a.width, a.theta, a.c, a.s, a.x, a.y, box);
   const Quad<R> other = *road;
-  Share<R> out;
-  bool tangent = false;
-  const int bits = separation_bits(box, other, tau * tau) | separation_bits(other, box, tau * tau);
-  if (!(bits & SEP_CLEAR) && (bits & NEAR_ANY)) tangent = true;
-  if (bits & SEP_ANY) out.value = R(0);
-  else if (contains(other, box, tau, tangent)) out.value = R(1);
-  else out.value = clip_area(box, other) / quad_area(box);
-  out.tangent = tangent ? 1 : 0;
-  return out;
+  return percentage_of(box, other, tau);
 }
 
 }  // namespace cav

@@ -18,7 +18,7 @@ namespace cav {
 
 constexpr int kThreads = 128;
 #ifndef CAV_MIN_BLOCKS_STEP
-#define CAV_MIN_BLOCKS_STEP 3
+#define CAV_MIN_BLOCKS_STEP 4
 #endif
 #ifndef CAV_MIN_BLOCKS_LOOP
 #define CAV_MIN_BLOCKS_LOOP 2
@@ -100,27 +100,31 @@ __device__ __forceinline__ void write_outputs(const EnvBuffers<R>& buf, const St
   if (io.tangent_out) io.tangent_out[e] = tangent ? 1 : 0;
 }
 
-// One transition of env e held in `env`, with all the bookkeeping shared by the three kernels:
-// frozen envs, invalid actions, outputs, latching and scoring.  Returns true if the episode ended.
-template <typename R, int M, bool AGENTS>
+// One transition of env e held in `env`, with all the bookkeeping shared by the three kernels: frozen envs, invalid
+// actions, outputs, latching and scoring.  Returns true if the episode ended in this step.  One output site: frozen
+// (finished, not yet reset) envs report reward 0 and their latched done / winner through the same stores.
+template <typename R, int M, bool AGENTS, bool GENERIC>
 __device__ __forceinline__ bool advance(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t e,
                                         int64_t t_global, EnvRegs<R, M>& env, const R (&ext)[M][2], LocalStats& ls) {
   StepResult<R, M> res;
+  bool ended = false;
   if (env.done) {  // frozen until reset
 #pragma unroll
     for (int b = 0; b < M; ++b) res.reward[b] = R(0);
-    write_outputs<R, M>(buf, io, e, env, res.reward, env.done == 1, env.winner, false);
-    return false;
+    res.terminate = env.done == 1;
+    res.winner = env.winner;
+    res.tangent = false;
+  } else {
+    transition<R, M, AGENTS, GENERIC>(sc, buf, e, t_global, env, ext, res);
+    if (res.invalid) buf.err[e] = 1;
+    if (res.tangent) ls.tangent += 1;
+    if (env.done) {
+      score_episode<R, M>(buf, e, env, ls);
+      ended = true;
+    }
   }
-  transition<R, M, AGENTS>(sc, buf, e, t_global, env, ext, res);
-  if (res.invalid) buf.err[e] = 1;
   write_outputs<R, M>(buf, io, e, env, res.reward, res.terminate, res.winner, res.tangent);
-  ls.tangent += res.tangent ? 1 : 0;
-  if (env.done) {
-    score_episode<R, M>(buf, e, env, ls);
-    return true;
-  }
-  return false;
+  return ended;
 }
 
 template <typename R, int M>
@@ -132,7 +136,7 @@ __device__ __forceinline__ void load_actions(const R* actions, int64_t n, int64_
   }
 }
 
-template <typename R, int M, bool AGENTS>
+template <typename R, int M, bool AGENTS, bool GENERIC>
 __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_STEP) step_kernel(const __grid_constant__ DevScenario<R> sc,
                                                         const __grid_constant__ EnvBuffers<R> buf,
                                                         const __grid_constant__ StepIO<R> io, int64_t t_global) {
@@ -144,14 +148,14 @@ __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_STEP) step_kernel(con
     load_env<R, M, AGENTS>(sc, buf, e, env);
     load_actions<R, M>(io.actions, buf.n, e, ext);
     const bool was_live = env.done == 0;
-    advance<R, M, AGENTS>(sc, buf, io, e, t_global, env, ext, ls);
+    advance<R, M, AGENTS, GENERIC>(sc, buf, io, e, t_global, env, ext, ls);
     if (was_live) store_env<R, M, AGENTS>(sc, buf, e, env, false);
   }
   flush_stats(ls, buf.stats);
 }
 
 // Trajectory outputs are [T][...] slabs of the per-step shapes; io.* point at step 0.
-template <typename R, int M>
+template <typename R, int M, bool GENERIC>
 __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) replay_kernel(const __grid_constant__ DevScenario<R> sc,
                                                           const __grid_constant__ EnvBuffers<R> buf,
                                                           const __grid_constant__ StepIO<R> io, int64_t t_global, int n_steps) {
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) replay_kernel(c
       if (io.done_out) at.done_out = io.done_out + (int64_t)t * n;
       if (io.winner_out) at.winner_out = io.winner_out + (int64_t)t * n;
       if (io.tangent_out) at.tangent_out = io.tangent_out + (int64_t)t * n;
-      advance<R, M, false>(sc, buf, at, e, t_global + t, env, ext, ls);
+      advance<R, M, false, GENERIC>(sc, buf, at, e, t_global + t, env, ext, ls);
 #pragma unroll
       for (int b = 0; b < M; ++b) { ext[b][0] = nxt[b][0]; ext[b][1] = nxt[b][1]; }
     }
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) replay_kernel(c
   flush_stats(ls, buf.stats);
 }
 
-template <typename R, int M>
+template <typename R, int M, bool GENERIC>
 __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) rollout_kernel(const __grid_constant__ DevScenario<R> sc,
                                                            const __grid_constant__ EnvBuffers<R> buf, int64_t t_global,
                                                            int n_steps, int auto_reset) {
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) rollout_kernel(
         reset_env<R, M>(sc, buf, nullptr, e, env);
         was_reset = true;
       }
-      advance<R, M, true>(sc, buf, io, e, t_global + t, env, ext, ls);
+      advance<R, M, true, GENERIC>(sc, buf, io, e, t_global + t, env, ext, ls);
     }
     if (auto_reset && env.done) { reset_env<R, M>(sc, buf, nullptr, e, env); was_reset = true; }
     store_env<R, M, true>(sc, buf, e, env, was_reset);
@@ -238,21 +242,30 @@ struct SmallLaunchers {
 
 template <typename R> inline unsigned grid_for(const EnvBuffers<R>& buf) { return (unsigned)((buf.hi - buf.lo + kThreads - 1) / kThreads); }
 
+// sc.homogeneous (set by the host when the scenario qualifies) selects the GENERIC = false instantiation.
 template <typename R, int M>
 void launch_step(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t t_global, bool agents,
                  cudaStream_t stream) {
-  if (agents) step_kernel<R, M, true><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, io, t_global);
-  else step_kernel<R, M, false><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, io, t_global);
+  const unsigned grid = grid_for(buf);
+  if (sc.homogeneous) {
+    if (agents) step_kernel<R, M, true, false><<<grid, kThreads, 0, stream>>>(sc, buf, io, t_global);
+    else step_kernel<R, M, false, false><<<grid, kThreads, 0, stream>>>(sc, buf, io, t_global);
+  } else {
+    if (agents) step_kernel<R, M, true, true><<<grid, kThreads, 0, stream>>>(sc, buf, io, t_global);
+    else step_kernel<R, M, false, true><<<grid, kThreads, 0, stream>>>(sc, buf, io, t_global);
+  }
 }
 template <typename R, int M>
 void launch_replay(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t t_global, int n_steps,
                    cudaStream_t stream) {
-  replay_kernel<R, M><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, io, t_global, n_steps);
+  if (sc.homogeneous) replay_kernel<R, M, false><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, io, t_global, n_steps);
+  else replay_kernel<R, M, true><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, io, t_global, n_steps);
 }
 template <typename R, int M>
 void launch_rollout(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t t_global, int n_steps, int auto_reset,
                     cudaStream_t stream) {
-  rollout_kernel<R, M><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
+  if (sc.homogeneous) rollout_kernel<R, M, false><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
+  else rollout_kernel<R, M, true><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
 }
 template <typename R, int M>
 void launch_reset(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const uint8_t* mask, const R* init, int first_time,

@@ -12,6 +12,9 @@
 // Used by the step, replay and rollout kernels (kernels_small.cuh), so the three share one
 // definition of a transition.  Thread-per-environment: every array below is indexed by
 // compile-time constants after unrolling and lives in registers.
+//
+// Boxes never become corner lists here: each body is (x, y, cos, sin, half length, half width) and every test is
+// written on that form (geometry.cuh).  What stays out of line: general quads, road corners, libm.
 #pragma once
 #include "agents.cuh"
 
@@ -63,16 +66,60 @@ __device__ __forceinline__ bool uses_agent_state(const DevScenario<R>& sc, int b
   return sc.bodies[b].agent == CAV_AGENT_RANDOM_CONSTRAINED || sc.bodies[b].agent == CAV_AGENT_PROXIMITY;
 }
 
-// Pose of body b from its post-step state; b must be a compile-time constant at the call site (unrolled loops).
+// Body b as a box / as a pose; b must be a compile-time constant at the call site (unrolled loops).
+template <typename R, int M>
+__device__ __forceinline__ Box<R> body_box(const DevScenario<R>& sc, const EnvRegs<R, M>& env, const int b) {
+  return {env.s[b][0], env.s[b][1], env.cs[b][0], env.cs[b][1], sc.bodies[b].k.hl, sc.bodies[b].k.hw};
+}
 template <typename R, int M>
 __device__ __forceinline__ Pose<R> body_pose(const DevScenario<R>& sc, const EnvRegs<R, M>& env, const int b) {
   const DevBody<R>& body = sc.bodies[b];
   return {env.s[b][0], env.s[b][1], env.s[b][3], env.cs[b][0], env.cs[b][1], body.k.length, body.k.width};
 }
 
+// closed predicate from a separating-axis margin; flags near-tangent decisions
+template <typename R>
+__device__ __forceinline__ bool margin_hit(R margin, R tau, bool& tangent) {
+  if (rabs(margin) < tau) tangent = true;
+  return !(margin > R(0));
+}
 __device__ __forceinline__ bool geo_hit(int r, bool& tangent) {
   if (r & GEO_TANGENT) tangent = true;
   return (r & GEO_HIT) != 0;
+}
+
+// Shape.percentage_intersects(body box, road r) (environment.py:141, geometry.py:80-87).
+//   AABB clear of the road            -> 0        (disjoint)
+//   axis-aligned road, clearly inside -> 1        (contained)
+//   axis-aligned road, one kerb       -> closed form (kerb_share)
+//   anything else                     -> general predicates, out of line
+// `near` is raised when the share is within tau of the liveness threshold 0.5 (environment.py:144) or a general
+// predicate was near-tangent.  GENERIC = false: every road is known to be an axis-aligned rectangle.
+template <typename R, int M, bool GENERIC>
+__device__ __forceinline__ R road_share(const DevScenario<R>& sc, const EnvRegs<R, M>& env, const int b, int r, R ex, R ey,
+                                        R tau, bool& near) {
+  const Aabb<R> rd = sc.road_bb[r];
+  const R px = env.s[b][0], py = env.s[b][1];
+  const R m0 = (px - ex) - rd.x0, m1 = rd.x1 - (px + ex), m2 = (py - ey) - rd.y0, m3 = rd.y1 - (py + ey);
+  const R mx = rmin(m0, m1), my = rmin(m2, m3);
+  if (mx < -((ex + ex) + tau) || my < -((ey + ey) + tau)) return R(0);
+  if (!GENERIC || sc.road_axis[r]) {
+    const bool x_edge = mx < my;
+    const R lo = x_edge ? mx : my, hi = x_edge ? my : mx;
+    if (lo >= tau) return R(1);
+    // one kerb: the smallest margin is clearly negative, the opposite edge and the other pair of edges clearly inside
+    const R opposite = x_edge ? rmax(m0, m1) : rmax(m2, m3);
+    if (lo <= -tau && hi >= tau && opposite >= tau) {
+      const R ac = rabs(env.cs[b][0]), as = rabs(env.cs[b][1]);
+      const R hl = sc.bodies[b].k.hl, hw = sc.bodies[b].k.hw;
+      const R p = kerb_share(lo + (x_edge ? ex : ey), (x_edge ? ac : as) * hl, (x_edge ? as : ac) * hw);
+      if (rabs(p - R(0.5)) < tau) near = true;
+      return p;
+    }
+  }
+  const Share<R> share = road_share_general(body_pose<R, M>(sc, env, b), &sc.quads[r], tau);
+  near |= (share.tangent != 0) || (rabs(share.value - R(0.5)) < tau);
+  return share.value;
 }
 
 // Result of one transition besides the updated EnvRegs.
@@ -84,12 +131,17 @@ struct StepResult {
 };
 
 // AGENTS = false compiles the replay-only variant: every body takes its action from `ext`.
-template <typename R, int M, bool AGENTS>
+// GENERIC = false compiles the homogeneous variant the engine selects when the scenario has no PelicanCrossing body,
+// every non-ego body is a Pedestrian and every road is an axis-aligned rectangle (the Pedestrians-v0 family, any
+// number of pedestrians): the per-body kind / flag tests disappear at compile time.
+template <typename R, int M, bool AGENTS, bool GENERIC>
 __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, int64_t t_global,
                                            EnvRegs<R, M>& env, const R (&ext)[M][2], StepResult<R, M>& out) {
   const R tau = sc.tau, dt = sc.dt;
   bool tangent = false;
   R act[M][2];
+  auto is_pelican = [&](int b) { return GENERIC && sc.bodies[b].kind == CAV_BODY_PELICAN; };
+  auto is_pedestrian = [&](int b) { return !GENERIC || (sc.bodies[b].flags & CAV_FLAG_PEDESTRIAN) != 0; };
 
   // ---- joint action from the pre-step state
   bool valid = true;
@@ -114,7 +166,7 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
         a0 = R(0); a1 = R(0);
       } else if (body.agent == CAV_AGENT_RANDOM) {  // RandomAgent.choose_action (template.py:52-56)
         if (u[0] < body.epsilon) {
-          if (body.kind == CAV_BODY_PELICAN) {
+          if (is_pelican(b)) {
             a0 = R(floor(u[1] * 4.0)); if (a0 > R(3)) a0 = R(3);
             a1 = R(0);
           } else {
@@ -141,7 +193,7 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
       }
     }
     act[b][0] = a0; act[b][1] = a1;
-    if (body.kind == CAV_BODY_PELICAN) valid = valid && (a0 == R(0) || a0 == R(1) || a0 == R(2) || a0 == R(3));
+    if (is_pelican(b)) valid = valid && (a0 == R(0) || a0 == R(1) || a0 == R(2) || a0 == R(3));
     else valid = valid && (a0 >= k.amin && a0 <= k.amax && a1 >= k.smin && a1 <= k.smax);
   }
   out.invalid = !valid;
@@ -154,24 +206,24 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
     return;
   }
 
-  // ---- body.step, then the AABB of every body (all later tests start from it)
-  Aabb<R> bb[M];
+  // ---- body.step, then the half extents of every body's AABB (all later tests start from them)
+  R ex[M], ey[M];
   R ego_steer = R(0);
 #pragma unroll
   for (int b = 0; b < M; ++b) {
     const DevBody<R>& body = sc.bodies[b];
     if (AGENTS) { env.held[b][0] = act[b][0]; env.held[b][1] = act[b][1]; }
-    if (body.kind == CAV_BODY_PELICAN) {  // PelicanCrossing.step (bodies.py:450-461)
+    if (is_pelican(b)) {  // PelicanCrossing.step (bodies.py:450-461)
       if (act[b][0] == R(1)) env.s[b][0] = R(0);
       else if (act[b][0] == R(2)) env.s[b][0] = R(1);
       else if (act[b][0] == R(3)) env.s[b][0] = R(2);
-      bb[b] = body.sbox_bb;
+      ex[b] = R(0); ey[b] = R(0);
     } else {
       const DevType<R>& k = body.k;
       R snapped;
       if (body_step(k, env.s[b], act[b][0], act[b][1], dt, env.cs[b][0], env.cs[b][1], snapped)) env.cs_dirty |= 1u << b;
       if (b == 0) ego_steer = snapped;
-      bb[b] = box_aabb(k.length, k.width, env.s[b][3], env.cs[b][0], env.cs[b][1], env.s[b][0], env.s[b][1]);
+      box_extents(env.cs[b][0], env.cs[b][1], k.hl, k.hw, ex[b], ey[b]);
     }
   }
 
@@ -186,36 +238,20 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
   out.reward[0] = r0;
 #pragma unroll
   for (int b = 1; b < M; ++b) {
-    const bool is_static = sc.bodies[b].kind == CAV_BODY_PELICAN;
     R p = R(0);
-    bool near = false;
+    if (is_pelican(b)) {
+      p = sc.bodies[b].static_share;  // static box vs static roads: a constant of the scenario
+    } else {
 #pragma unroll 1
-    for (int r = 0; r < sc.n_roads; ++r) {  // max over roads (environment.py:141)
-      R q = R(0);
-      if (!aabb_apart(bb[b], sc.road_bb[r], tau)) {  // otherwise disjoint: percentage 0
-        if (is_static) {
-          const Quad<R> mine = sc.bodies[b].sbox;
-          q = percentage_intersects(mine, sc.roads[r], tau).value;  // static vs static: never tangent-flagged
-        } else {
-          const int how = sc.road_axis[r] ? axis_case(bb[b], sc.road_bb[r], tau) : AXIS_GENERAL;
-          if (how == AXIS_INSIDE) q = R(1);
-          else if (how == AXIS_ONE_EDGE) q = kerb_share(body_pose<R, M>(sc, env, b), bb[b], sc.road_bb[r], tau);
-          else {
-            const Share<R> share = road_share_general(body_pose<R, M>(sc, env, b), &sc.roads[r], tau);
-            q = share.value;
-            near |= share.tangent != 0;
-          }
-        }
+      for (int r = 0; r < sc.n_roads; ++r) {  // max over roads (environment.py:141)
+        const R q = road_share<R, M, GENERIC>(sc, env, b, r, ex[b], ey[b], tau, tangent);
+        if (r == 0 || q > p) p = q;
       }
-      if (r == 0 || q > p) p = q;
     }
     R rb = R(0);
     rb -= p * c;
     rb += ego_rel * c;
     out.reward[b] = rb;
-    if (!is_static) {
-      if (near || rabs(p - R(0.5)) < tau) tangent = true;
-    }
     if (p > R(0.5)) buf.liveness[(int64_t)b * buf.n + e] += 1;
   }
 
@@ -223,25 +259,34 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
   bool terminate = false, win_ego = false;
   int win_tester = -1;
   {
-    const R margin = bb[0].x0 - W;  // all four ego corners x > viewer_width  <=>  min corner x > W
-    if (rabs(margin) < tau) tangent = true;
-    if (margin > R(0)) { terminate = true; win_ego = true; }
+    const R margin = (env.s[0][0] - ex[0]) - W;  // all four ego corners x > viewer_width  <=>  min corner x > W
+    if (margin > -tau) {                         // only the last steps of an episode get here
+      if (margin < tau) tangent = true;
+      if (margin > R(0)) { terminate = true; win_ego = true; }
+    }
   }
   if (!terminate && sc.collisions == CAV_COLLISIONS_ALL) {
     bool hit = false;
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-      if (sc.bodies[i].kind == CAV_BODY_PELICAN) continue;
+      if (is_pelican(i)) continue;
 #pragma unroll
       for (int j = i + 1; j < M; ++j) {
-        if (sc.bodies[j].kind == CAV_BODY_PELICAN) continue;
-        if (!aabb_apart(bb[i], bb[j], tau))
-          hit |= geo_hit(sat_pose_pose(body_pose<R, M>(sc, env, i), body_pose<R, M>(sc, env, j), tau), tangent);
+        if (is_pelican(j)) continue;
+        const bool apart = rabs(env.s[i][0] - env.s[j][0]) - (ex[i] + ex[j]) > tau ||
+                           rabs(env.s[i][1] - env.s[j][1]) - (ey[i] + ey[j]) > tau;
+        if (!apart) hit |= margin_hit(box_margin(body_box<R, M>(sc, env, i), body_box<R, M>(sc, env, j)), tau, tangent);
       }
 #pragma unroll 1
       for (int s = 0; s < sc.n_statics; ++s) {
-        if (!aabb_apart(bb[i], sc.static_bb[s], tau))
-          hit |= geo_hit(sat_pose_quad(body_pose<R, M>(sc, env, i), &sc.statics[s], tau), tangent);
+        const Aabb<R> sb = sc.static_bb[s];
+        const R px = env.s[i][0], py = env.s[i][1];
+        const bool apart = (px - ex[i]) - sb.x1 > tau || sb.x0 - (px + ex[i]) > tau || (py - ey[i]) - sb.y1 > tau ||
+                           sb.y0 - (py + ey[i]) > tau;
+        if (!apart) {
+          if (sc.static_rect[s]) hit |= margin_hit(box_margin(body_box<R, M>(sc, env, i), sc.static_box[s]), tau, tangent);
+          else hit |= geo_hit(sat_pose_quad(body_pose<R, M>(sc, env, i), &sc.quads[CAV_MAX_ROADS + s], tau), tangent);
+        }
       }
     }
     terminate = hit;
@@ -250,47 +295,47 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
     bool on_road = false;
 #pragma unroll 1
     for (int r = 0; r < sc.n_roads; ++r) {
-      if (!aabb_apart(bb[0], sc.road_bb[r], tau))
-        on_road |= geo_hit(sat_pose_quad(body_pose<R, M>(sc, env, 0), &sc.roads[r], tau), tangent);
+      const Aabb<R> rd = sc.road_bb[r];
+      const R px = env.s[0][0], py = env.s[0][1];
+      const bool apart = (px - ex[0]) - rd.x1 > tau || rd.x0 - (px + ex[0]) > tau || (py - ey[0]) - rd.y1 > tau ||
+                         rd.y0 - (py + ey[0]) > tau;
+      if (!apart) {
+        if (!GENERIC || sc.road_rect[r]) on_road |= margin_hit(box_margin(body_box<R, M>(sc, env, 0), sc.road_box[r]), tau, tangent);
+        else on_road |= geo_hit(sat_pose_quad(body_pose<R, M>(sc, env, 0), &sc.quads[r], tau), tangent);
+      }
     }
     terminate = !on_road;
   }
   if (!terminate && (sc.collisions == CAV_COLLISIONS_EGO || sc.zones)) {
     const DevType<R>& k0 = sc.bodies[0].k;
-    const R th0 = env.s[0][3], c0 = env.cs[0][0], s0 = env.cs[0][1];
-    const ZoneFrame<R> zf = zone_frame(k0, env.s[0][0], env.s[0][1], env.s[0][2], th0, c0, s0, ego_steer);
-    const bool have_zones = zf.have;
-    Aabb<R> braking_bb = {R(0), R(0), R(0), R(0)}, reaction_bb = braking_bb;
-    if (have_zones) {
-      braking_bb = zone_aabb(zf, th0, c0, s0, R(0), zf.bd);
-      reaction_bb = zone_aabb(zf, th0, c0, s0, zf.bd, zf.td);
-    }
-    if (sc.collisions == CAV_COLLISIONS_EGO) {
-      bool hit = false;
+    EgoFrame<R> f;
+    f.x = env.s[0][0]; f.y = env.s[0][1]; f.c = env.cs[0][0]; f.s = env.cs[0][1]; f.hl = k0.hl; f.hw = k0.hw;
+    const R v0 = env.s[0][2];
+    f.bd = (v0 * v0) * k0.inv_2brake;           // bodies.py:123
+    f.td = f.bd + v0 * R(0.675);                // bodies.py:124-125 (REACTION_TIME)
+    f.have = !(f.td == R(0)) && (ego_steer == R(0));
+    const bool ego_mode = sc.collisions == CAV_COLLISIONS_EGO;
+    bool hit = false;
 #pragma unroll
-      for (int b = 1; b < M; ++b) {
-        if (!(sc.bodies[b].flags & CAV_FLAG_PEDESTRIAN)) continue;
-        bool h = false;
-        if (!aabb_apart(bb[b], bb[0], tau))
-          h = geo_hit(sat_pose_pose(body_pose<R, M>(sc, env, b), body_pose<R, M>(sc, env, 0), tau), tangent);
-        if (!h && have_zones && !aabb_apart(bb[b], braking_bb, tau))
-          h = geo_hit(sat_pose_zone(body_pose<R, M>(sc, env, b), zf, th0, c0, s0, R(0), zf.bd, tau), tangent);
+    for (int b = 1; b < M; ++b) {
+      if (!is_pedestrian(b)) continue;   // environment.py:192,199
+      // Common case, decided with one predicate chain: the pedestrian is clear (by tau or more) of the strip swept by
+      // the ego box and both zones.  Only otherwise are the closed predicates and near-tangent flags evaluated.
+      const EgoMargins<R> m = ego_margins(f, env.s[b][0], env.s[b][1], env.cs[b][0], env.cs[b][1], sc.bodies[b].k.hl,
+                                          sc.bodies[b].k.hw, tau);
+      if (m.all_clear) continue;
+      if (ego_mode) {   // environment.py:183-193: ego box, then the braking zone
+        bool h = margin_hit(m.ego, tau, tangent);
+        if (!h && f.have) h = margin_hit(m.braking, tau, tangent);
         hit |= h;
       }
-      terminate = hit;
-    }
-    if (!terminate && sc.zones) {
-      if (have_zones) {
-#pragma unroll
-        for (int b = 1; b < M; ++b) {
-          if (!(sc.bodies[b].flags & CAV_FLAG_PEDESTRIAN) || win_tester >= 0) continue;
-          if (!aabb_apart(bb[b], reaction_bb, tau)) {
-            if (geo_hit(sat_pose_zone(body_pose<R, M>(sc, env, b), zf, th0, c0, s0, zf.bd, zf.td, tau), tangent)) win_tester = b;
-          }
-        }
+      // environment.py:195-206: first pedestrian in the reaction zone wins (only consulted if nothing terminated above)
+      if (sc.zones && f.have && win_tester < 0 && !hit) {
+        if (margin_hit(m.reaction, tau, tangent)) win_tester = b;
       }
-      terminate = win_tester >= 0;
     }
+    if (hit) { terminate = true; win_tester = -1; }
+    else terminate = win_tester >= 0;
   }
 
   // ---- terminal rewards and winner
