@@ -30,6 +30,7 @@ N_ENVS = 65536          # per GPU (weak scaling)
 SEGMENT = 500           # steps replayed from a fresh reset before resetting again (ego finishes at step 901)
 CHUNK = 50              # steps fused per cavgym_replay launch
 HBM_ENVS = 4 * 1024 * 1024
+HBM_ADVANCE = 300        # unrecorded steps before the HBM-config trace: envs are mid-episode, pedestrians mid-crossing
 EPSILON = 0.01
 BYTES_PER_BODY_STEP = {"float64": 88, "float32": 44}   # 4w state in + 2w action + 4w state out + 1w reward
 BYTES_PER_ENV_STEP_EXTRA = 5                            # 1 B done + 4 B winner
@@ -84,13 +85,17 @@ def scenario(mode):
     return compile_from_meta(meta, mode=mode)
 
 
-def make_trace(torch, device, n_envs, n_steps, dtype, env_offset):
-    """Untimed set-up: run the on-device agents once and log every joint action -> (init_state, actions[T,M,2,N])."""
+def make_trace(torch, device, n_envs, n_steps, dtype, env_offset, advance=0):
+    """Untimed set-up: run the on-device agents once and log every joint action -> (init_state, actions[T,M,2,N]).
+    `advance` first runs that many unrecorded steps (auto-reset on), so the trace starts mid-episode with the
+    envs spread over every phase of a crossing."""
     from cavgym_b200 import BatchedCAVEnv
     gen = BatchedCAVEnv(None, None, None, num_envs=n_envs, dtype=dtype, compiled=scenario("device"), device=device, seed=0,
                         env_offset=env_offset)
     gen.set_action_logging(True)
     gen.reset()
+    if advance:
+        gen.rollout(advance, auto_reset=True)
     init = gen.state.clone()
     actions = torch.empty((n_steps, gen.num_bodies, 2, n_envs), dtype=gen.dtype, device=device)
     for t in range(n_steps):
@@ -268,7 +273,7 @@ def hbm_config(torch, device, dtype, peak_gbs):
     """The per-step kernel (cavgym_step) at 4,194,304 envs: 268 MB of state, 0.77 GB algorithmic bytes per launch."""
     from cavgym_b200 import BatchedCAVEnv
     n, m, t_len = HBM_ENVS, 2, 6
-    init, actions = make_trace(torch, device, n, t_len, dtype, env_offset=0)
+    init, actions = make_trace(torch, device, n, t_len, dtype, env_offset=0, advance=HBM_ADVANCE)
     env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=scenario("external"), device=device)
     env.reset(init_state=init)
     for t in range(3):
@@ -288,7 +293,8 @@ def hbm_config(torch, device, dtype, peak_gbs):
     bytes_launch = n * (m * BYTES_PER_BODY_STEP[dtype] + BYTES_PER_ENV_STEP_EXTRA)
     achieved = bytes_launch / (mean_ms * 1e-3) / 1e9
     env.close()
-    return {"workload": "pedestrians x 4,194,304 envs, cavgym_step (one launch per step), replayed actions, working set >> L2",
+    return {"workload": "pedestrians x 4,194,304 envs, 300 steps into their episodes, cavgym_step (one launch per step), "
+                        "replayed actions, working set >> L2",
             "kernel": f"step_kernel<{'double' if dtype == 'float64' else 'float'},2,false>", "envs": n,
             "env_steps_per_sec": n / (mean_ms * 1e-3), "body_steps_per_sec": n * m / (mean_ms * 1e-3),
             "avg_launch_ms": round(mean_ms, 4), "min_launch_ms": round(ms[0], 4), "algorithmic_bytes_per_launch": bytes_launch,

@@ -16,7 +16,7 @@ PKG = os.path.dirname(HERE)
 LIB = os.environ.get("CAVGYM_LIB_OUT") or os.path.join(PKG, "libcavgym_sm100.so")
 OBJ_DIR = os.environ.get("CAVGYM_OBJ_DIR") or os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=" + os.environ.get("CAVGYM_FMAD", "false"), "-std=c++17",
          "-Xcompiler", "-fPIC,-O2", "--threads", "1"]
 
 

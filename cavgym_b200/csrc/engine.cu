@@ -272,6 +272,7 @@ struct CavEngine {
   int64_t n = 0, t_global = 0, launches = 0;
   uint64_t seed = 0;
   bool has_external = false, has_device_agents = false;
+  bool use_tma = true;  // cavgym_set_step_path: 0 = plain thread-per-env kernel only
   double tau = 1e-7;
   CavScenario host{};
   std::vector<CavBody> bodies;
@@ -364,6 +365,19 @@ static int do_reset(CavEngine* eng, const uint8_t* mask, const void* init, int f
   return launch_check(eng, "reset kernel");
 }
 
+template <typename R>
+static int step_range_typed(CavEngine* eng, const DevScenario<R>& sc, EnvBuffers<R> buf, const StepIO<R>& io, cudaStream_t stream) {
+  const SmallLaunchers<R>* k = small_launchers<R>(eng->m);
+  int launches = 0;
+  if (!eng->has_device_agents && eng->use_tma) {   // replayed actions: persistent TMA-staged kernel over the whole tiles
+    int64_t taken = 0;
+    if (!k->step_tma(sc, buf, io, eng->t_global, stream, &taken)) return fail(CAV_ECUDA, "TMA step kernel set-up failed");
+    if (taken > 0) { buf.lo += taken; ++launches; }
+  }
+  if (buf.lo < buf.hi) { k->step(sc, buf, io, eng->t_global, eng->has_device_agents, stream); ++launches; }
+  return launch_check(eng, "step kernel", launches);
+}
+
 extern "C" {
 
 const char* cavgym_last_error(void) { return g_error.c_str(); }
@@ -452,13 +466,11 @@ static int step_range(CavEngine* eng, int64_t lo, int64_t hi, const void* action
   if (eng->dtype == CAV_F64) {
     EnvBuffers<double> buf = eng->buf64; buf.lo = lo; buf.hi = hi;
     StepIO<double> io{(const double*)actions, (double*)state_out, (double*)reward_out, done_out, winner_out, tangent_out};
-    small_launchers<double>(eng->m)->step(eng->sc64, buf, io, eng->t_global, eng->has_device_agents, stream);
-  } else {
-    EnvBuffers<float> buf = eng->buf32; buf.lo = lo; buf.hi = hi;
-    StepIO<float> io{(const float*)actions, (float*)state_out, (float*)reward_out, done_out, winner_out, tangent_out};
-    small_launchers<float>(eng->m)->step(eng->sc32, buf, io, eng->t_global, eng->has_device_agents, stream);
+    return step_range_typed(eng, eng->sc64, buf, io, stream);
   }
-  return launch_check(eng, "step kernel");
+  EnvBuffers<float> buf = eng->buf32; buf.lo = lo; buf.hi = hi;
+  StepIO<float> io{(const float*)actions, (float*)state_out, (float*)reward_out, done_out, winner_out, tangent_out};
+  return step_range_typed(eng, eng->sc32, buf, io, stream);
 }
 
 int cavgym_step(CavEngine* eng, const void* actions, void* state_out, void* reward_out, uint8_t* done_out, int32_t* winner_out,
@@ -618,6 +630,12 @@ int cavgym_set_spawn_override(CavEngine* eng, const double* draws) {
 int cavgym_set_action_logging(CavEngine* eng, int enabled) {
   if (!eng) return fail(CAV_EINVAL, "engine is NULL");
   eng->buf64.log_actions = enabled; eng->buf32.log_actions = enabled;
+  return CAV_OK;
+}
+
+int cavgym_set_step_path(CavEngine* eng, int use_tma) {
+  if (!eng) return fail(CAV_EINVAL, "engine is NULL");
+  eng->use_tma = use_tma != 0;
   return CAV_OK;
 }
 

@@ -32,6 +32,10 @@ __device__ __forceinline__ void load_env(const DevScenario<R>& sc, const EnvBuff
   env.winner = env.done ? buf.winner[e] : -1;
   env.ag_dirty = 0;
   env.cs_dirty = 0;
+  env.live_dirty = 0;
+  env.live[0] = 0;
+#pragma unroll
+  for (int b = 1; b < M; ++b) env.live[b] = buf.liveness[(int64_t)b * n + e];
   env.episode = AGENTS ? buf.episode[e] : 0;
 #pragma unroll
   for (int b = 0; b < M; ++b) {
@@ -67,6 +71,7 @@ __device__ __forceinline__ void store_env(const DevScenario<R>& sc, const EnvBuf
       buf.action[((int64_t)b * 2 + 0) * n + e] = env.held[b][0];
       buf.action[((int64_t)b * 2 + 1) * n + e] = env.held[b][1];
     }
+    if (all || (env.live_dirty >> b & 1u)) buf.liveness[(int64_t)b * n + e] = env.live[b];
     if (all || (env.cs_dirty >> b & 1u)) {
       buf.cs[((int64_t)b * 2 + 0) * n + e] = env.cs[b][0];
       buf.cs[((int64_t)b * 2 + 1) * n + e] = env.cs[b][1];
@@ -105,7 +110,7 @@ __device__ __forceinline__ void write_outputs(const EnvBuffers<R>& buf, const St
 // (finished, not yet reset) envs report reward 0 and their latched done / winner through the same stores.
 template <typename R, int M, bool AGENTS, bool GENERIC>
 __device__ __forceinline__ bool advance(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t e,
-                                        int64_t t_global, EnvRegs<R, M>& env, const R (&ext)[M][2], LocalStats& ls) {
+                                        int64_t t_global, EnvRegs<R, M>& env, const R (&ext)[M][2]) {
   StepResult<R, M> res;
   bool ended = false;
   if (env.done) {  // frozen until reset
@@ -117,9 +122,9 @@ __device__ __forceinline__ bool advance(const DevScenario<R>& sc, const EnvBuffe
   } else {
     transition<R, M, AGENTS, GENERIC>(sc, buf, e, t_global, env, ext, res);
     if (res.invalid) buf.err[e] = 1;
-    if (res.tangent) ls.tangent += 1;
+    if (res.tangent) count_tangent(buf.stats);
     if (env.done) {
-      score_episode<R, M>(buf, e, env, ls);
+      score_episode<R, M>(buf, env);
       ended = true;
     }
   }
@@ -141,17 +146,15 @@ __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_STEP) step_kernel(con
                                                         const __grid_constant__ EnvBuffers<R> buf,
                                                         const __grid_constant__ StepIO<R> io, int64_t t_global) {
   const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  LocalStats ls;
   if (e < buf.hi) {
     EnvRegs<R, M> env;
     R ext[M][2];
     load_env<R, M, AGENTS>(sc, buf, e, env);
     load_actions<R, M>(io.actions, buf.n, e, ext);
     const bool was_live = env.done == 0;
-    advance<R, M, AGENTS, GENERIC>(sc, buf, io, e, t_global, env, ext, ls);
+    advance<R, M, AGENTS, GENERIC>(sc, buf, io, e, t_global, env, ext);
     if (was_live) store_env<R, M, AGENTS>(sc, buf, e, env, false);
   }
-  flush_stats(ls, buf.stats);
 }
 
 // Trajectory outputs are [T][...] slabs of the per-step shapes; io.* point at step 0.
@@ -161,7 +164,6 @@ __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) replay_kernel(c
                                                           const __grid_constant__ StepIO<R> io, int64_t t_global, int n_steps) {
   const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int64_t n = buf.n;
-  LocalStats ls;
   if (e < buf.hi) {
     EnvRegs<R, M> env;
     load_env<R, M, false>(sc, buf, e, env);
@@ -178,13 +180,12 @@ __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) replay_kernel(c
       if (io.done_out) at.done_out = io.done_out + (int64_t)t * n;
       if (io.winner_out) at.winner_out = io.winner_out + (int64_t)t * n;
       if (io.tangent_out) at.tangent_out = io.tangent_out + (int64_t)t * n;
-      advance<R, M, false, GENERIC>(sc, buf, at, e, t_global + t, env, ext, ls);
+      advance<R, M, false, GENERIC>(sc, buf, at, e, t_global + t, env, ext);
 #pragma unroll
       for (int b = 0; b < M; ++b) { ext[b][0] = nxt[b][0]; ext[b][1] = nxt[b][1]; }
     }
     if (was_live) store_env<R, M, false>(sc, buf, e, env, false);
   }
-  flush_stats(ls, buf.stats);
 }
 
 template <typename R, int M, bool GENERIC>
@@ -192,7 +193,6 @@ __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) rollout_kernel(
                                                            const __grid_constant__ EnvBuffers<R> buf, int64_t t_global,
                                                            int n_steps, int auto_reset) {
   const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  LocalStats ls;
   if (e < buf.hi) {
     EnvRegs<R, M> env;
     load_env<R, M, true>(sc, buf, e, env);
@@ -206,12 +206,11 @@ __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) rollout_kernel(
         reset_env<R, M>(sc, buf, nullptr, e, env);
         was_reset = true;
       }
-      advance<R, M, true, GENERIC>(sc, buf, io, e, t_global + t, env, ext, ls);
+      advance<R, M, true, GENERIC>(sc, buf, io, e, t_global + t, env, ext);
     }
     if (auto_reset && env.done) { reset_env<R, M>(sc, buf, nullptr, e, env); was_reset = true; }
     store_env<R, M, true>(sc, buf, e, env, was_reset);
   }
-  flush_stats(ls, buf.stats);
 }
 
 template <typename R, int M>
@@ -238,6 +237,9 @@ struct SmallLaunchers {
   void (*replay)(const DevScenario<R>&, const EnvBuffers<R>&, const StepIO<R>&, int64_t t_global, int n_steps, cudaStream_t);
   void (*rollout)(const DevScenario<R>&, const EnvBuffers<R>&, int64_t t_global, int n_steps, int auto_reset, cudaStream_t);
   void (*reset)(const DevScenario<R>&, const EnvBuffers<R>&, const uint8_t* mask, const R* init, int first_time, cudaStream_t);
+  // TMA-staged step for replayed actions (kernels_tma.cuh): steps the whole tiles of [lo, hi) it can take and reports how
+  // many envs that was (0 = buffers not 16-byte aligned: use `step`); false = launch set-up failed.
+  bool (*step_tma)(const DevScenario<R>&, const EnvBuffers<R>&, const StepIO<R>&, int64_t t_global, cudaStream_t, int64_t* envs_done);
 };
 
 template <typename R> inline unsigned grid_for(const EnvBuffers<R>& buf) { return (unsigned)((buf.hi - buf.lo + kThreads - 1) / kThreads); }
@@ -271,11 +273,6 @@ template <typename R, int M>
 void launch_reset(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const uint8_t* mask, const R* init, int first_time,
                   cudaStream_t stream) {
   reset_kernel<R, M><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, mask, init, first_time);
-}
-
-template <typename R, int M>
-constexpr SmallLaunchers<R> make_launchers() {
-  return {&launch_step<R, M>, &launch_replay<R, M>, &launch_rollout<R, M>, &launch_reset<R, M>};
 }
 
 // Defined in small_mK.cu (one translation unit per body count so they compile in parallel).

@@ -26,39 +26,22 @@ struct EnvRegs {
   R held[M][2];      // last action of on-device agents (RandomAgent holds it)
   R ag[M][CAV_AGENT_WORDS];
   R cs[M][2];        // cos, sin of the heading (EnvBuffers::cs)
+  int32_t live[M];   // episode_liveness (environment.py:144-146); [0] unused
   int32_t t_ep, episode, winner;
+  uint32_t live_dirty;  // bit b: live[b] changed since it was loaded
   uint32_t cs_dirty;  // bit b: cs[b] changed since it was loaded
   uint32_t ag_dirty;  // bit b: ag[b] changed since it was loaded
   uint8_t done;
 };
 
-struct LocalStats {
-  unsigned long long episodes = 0, interesting = 0, sum_t = 0, sum_t2 = 0, tangent = 0;
-  long long sum_score = 0, sum_score2 = 0;
-};
+// Episode statistics (reporting.py:227-269) are updated with atomics at the moment an episode ends or a near-tangent
+// step is flagged — about one env-step in a thousand — so no per-thread accumulators stay live through the step.
+__device__ __forceinline__ void count_tangent(unsigned long long* stats) { atomicAdd(&stats[CAV_STAT_TANGENT], 1ull); }
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
-}
-
-// Whole-warp call: reduce with shuffles, one atomic per counter per warp, skipped when the warp has nothing.
-__device__ __forceinline__ void flush_stats(const LocalStats& ls, unsigned long long* stats) {
-  const bool any = (ls.episodes | ls.tangent) != 0;
-  if (!__any_sync(0xffffffffu, any)) return;
-  const unsigned long long ep = warp_sum(ls.episodes), in = warp_sum(ls.interesting), st = warp_sum(ls.sum_t),
-                           st2 = warp_sum(ls.sum_t2), tg = warp_sum(ls.tangent),
-                           sc = warp_sum((unsigned long long)ls.sum_score), sc2 = warp_sum((unsigned long long)ls.sum_score2);
-  if ((threadIdx.x & 31) == 0) {
-    if (ep) atomicAdd(&stats[CAV_STAT_EPISODES], ep);
-    if (in) atomicAdd(&stats[CAV_STAT_INTERESTING], in);
-    if (st) atomicAdd(&stats[CAV_STAT_SUM_T], st);
-    if (st2) atomicAdd(&stats[CAV_STAT_SUM_T2], st2);
-    if (sc) atomicAdd(&stats[CAV_STAT_SUM_SCORE], sc);  // two's complement: wraps to the signed sum
-    if (sc2) atomicAdd(&stats[CAV_STAT_SUM_SCORE2], sc2);
-    if (tg) atomicAdd(&stats[CAV_STAT_TANGENT], tg);
-  }
 }
 
 template <typename R, int M>
@@ -134,9 +117,16 @@ struct StepResult {
 // GENERIC = false compiles the homogeneous variant the engine selects when the scenario has no PelicanCrossing body,
 // every non-ego body is a Pedestrian and every road is an axis-aligned rectangle (the Pedestrians-v0 family, any
 // number of pedestrians): the per-body kind / flag tests disappear at compile time.
-template <typename R, int M, bool AGENTS, bool GENERIC>
+struct NoSink {
+  template <typename E> __device__ __forceinline__ void operator()(const E&) const {}
+};
+
+// `moved(env)` is called once, right after body.step: a kernel that stages state in shared memory writes the new
+// state there at that point, so x, y, v, theta need not stay in registers through the geometry.
+template <typename R, int M, bool AGENTS, bool GENERIC, typename Sink = NoSink>
 __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, int64_t t_global,
-                                           EnvRegs<R, M>& env, const R (&ext)[M][2], StepResult<R, M>& out) {
+                                           EnvRegs<R, M>& env, const R (&ext)[M][2], StepResult<R, M>& out,
+                                           Sink moved = Sink()) {
   const R tau = sc.tau, dt = sc.dt;
   bool tangent = false;
   R act[M][2];
@@ -226,36 +216,11 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
       box_extents(env.cs[b][0], env.cs[b][1], k.hl, k.hw, ex[b], ey[b]);
     }
   }
+  moved(env);
 
-  // ---- rewards and liveness
-  const R c = sc.cost_step, W = sc.W;
-  // Both divisors are scenario constants: multiply by the host-computed reciprocal (<= 1 ulp from the division).
-  const R ego_rel = rmax(R(0), rmin(R(1), (W - env.s[0][0]) * sc.inv_W));
-  const R voff = rabs(env.s[0][2] - sc.v_maint) * sc.inv_v_off;
-  R r0 = R(0);
-  r0 -= voff * c;
-  r0 += (R(1) - ego_rel) * c;
-  out.reward[0] = r0;
-#pragma unroll
-  for (int b = 1; b < M; ++b) {
-    R p = R(0);
-    if (is_pelican(b)) {
-      p = sc.bodies[b].static_share;  // static box vs static roads: a constant of the scenario
-    } else {
-#pragma unroll 1
-      for (int r = 0; r < sc.n_roads; ++r) {  // max over roads (environment.py:141)
-        const R q = road_share<R, M, GENERIC>(sc, env, b, r, ex[b], ey[b], tau, tangent);
-        if (r == 0 || q > p) p = q;
-      }
-    }
-    R rb = R(0);
-    rb -= p * c;
-    rb += ego_rel * c;
-    out.reward[b] = rb;
-    if (p > R(0.5)) buf.liveness[(int64_t)b * buf.n + e] += 1;
-  }
-
-  // ---- termination cascade
+  // ---- termination cascade (evaluated before the rewards: neither depends on the other, and the rare general
+  //      road-share call below then happens with almost nothing live)
+  const R W = sc.W;
   bool terminate = false, win_ego = false;
   int win_tester = -1;
   {
@@ -338,6 +303,34 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
     else terminate = win_tester >= 0;
   }
 
+  // ---- rewards and liveness
+  const R c = sc.cost_step;
+  // Both divisors are scenario constants: multiply by the host-computed reciprocal (<= 1 ulp from the division).
+  const R ego_rel = rmax(R(0), rmin(R(1), (W - env.s[0][0]) * sc.inv_W));
+  const R voff = rabs(env.s[0][2] - sc.v_maint) * sc.inv_v_off;
+  R r0 = R(0);
+  r0 -= voff * c;
+  r0 += (R(1) - ego_rel) * c;
+  out.reward[0] = r0;
+#pragma unroll
+  for (int b = 1; b < M; ++b) {
+    R p = R(0);
+    if (is_pelican(b)) {
+      p = sc.bodies[b].static_share;  // static box vs static roads: a constant of the scenario
+    } else {
+#pragma unroll 1
+      for (int r = 0; r < sc.n_roads; ++r) {  // max over roads (environment.py:141)
+        const R q = road_share<R, M, GENERIC>(sc, env, b, r, ex[b], ey[b], tau, tangent);
+        if (r == 0 || q > p) p = q;
+      }
+    }
+    R rb = R(0);
+    rb -= p * c;
+    rb += ego_rel * c;
+    out.reward[b] = rb;
+    if (p > R(0.5)) { env.live[b] += 1; env.live_dirty |= 1u << b; }
+  }
+
   // ---- terminal rewards and winner
   if (terminate || t_global == sc.max_timesteps - 1) {
     out.reward[0] += win_ego ? sc.reward_win : (win_tester >= 0 ? -sc.reward_win : sc.reward_draw);
@@ -370,19 +363,25 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
 
 // reporting.analyse_episode (reporting.py:227-243) for an env whose episode just ended.
 template <typename R, int M>
-__device__ __forceinline__ void score_episode(const EnvBuffers<R>& buf, int64_t e, const EnvRegs<R, M>& env, LocalStats& ls) {
-  const long long t = env.t_ep;
-  ls.episodes += 1;
-  ls.sum_t += t;
-  ls.sum_t2 += t * t;
-  if (env.winner > 0) {
-    long long score = 0;
-#pragma unroll
-    for (int b = 1; b < M; ++b) score -= buf.liveness[(int64_t)b * buf.n + e];
-    ls.interesting += 1;
-    ls.sum_score += score;
-    ls.sum_score2 += score * score;
+__device__ __noinline__ void score_episode(unsigned long long* stats, int32_t t_ep, int32_t winner, long long liveness_sum) {
+  const unsigned long long t = (unsigned long long)t_ep;
+  atomicAdd(&stats[CAV_STAT_EPISODES], 1ull);
+  atomicAdd(&stats[CAV_STAT_SUM_T], t);
+  atomicAdd(&stats[CAV_STAT_SUM_T2], t * t);
+  if (winner > 0) {
+    const long long score = -liveness_sum;
+    atomicAdd(&stats[CAV_STAT_INTERESTING], 1ull);
+    atomicAdd(&stats[CAV_STAT_SUM_SCORE], (unsigned long long)score);  // two's complement: wraps to the signed sum
+    atomicAdd(&stats[CAV_STAT_SUM_SCORE2], (unsigned long long)(score * score));
   }
+}
+
+template <typename R, int M>
+__device__ __forceinline__ void score_episode(const EnvBuffers<R>& buf, const EnvRegs<R, M>& env) {
+  long long sum = 0;
+#pragma unroll
+  for (int b = 1; b < M; ++b) sum += env.live[b];
+  score_episode<R, M>(buf.stats, env.t_ep, env.winner, sum);
 }
 
 // CAVEnv.reset for one env (environment.py:225-229): bodies back to init_state (SpawnPedestrians re-drawn),
@@ -421,12 +420,13 @@ __device__ __forceinline__ void reset_env(const DevScenario<R>& sc, const EnvBuf
     if (body.kind == CAV_BODY_DYNAMIC) heading_cs(sc, st[3], env.cs[b][0], env.cs[b][1]);
 #pragma unroll
     for (int w = 0; w < CAV_AGENT_WORDS; ++w) env.ag[b][w] = nan_<R>();
-    buf.liveness[(int64_t)b * buf.n + e] = 0;
+    env.live[b] = 0;
   }
   env.t_ep = 0;
   env.done = 0;
   env.winner = -1;
   env.ag_dirty = 0xFFFFFFFFu;  // everything must be written back
+  env.live_dirty = 0xFFFFFFFFu;
   env.cs_dirty = 0xFFFFFFFFu;
 }
 

@@ -161,6 +161,10 @@ class BatchedCAVEnv:
     def set_global_timestep(self, t):
         _native.check(self._lib.cavgym_set_global_timestep(self._handle, int(t)))
 
+    def set_step_path(self, use_tma=True):
+        """False forces the plain thread-per-env step kernel (the TMA-staged kernel is the default where it applies)."""
+        _native.check(self._lib.cavgym_set_step_path(self._handle, int(bool(use_tma))))
+
     def set_tangent_tolerance(self, tau):
         _native.check(self._lib.cavgym_set_tangent_tolerance(self._handle, float(tau)))
 

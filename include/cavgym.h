@@ -215,6 +215,11 @@ int cavgym_set_spawn_override(CavEngine* engine, const double* draws);
  * every on-device agent's chosen action is stored there each step (parity tests, compat view). */
 int cavgym_set_action_logging(CavEngine* engine, int enabled);
 
+/* cavgym_step with replayed actions normally runs the persistent TMA-staged kernel (whole 128-env tiles, 16-byte
+ * aligned buffers) and the plain thread-per-env kernel for whatever is left; use_tma = 0 forces the plain kernel
+ * everywhere (A/B measurements, parity of the two paths). */
+int cavgym_set_step_path(CavEngine* engine, int use_tma);
+
 /* CAVEnv.current_timestep (environment.py:90,222) is never reset by the reference;
  * the engine keeps ONE counter of step calls for the whole batch. */
 int cavgym_set_global_timestep(CavEngine* engine, int64_t t);

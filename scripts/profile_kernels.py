@@ -25,12 +25,9 @@ def main():
     args = parser.parse_args()
     device = torch.device("cuda", 0)
     if args.mode in ("step", "all"):
-        init, actions = bench.make_trace(torch, device, args.envs, 8 + args.advance, args.dtype, 0)
+        init, actions = bench.make_trace(torch, device, args.envs, 8, args.dtype, 0, advance=args.advance)
         env = BatchedCAVEnv(None, None, None, num_envs=args.envs, dtype=args.dtype, compiled=bench.scenario("external"), device=device)
         env.reset(init_state=init)
-        if args.advance:
-            env.replay(actions[:args.advance], record=())
-            actions = actions[args.advance:]
         times = []
         for t in range(args.launches + 2):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

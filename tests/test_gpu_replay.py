@@ -149,3 +149,34 @@ def test_missing_actions_is_an_error():
     env = make_env(meta, 2, "float64")
     with pytest.raises(CavgymError):
         env.step(None)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", ["pedestrians_rc_seed0", "pedestrians3_rc_seed2", "crossroads_random_all_seed6", "pelican_random_all_seed10"])
+def test_tma_step_kernel_is_bitwise_equal_to_plain_kernel(name, dtype):
+    """cavgym_step on replayed actions runs the persistent TMA-staged kernel over whole 128-env tiles and the plain
+    thread-per-env kernel over the ragged tail; both must produce the same bits as the plain kernel alone, every step,
+    for every output (state, reward, done, winner, tangent, liveness, timestep)."""
+    import torch
+    meta, episodes = load_golden(name)
+    n, m, k = 128 * 5 + 52, meta["n_bodies"], len(episodes)     # 5 whole tiles + a 52-env tail, n % 4 == 0
+    t_max = min(400, max(ep["actions"].shape[0] for ep in episodes))
+    init = soa(np.stack([episodes[e % k]["init_state"] for e in range(n)]))
+    actions = np.zeros((t_max, m, 2, n))
+    for j, ep in enumerate(episodes):
+        a = ep["actions"][:t_max]
+        actions[:a.shape[0], :, :, j::k] = a[..., None]
+    envs = [make_env(meta, n, dtype), make_env(meta, n, dtype)]
+    envs[1].set_step_path(use_tma=False)
+    acts = torch.tensor(actions, dtype=envs[0].dtype, device=envs[0].device)
+    for env in envs:
+        env.reset(init_state=init)
+    for t in range(t_max):
+        outs = [env.step(acts[t]) for env in envs]
+        if t % 7 == 0 or t == t_max - 1:
+            for a, b in zip(*outs):
+                assert torch.equal(a, b), f"step {t}"
+    for attr in ("episode_liveness", "timestep", "done_latch", "winner_latch"):
+        assert torch.equal(getattr(envs[0], attr), getattr(envs[1], attr)), attr
+    assert envs[0].stats() == envs[1].stats()
+    assert envs[0].launch_count() > envs[1].launch_count()      # two launches per step (tiles + tail) vs one
