@@ -24,11 +24,19 @@
 
 namespace cav {
 
-constexpr int kTile = 128;  // envs per tile = threads per CTA
-constexpr int kTmaStages = 2;
-#ifndef CAV_MIN_BLOCKS_TMA
-#define CAV_MIN_BLOCKS_TMA 4
+#ifndef CAV_TMA_CONSUMER_WARPS
+#define CAV_TMA_CONSUMER_WARPS 4
 #endif
+#ifndef CAV_MIN_BLOCKS_TMA
+#define CAV_MIN_BLOCKS_TMA 3
+#endif
+constexpr int kConsumerWarps = CAV_TMA_CONSUMER_WARPS;
+constexpr int kTile = 32 * kConsumerWarps;   // envs per tile = consumer threads per CTA
+constexpr int kTmaThreads = kTile + 32;      // + one producer warp that only moves data
+#ifndef CAV_TMA_STAGES
+#define CAV_TMA_STAGES 3
+#endif
+constexpr int kTmaStages = CAV_TMA_STAGES;
 
 // ---------------------------------------------------------------- PTX: mbarrier and bulk asynchronous copies
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -39,6 +47,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -101,22 +112,28 @@ struct TmaRow {               // one row segment per tile: global address of til
 };
 
 template <typename R, int M, bool GENERIC>
-__global__ void __launch_bounds__(kTile, CAV_MIN_BLOCKS_TMA) step_tma_kernel(const __grid_constant__ DevScenario<R> sc,
+#ifdef CAV_TMA_MAXNREG
+__global__ void __launch_bounds__(kTmaThreads) __maxnreg__(CAV_TMA_MAXNREG) step_tma_kernel(
+#else
+__global__ void __launch_bounds__(kTmaThreads, CAV_MIN_BLOCKS_TMA) step_tma_kernel(
+#endif
+    const __grid_constant__ DevScenario<R> sc,
                                                                               const __grid_constant__ EnvBuffers<R> buf,
                                                                               const __grid_constant__ StepIO<R> io,
                                                                               int64_t t_global, int64_t n_tiles) {
   using L = TmaLayout<R, M>;
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);   // [stages] tile landed (producer -> consumers)
+  uint64_t* done = full + kTmaStages;                                    // [stages] tile computed (consumers -> producer)
   TmaRow* in_rows = reinterpret_cast<TmaRow*>(smem + L::kTableOffset);
   TmaRow* out_rows = in_rows + L::kMaxRows;
-  __shared__ int n_in_s, n_out_s;
+  __shared__ int n_in_s, n_out_s, in_bytes_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n = buf.n, lo = buf.lo;
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < kTmaStages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kConsumerWarps); }
     mbar_fence_init();
     // row tables (a few dozen entries, once per CTA)
     int ni = 0, no = 0;
@@ -143,18 +160,18 @@ __global__ void __launch_bounds__(kTile, CAV_MIN_BLOCKS_TMA) step_tma_kernel(con
     if (io.done_out) out(io.done_out, 0, 1, L::oDoneOut);
     if (io.tangent_out) out(io.tangent_out, 0, 1, L::oTangent);
     n_in_s = ni; n_out_s = no;
+    uint32_t total = 0;
+    for (int r = 0; r < ni; ++r) total += in_rows[r].bytes;
+    in_bytes_s = (int)total;
   }
   __syncthreads();
   const int n_in = n_in_s, n_out = n_out_s;
+  const uint32_t in_bytes = (uint32_t)in_bytes_s;
 
   // whole-warp call (warp 0): arm the stage's barrier with the tile's byte count, then one bulk copy per row
   auto issue_loads = [&](int s, int64_t tile) {
     unsigned char* st = smem + s * L::kStageBytes;
-    if (lane == 0) {
-      uint32_t total = 0;
-      for (int r = 0; r < n_in; ++r) total += in_rows[r].bytes;
-      mbar_expect_tx(&full[s], total);
-    }
+    if (lane == 0) mbar_expect_tx(&full[s], in_bytes);
     __syncwarp();
     for (int r = lane; r < n_in; r += 32) {
       const TmaRow row = in_rows[r];
@@ -163,14 +180,37 @@ __global__ void __launch_bounds__(kTile, CAV_MIN_BLOCKS_TMA) step_tma_kernel(con
   };
 
   const int64_t first = blockIdx.x, stride = gridDim.x;
-  if (warp == 0) {
+
+  if (warp == kConsumerWarps) {
+    // ================= producer warp: HBM -> shared (bulk loads), shared -> HBM (bulk stores); no arithmetic
 #pragma unroll
     for (int s = 0; s < kTmaStages; ++s) {
       const int64_t tile = first + (int64_t)s * stride;
       if (tile < n_tiles) issue_loads(s, tile);
     }
+    int it = 0;
+    for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
+      const int s = it % kTmaStages;
+      const uint32_t parity = (uint32_t)(it / kTmaStages) & 1u;
+      unsigned char* st = smem + s * L::kStageBytes;
+      mbar_wait(&done[s], parity);   // every consumer warp has written its results for this tile
+      for (int r = lane; r < n_out; r += 32) {
+        const TmaRow row = out_rows[r];
+        bulk_store(reinterpret_cast<void*>(row.gbase + (unsigned long long)tile * row.bytes), st + row.smem_off, row.bytes);
+      }
+      bulk_commit();
+      const int64_t next = tile + (int64_t)kTmaStages * stride;
+      if (next < n_tiles) {
+        bulk_wait_read_all();   // the stores above have read the stage: it may be overwritten
+        __syncwarp();
+        issue_loads(s, next);
+      }
+    }
+    bulk_wait_read_all();   // shared memory must outlive the last bulk stores
+    return;
   }
 
+  // ================= consumer warps: one env per thread, no block-wide synchronisation
   int it = 0;
   for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
     const int s = it % kTmaStages;
@@ -246,24 +286,11 @@ __global__ void __launch_bounds__(kTile, CAV_MIN_BLOCKS_TMA) step_tma_kernel(con
     st[L::oDoneOut + tid] = res.terminate ? 1 : 0;
     st[L::oTangent + tid] = res.tangent ? 1 : 0;
 
-    // ---- shared memory -> HBM, then refill this stage with the tile two ahead
+    // ---- hand the tile to the producer: writes visible to the bulk-copy engine, one arrival per warp
     fence_async_smem();
-    __syncthreads();
-    if (warp == 0) {
-      for (int r = lane; r < n_out; r += 32) {
-        const TmaRow row = out_rows[r];
-        bulk_store(reinterpret_cast<void*>(row.gbase + (unsigned long long)tile * row.bytes), st + row.smem_off, row.bytes);
-      }
-      bulk_commit();
-      const int64_t next = tile + (int64_t)kTmaStages * stride;
-      if (next < n_tiles) {
-        bulk_wait_read_all();   // the stores above have read the stage: it may be overwritten
-        __syncwarp();
-        issue_loads(s, next);
-      }
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&done[s]);
   }
-  if (warp == 0) bulk_wait_read_all();   // shared memory must outlive the last bulk stores
 }
 
 // Host side: can [lo, hi) of this engine be stepped by the TMA kernel?  Returns the number of whole tiles (0 = no).
@@ -290,13 +317,13 @@ bool launch_step_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const S
   int& res = resident[sc.homogeneous ? 0 : 1];
   if (res == 0) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes) != cudaSuccess) return false;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, kernel, kTile, L::kSmemBytes) != cudaSuccess || res < 1) { res = 0; return false; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, kernel, kTmaThreads, L::kSmemBytes) != cudaSuccess || res < 1) { res = 0; return false; }
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int64_t grid = tiles < (int64_t)sms * res ? tiles : (int64_t)sms * res;
-  kernel<<<(unsigned)grid, kTile, L::kSmemBytes, stream>>>(sc, buf, io, t_global, tiles);
+  kernel<<<(unsigned)grid, kTmaThreads, L::kSmemBytes, stream>>>(sc, buf, io, t_global, tiles);
   *envs_done = tiles * kTile;
   return true;
 }

@@ -23,7 +23,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "launch list rc=$?"
 # full capture of the per-step kernel at 4M envs and of the fused replay kernel
 has prof && timeout 300 python scripts/profile_kernels.py --mode step --envs 4194304 --launches 3 --advance 300 > $out/${tag}_prof_plain.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:step_kernel<double, .int.2, .bool.0,' -s 4 -c 1 -f -o $out/${tag}_step \
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:step_tma_kernel<double' -s 4 -c 1 -f -o $out/${tag}_step \
     python scripts/profile_kernels.py --mode step --envs 4194304 --launches 3 --advance 300 > $out/${tag}_ncu_step.log 2>&1
 echo "ncu step rc=$?"; cat $out/${tag}_prof_plain.log | tail -2
 has prof && timeout 300 python scripts/profile_kernels.py --mode replay --launches 2 > $out/${tag}_prof_plain2.log 2>&1 &&

@@ -89,3 +89,20 @@ def state_err(got, want, dynamic=None):
     plain = np.abs(d) / np.maximum(1.0, np.abs(want[..., 3]))
     ang = np.minimum(plain, np.abs(np.arctan2(np.sin(d), np.cos(d))) / np.maximum(1.0, np.abs(want[..., 3])))
     return float(max(pos.max(), vel.max(), ang.max()))
+
+
+def state_err_trajectory(got, want):
+    """state_err for a whole trajectory [T, M, 4] of an integration carried in float32: the position error is taken
+    relative to the largest |position| the body has reached SO FAR in the episode (running maximum along T) instead of
+    its current |position| (likewise the velocity, a running sum of throttle * dt).  A float32 coordinate is quantised relative to its magnitude when it is stored, so what an
+    fp32 integration can preserve is digits of the trajectory's scale; dividing by the instantaneous |p| would demand
+    absolute accuracy far below one ulp of the values that were summed whenever a body passes near the origin."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    if not got.size:
+        return 0.0
+    scale = np.maximum(1.0, np.maximum.accumulate(np.hypot(want[..., 0], want[..., 1]), axis=0))
+    pos = np.hypot(got[..., 0] - want[..., 0], got[..., 1] - want[..., 1]) / scale
+    vel = np.abs(got[..., 2] - want[..., 2]) / np.maximum(1.0, np.maximum.accumulate(np.abs(want[..., 2]), axis=0))
+    d = got[..., 3] - want[..., 3]
+    ang = np.abs(np.arctan2(np.sin(d), np.cos(d))) / np.maximum(1.0, np.abs(want[..., 3]))
+    return float(max(pos.max(), vel.max(), ang.max()))
