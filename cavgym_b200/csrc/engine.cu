@@ -378,6 +378,21 @@ static int step_range_typed(CavEngine* eng, const DevScenario<R>& sc, EnvBuffers
   return launch_check(eng, "step kernel", launches);
 }
 
+// Replayed actions, T fused steps: whole 128-env tiles through the TMA-pipelined kernel, the ragged tail through the
+// plain one.  The trajectory pointers of the tail launch are the same (env-indexed rows), only the env range differs.
+template <typename R>
+static int replay_typed(CavEngine* eng, const DevScenario<R>& sc, EnvBuffers<R> buf, const StepIO<R>& io, int n_steps,
+                        cudaStream_t stream, int* launches) {
+  const SmallLaunchers<R>* k = small_launchers<R>(eng->m);
+  if (eng->use_tma) {
+    int64_t taken = 0;
+    if (!k->replay_tma(sc, buf, io, eng->t_global, n_steps, stream, &taken)) return fail(CAV_ECUDA, "TMA replay kernel set-up failed");
+    if (taken > 0) { buf.lo += taken; ++*launches; }
+  }
+  if (buf.lo < buf.hi) { k->replay(sc, buf, io, eng->t_global, n_steps, stream); ++*launches; }
+  return CAV_OK;
+}
+
 extern "C" {
 
 const char* cavgym_last_error(void) { return g_error.c_str(); }
@@ -506,14 +521,16 @@ int cavgym_replay(CavEngine* eng, int n_steps, const void* actions, void* state_
   if (!actions) return fail(CAV_EINVAL, "actions is NULL");
   if (eng->has_device_agents) return fail(CAV_ESTATE, "cavgym_replay needs CAV_AGENT_EXTERNAL for every body");
   if (n_steps == 0) return CAV_OK;
+  int launches = 0;
   if (eng->dtype == CAV_F64) {
     StepIO<double> io{(const double*)actions, (double*)state_traj, (double*)reward_traj, done_traj, winner_traj, tangent_traj};
-    small_launchers<double>(eng->m)->replay(eng->sc64, eng->buf64, io, eng->t_global, n_steps, stream);
+    rc = replay_typed(eng, eng->sc64, eng->buf64, io, n_steps, stream, &launches);
   } else {
     StepIO<float> io{(const float*)actions, (float*)state_traj, (float*)reward_traj, done_traj, winner_traj, tangent_traj};
-    small_launchers<float>(eng->m)->replay(eng->sc32, eng->buf32, io, eng->t_global, n_steps, stream);
+    rc = replay_typed(eng, eng->sc32, eng->buf32, io, n_steps, stream, &launches);
   }
-  rc = launch_check(eng, "replay kernel");
+  if (rc) return rc;
+  rc = launch_check(eng, "replay kernel", launches);
   if (rc) return rc;
   eng->t_global += n_steps;
   return CAV_OK;

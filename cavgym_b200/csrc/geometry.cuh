@@ -22,6 +22,13 @@
 
 namespace cav {
 
+#ifdef CAV_DEBUG_TIMES
+__device__ unsigned long long g_dbg[16];
+#define CAV_DBG(i) atomicAdd(&g_dbg[i], 1ull)
+#else
+#define CAV_DBG(i)
+#endif
+
 // a / b to ~2 ulp with a float reciprocal seed and two Newton steps (10 instructions instead of the ~60 of the
 // IEEE division subroutine).  Used only where |b| is a normal float (pixel distances, sines of steering angles).
 __device__ __forceinline__ double fast_div(double a, double b) {
@@ -322,16 +329,70 @@ struct Pose {  // what is needed to rebuild a body's corners: make_rectangle(len
 // body box vs a quad of the scenario tables that is not a rectangle
 template <typename R>
 __device__ __noinline__ int sat_pose_quad(Pose<R> a, const Quad<R>* other, R tau) {
+  CAV_DBG(0);
   Quad<R> qa;
   const Quad<R> qb = *other;
   make_box(a.length, a.width, a.theta, a.c, a.s, a.x, a.y, qa);
   return sat_bits(qa, qb, tau);
 }
 
+// Share of a body box lying on an axis-aligned road across one of its CORNERS: the box crosses one x-edge and one
+// y-edge and is clear of the other two, so box ∩ road = box ∩ {sx x <= bx} ∩ {sy y <= by}.  Two Sutherland–Hodgman
+// stages chained as a stream — every vertex the first stage emits is clipped by the second at once and goes straight
+// into a running shoelace sum — so no vertex list exists and everything stays in registers.  (A pedestrian walking
+// off the end of the road while it crosses the kerb stays in this case for dozens of steps; with the local-memory
+// clipper below one such env made its whole warp several times slower.)  Disjoint boxes give area 0, which is what
+// the reference returns too (intersects() false -> 0).
+template <typename R>
+__device__ __noinline__ R corner_share(Pose<R> a, R sx, R bx, R sy, R by) {
+  Quad<R> q;
+  make_box(a.length, a.width, a.theta, a.c, a.s, a.x, a.y, q);
+  R acc = R(0), fx2 = R(0), fy2 = R(0), px2 = R(0), py2 = R(0);
+  bool have2 = false;
+  auto emit2 = [&](R x, R y) {   // vertex of the final polygon, in order
+    if (have2) acc += px2 * y - x * py2;
+    else { fx2 = x; fy2 = y; have2 = true; }
+    px2 = x; py2 = y;
+  };
+  R f1x = R(0), f1y = R(0), f1d = R(0), q1x = R(0), q1y = R(0), q1d = R(0);
+  bool have1 = false;
+  auto crossing = [](R da, R db) { return (da > R(0) && db < R(0)) || (da < R(0) && db > R(0)); };
+  auto emit1 = [&](R x, R y) {   // vertex of box ∩ first half-plane: clip the edge from the previous one by the second
+    const R d = by - sy * y;
+    if (!have1) {
+      f1x = x; f1y = y; f1d = d; have1 = true;
+    } else if (crossing(q1d, d)) {
+      const R t = fast_div(q1d, q1d - d);
+      emit2(q1x + t * (x - q1x), q1y + t * (y - q1y));
+    }
+    if (d >= R(0)) emit2(x, y);
+    q1x = x; q1y = y; q1d = d;
+  };
+  R d1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d1[i] = bx - sx * q.x[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = (i + 1) & 3;
+    if (d1[i] >= R(0)) emit1(q.x[i], q.y[i]);
+    if (crossing(d1[i], d1[j])) {
+      const R t = fast_div(d1[i], d1[i] - d1[j]);
+      emit1(q.x[i] + t * (q.x[j] - q.x[i]), q.y[i] + t * (q.y[j] - q.y[i]));
+    }
+  }
+  if (have1 && crossing(q1d, f1d)) {   // closing edge of the first stage's polygon
+    const R t = fast_div(q1d, q1d - f1d);
+    emit2(q1x + t * (f1x - q1x), q1y + t * (f1y - q1y));
+  }
+  if (have2) acc += px2 * fy2 - fx2 * py2;
+  return fast_div(rabs(acc) * R(0.5), a.length * a.width);
+}
+
 // Share of a body box lying on a road by the general predicates: rotated roads, road corners, near-tangent
 // configurations.
 template <typename R>
 __device__ __noinline__ Share<R> road_share_general(Pose<R> a, const Quad<R>* road, R tau) {
+  CAV_DBG(1);
   Quad<R> box;
   make_box(a.length, a.width, a.theta, a.c, a.s, a.x, a.y, box);
   const Quad<R> other = *road;

@@ -17,6 +17,12 @@
 namespace cav {
 
 constexpr int kThreads = 128;
+// The multi-step kernels (replay, rollout) are ONE wave of long-running blocks: with 224-thread blocks, two per SM, the
+// 65,536-env configuration is 293 blocks on 296 slots, every env resident from the first step to the last.
+#ifndef CAV_LOOP_THREADS
+#define CAV_LOOP_THREADS 224
+#endif
+constexpr int kLoopThreads = CAV_LOOP_THREADS;
 #ifndef CAV_MIN_BLOCKS_STEP
 #define CAV_MIN_BLOCKS_STEP 4
 #endif
@@ -159,10 +165,10 @@ __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_STEP) step_kernel(con
 
 // Trajectory outputs are [T][...] slabs of the per-step shapes; io.* point at step 0.
 template <typename R, int M, bool GENERIC>
-__global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) replay_kernel(const __grid_constant__ DevScenario<R> sc,
+__global__ void __launch_bounds__(kLoopThreads, CAV_MIN_BLOCKS_LOOP) replay_kernel(const __grid_constant__ DevScenario<R> sc,
                                                           const __grid_constant__ EnvBuffers<R> buf,
                                                           const __grid_constant__ StepIO<R> io, int64_t t_global, int n_steps) {
-  const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t e = buf.lo + (int64_t)blockIdx.x * kLoopThreads + threadIdx.x;
   const int64_t n = buf.n;
   if (e < buf.hi) {
     EnvRegs<R, M> env;
@@ -189,10 +195,10 @@ __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) replay_kernel(c
 }
 
 template <typename R, int M, bool GENERIC>
-__global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_LOOP) rollout_kernel(const __grid_constant__ DevScenario<R> sc,
+__global__ void __launch_bounds__(kLoopThreads, CAV_MIN_BLOCKS_LOOP) rollout_kernel(const __grid_constant__ DevScenario<R> sc,
                                                            const __grid_constant__ EnvBuffers<R> buf, int64_t t_global,
                                                            int n_steps, int auto_reset) {
-  const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t e = buf.lo + (int64_t)blockIdx.x * kLoopThreads + threadIdx.x;
   if (e < buf.hi) {
     EnvRegs<R, M> env;
     load_env<R, M, true>(sc, buf, e, env);
@@ -240,9 +246,13 @@ struct SmallLaunchers {
   // TMA-staged step for replayed actions (kernels_tma.cuh): steps the whole tiles of [lo, hi) it can take and reports how
   // many envs that was (0 = buffers not 16-byte aligned: use `step`); false = launch set-up failed.
   bool (*step_tma)(const DevScenario<R>&, const EnvBuffers<R>&, const StepIO<R>&, int64_t t_global, cudaStream_t, int64_t* envs_done);
+  bool (*replay_tma)(const DevScenario<R>&, const EnvBuffers<R>&, const StepIO<R>&, int64_t t_global, int n_steps, cudaStream_t,
+                     int64_t* envs_done);
 };
 
-template <typename R> inline unsigned grid_for(const EnvBuffers<R>& buf) { return (unsigned)((buf.hi - buf.lo + kThreads - 1) / kThreads); }
+template <typename R> inline unsigned grid_for(const EnvBuffers<R>& buf, int threads = kThreads) {
+  return (unsigned)((buf.hi - buf.lo + threads - 1) / threads);
+}
 
 // sc.homogeneous (set by the host when the scenario qualifies) selects the GENERIC = false instantiation.
 template <typename R, int M>
@@ -260,14 +270,14 @@ void launch_step(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepI
 template <typename R, int M>
 void launch_replay(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t t_global, int n_steps,
                    cudaStream_t stream) {
-  if (sc.homogeneous) replay_kernel<R, M, false><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, io, t_global, n_steps);
-  else replay_kernel<R, M, true><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, io, t_global, n_steps);
+  if (sc.homogeneous) replay_kernel<R, M, false><<<grid_for(buf, kLoopThreads), kLoopThreads, 0, stream>>>(sc, buf, io, t_global, n_steps);
+  else replay_kernel<R, M, true><<<grid_for(buf, kLoopThreads), kLoopThreads, 0, stream>>>(sc, buf, io, t_global, n_steps);
 }
 template <typename R, int M>
 void launch_rollout(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t t_global, int n_steps, int auto_reset,
                     cudaStream_t stream) {
-  if (sc.homogeneous) rollout_kernel<R, M, false><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
-  else rollout_kernel<R, M, true><<<grid_for(buf), kThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
+  if (sc.homogeneous) rollout_kernel<R, M, false><<<grid_for(buf, kLoopThreads), kLoopThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
+  else rollout_kernel<R, M, true><<<grid_for(buf, kLoopThreads), kLoopThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
 }
 template <typename R, int M>
 void launch_reset(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const uint8_t* mask, const R* init, int first_time,

@@ -1,42 +1,55 @@
-// kernels_tma.cuh — the per-step kernel for replayed joint actions (cavgym_step with an `actions` buffer, every body
-// CAV_AGENT_EXTERNAL) as a persistent, TMA-staged stream.
+// kernels_tma.cuh — the two kernels that run on replayed joint actions (every body CAV_AGENT_EXTERNAL), written as
+// warp-specialised TMA pipelines:
 //
-// One CAVEnv.step (environment.py:119-223) over N envs moves ~200 B per env through HBM and keeps ~20 values per
-// env live while it computes.  In the plain thread-per-env kernel (kernels_small.cuh) those values sit in registers
-// from the moment their loads are issued, every access costs a 64-bit address computation, and the only way to hide
-// DRAM latency is more resident warps — which the register footprint forbids.  Here instead:
+//   step_tma_kernel     cavgym_step    one CAVEnv.step (environment.py:119-223) over N envs; persistent CTAs walk
+//                                      128-env tiles; the pipeline runs over TILES
+//   replay_tma_kernel   cavgym_replay  T fused steps with the state in registers; one CTA per 160-env tile; the
+//                                      pipeline runs over TIME STEPS (actions in, trajectory rows out)
 //
-//   * CTAs are persistent (grid = SMs x resident CTAs) and walk tiles of 128 consecutive envs;
-//   * warp 0 brings a tile's SoA rows (state 4M, cos/sin 2M, actions 2M, timestep, liveness, done) into shared
-//     memory with one `cp.async.bulk` (TMA, SASS UBLKCP) per row — each row of a tile is one contiguous 1 KiB
-//     (fp64) / 512 B (fp32) segment because the env index is the fastest axis — completing on an mbarrier;
-//   * tiles are double-buffered: the rows of tile i+1 land while tile i is being computed, so DRAM latency is hidden
-//     without any registers being held for loads in flight;
-//   * each thread reads its env from shared memory (conflict-free: lane i touches word i), runs the same
-//     `transition` as every other kernel, and writes the new state / reward / flags back to shared memory;
-//   * warp 0 sends the output rows to HBM with bulk stores (shared -> global), again one per row.
+// Why: a step moves ~200 B per env through HBM and keeps ~20 values per env live while it computes.  In the plain
+// thread-per-env kernels (kernels_small.cuh) those values sit in registers from the moment their loads are issued,
+// every access costs a 64-bit address computation, and DRAM latency can only be hidden by more resident warps — which
+// the register footprint forbids (ncu: 22 % occupancy, long-scoreboard the top stall).  Here instead
+//   * one PRODUCER warp per CTA moves data and does no arithmetic: it brings a tile's SoA rows into shared memory with
+//     one `cp.async.bulk` per row (TMA engine, SASS UBLKCP) — the env index is the fastest axis, so each row of a tile
+//     is one contiguous segment (1 KiB in fp64) — completing on an mbarrier, and sends result rows back to HBM with
+//     bulk stores (shared -> global);
+//   * CONSUMER warps (one env per thread) wait on that mbarrier, read their env from shared memory (conflict-free:
+//     lane i touches word i), run the same `transition` as every other kernel, write results to shared memory and
+//     hand the stage back with one mbarrier arrival per warp — no block-wide barrier anywhere in the loop;
+//   * kTmaStages stages are in flight, so loads for later tiles / steps land while the current one is computed and no
+//     register is ever held for a load in flight.
 // Per-thread global addressing is left only on the rare paths (heading cache, liveness and done latches, errors).
 //
-// Requirements checked by the host (otherwise the plain kernel runs): every row segment 16-byte aligned (n % 4 == 0,
-// tile-aligned range, 16-byte aligned caller buffers).  A ragged last tile goes through the plain kernel.
+// Alignment (checked by the host, otherwise the plain kernels run): every row segment must start and end on 16 bytes.
+// With n % 16 == 0 a ragged last tile is handled here too (shorter bulk copies); with only n % 4 == 0 the step kernel
+// takes the whole tiles and leaves the tail to the plain kernel.
 #pragma once
 #include "kernels_small.cuh"
 
 namespace cav {
 
-#ifndef CAV_TMA_CONSUMER_WARPS
-#define CAV_TMA_CONSUMER_WARPS 4
+#ifndef CAV_TMA_STEP_WARPS
+#define CAV_TMA_STEP_WARPS 4       // consumer warps per CTA in step_tma_kernel: 128-env tiles
+#endif
+// replay_tma_kernel: a launch is ONE wave of long-running CTAs, so the tile size decides whether every env is resident
+// at once.  The fp64 transition with the state in registers needs 128 registers; 7 consumer warps + the producer are
+// 256 threads, 2 CTAs per SM use the whole register file, and 65,536 envs are 293 tiles of 224 <= 296 slots.
+#ifndef CAV_TMA_REPLAY_WARPS
+#define CAV_TMA_REPLAY_WARPS 7
+#endif
+#ifndef CAV_MIN_BLOCKS_REPLAY
+#define CAV_MIN_BLOCKS_REPLAY 2
 #endif
 #ifndef CAV_MIN_BLOCKS_TMA
 #define CAV_MIN_BLOCKS_TMA 3
 #endif
-constexpr int kConsumerWarps = CAV_TMA_CONSUMER_WARPS;
-constexpr int kTile = 32 * kConsumerWarps;   // envs per tile = consumer threads per CTA
-constexpr int kTmaThreads = kTile + 32;      // + one producer warp that only moves data
 #ifndef CAV_TMA_STAGES
 #define CAV_TMA_STAGES 3
 #endif
 constexpr int kTmaStages = CAV_TMA_STAGES;
+constexpr int kStepWarps = CAV_TMA_STEP_WARPS, kStepTile = 32 * kStepWarps;
+constexpr int kReplayWarps = CAV_TMA_REPLAY_WARPS, kReplayTile = 32 * kReplayWarps;
 
 // ---------------------------------------------------------------- PTX: mbarrier and bulk asynchronous copies
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,11 +96,19 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // make this thread's shared-memory writes (generic proxy) visible to the bulk-copy engine (async proxy)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---------------------------------------------------------------- shared-memory layout of one stage
+// One SoA row as the producer sees it: where its segment for unit 0 (tile 0 / step 0) starts in HBM, how far the next
+// unit's segment is, where it lives in a stage, and the element size (segment bytes = envs in the tile * elem).
+struct TmaRow {
+  unsigned long long gbase, unit_stride;
+  uint32_t smem_off, elem;
+};
+
+// ================================================================ cavgym_step
 template <typename R, int M>
-struct TmaLayout {
-  static constexpr int kRow = kTile * (int)sizeof(R);   // one R row of a tile
-  static constexpr int kRowI = kTile * 4;               // one int32 row
+struct StepLayout {
+  static constexpr int T = kStepTile;
+  static constexpr int kRow = T * (int)sizeof(R);   // one R row of a tile
+  static constexpr int kRowI = T * 4;               // one int32 row
   static constexpr int kLiveRows = M > 1 ? M - 1 : 1;
   static constexpr int oState = 0;                            // R [M*4][T]   in / out (in place)
   static constexpr int oCs = oState + M * 4 * kRow;           // R [M*2][T]   in
@@ -97,51 +118,44 @@ struct TmaLayout {
   static constexpr int oLive = oTep + kRowI;                  // i32 [M-1][T] in   (bodies 1..)
   static constexpr int oWinner = oLive + kLiveRows * kRowI;   // i32 [T]      in (latch) / out
   static constexpr int oDone = oWinner + kRowI;               // u8 [T]       in   (latched done)
-  static constexpr int oDoneOut = oDone + kTile;              // u8 [T]       out
-  static constexpr int oTangent = oDoneOut + kTile;           // u8 [T]       out
-  static constexpr int kStageBytes = oTangent + kTile;        // multiple of 128
+  static constexpr int oDoneOut = oDone + T;                  // u8 [T]       out
+  static constexpr int oTangent = oDoneOut + T;               // u8 [T]       out
+  static constexpr int kStageBytes = oTangent + T;            // multiple of 128
   static constexpr int kMaxRows = M * 4 * 2 + M * 2 * 2 + M + 8;
   static constexpr int kBarOffset = kTmaStages * kStageBytes;
-  static constexpr int kTableOffset = kBarOffset + 64;
-  static constexpr int kSmemBytes = kTableOffset + 2 * kMaxRows * 16;
-};
-
-struct TmaRow {               // one row segment per tile: global address of tile 0, smem offset, bytes (stride = bytes)
-  unsigned long long gbase;
-  uint32_t smem_off, bytes;
+  static constexpr int kTableOffset = kBarOffset + 128;
+  static constexpr int kSmemBytes = kTableOffset + 2 * kMaxRows * (int)sizeof(TmaRow);
 };
 
 template <typename R, int M, bool GENERIC>
-#ifdef CAV_TMA_MAXNREG
-__global__ void __launch_bounds__(kTmaThreads) __maxnreg__(CAV_TMA_MAXNREG) step_tma_kernel(
-#else
-__global__ void __launch_bounds__(kTmaThreads, CAV_MIN_BLOCKS_TMA) step_tma_kernel(
-#endif
-    const __grid_constant__ DevScenario<R> sc,
-                                                                              const __grid_constant__ EnvBuffers<R> buf,
-                                                                              const __grid_constant__ StepIO<R> io,
-                                                                              int64_t t_global, int64_t n_tiles) {
-  using L = TmaLayout<R, M>;
+__global__ void __launch_bounds__(kStepTile + 32, CAV_MIN_BLOCKS_TMA) step_tma_kernel(
+    const __grid_constant__ DevScenario<R> sc, const __grid_constant__ EnvBuffers<R> buf, const __grid_constant__ StepIO<R> io,
+    int64_t t_global, int64_t n_tiles) {
+  using L = StepLayout<R, M>;
+  constexpr int T = kStepTile;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);   // [stages] tile landed (producer -> consumers)
   uint64_t* done = full + kTmaStages;                                    // [stages] tile computed (consumers -> producer)
   TmaRow* in_rows = reinterpret_cast<TmaRow*>(smem + L::kTableOffset);
   TmaRow* out_rows = in_rows + L::kMaxRows;
-  __shared__ int n_in_s, n_out_s, in_bytes_s;
+  __shared__ int n_in_s, n_out_s, in_elems_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n = buf.n, lo = buf.lo;
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kTmaStages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kConsumerWarps); }
+    for (int s = 0; s < kTmaStages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kStepWarps); }
     mbar_fence_init();
     // row tables (a few dozen entries, once per CTA)
-    int ni = 0, no = 0;
+    int ni = 0, no = 0, elems = 0;
     auto in = [&](const void* base, int64_t row, int elem, int off) {
-      in_rows[ni++] = {(unsigned long long)base + (unsigned long long)((row * n + lo) * elem), (uint32_t)off, (uint32_t)(kTile * elem)};
+      in_rows[ni++] = {(unsigned long long)base + (unsigned long long)((row * n + lo) * elem), (unsigned long long)(T * elem),
+                       (uint32_t)off, (uint32_t)elem};
+      elems += elem;
     };
     auto out = [&](void* base, int64_t row, int elem, int off) {
-      out_rows[no++] = {(unsigned long long)base + (unsigned long long)((row * n + lo) * elem), (uint32_t)off, (uint32_t)(kTile * elem)};
+      out_rows[no++] = {(unsigned long long)base + (unsigned long long)((row * n + lo) * elem), (unsigned long long)(T * elem),
+                        (uint32_t)off, (uint32_t)elem};
     };
     for (int k = 0; k < M * 4; ++k) in(buf.state, k, sizeof(R), L::oState + k * L::kRow);
     for (int k = 0; k < M * 2; ++k) in(buf.cs, k, sizeof(R), L::oCs + k * L::kRow);
@@ -159,30 +173,27 @@ __global__ void __launch_bounds__(kTmaThreads, CAV_MIN_BLOCKS_TMA) step_tma_kern
     if (io.winner_out) out(io.winner_out, 0, 4, L::oWinner);
     if (io.done_out) out(io.done_out, 0, 1, L::oDoneOut);
     if (io.tangent_out) out(io.tangent_out, 0, 1, L::oTangent);
-    n_in_s = ni; n_out_s = no;
-    uint32_t total = 0;
-    for (int r = 0; r < ni; ++r) total += in_rows[r].bytes;
-    in_bytes_s = (int)total;
+    n_in_s = ni; n_out_s = no; in_elems_s = elems;
   }
   __syncthreads();
   const int n_in = n_in_s, n_out = n_out_s;
-  const uint32_t in_bytes = (uint32_t)in_bytes_s;
-
-  // whole-warp call (warp 0): arm the stage's barrier with the tile's byte count, then one bulk copy per row
-  auto issue_loads = [&](int s, int64_t tile) {
-    unsigned char* st = smem + s * L::kStageBytes;
-    if (lane == 0) mbar_expect_tx(&full[s], in_bytes);
-    __syncwarp();
-    for (int r = lane; r < n_in; r += 32) {
-      const TmaRow row = in_rows[r];
-      bulk_load(st + row.smem_off, reinterpret_cast<const void*>(row.gbase + (unsigned long long)tile * row.bytes), row.bytes, &full[s]);
-    }
-  };
-
+  const uint32_t in_elems = (uint32_t)in_elems_s;
   const int64_t first = blockIdx.x, stride = gridDim.x;
+  auto envs_in = [&](int64_t tile) { return (uint32_t)((buf.hi - lo - tile * T) < T ? (buf.hi - lo - tile * T) : T); };
 
-  if (warp == kConsumerWarps) {
+  if (warp == kStepWarps) {
     // ================= producer warp: HBM -> shared (bulk loads), shared -> HBM (bulk stores); no arithmetic
+    auto issue_loads = [&](int s, int64_t tile) {
+      unsigned char* st = smem + s * L::kStageBytes;
+      const uint32_t cnt = envs_in(tile);
+      if (lane == 0) mbar_expect_tx(&full[s], in_elems * cnt);
+      __syncwarp();
+      for (int r = lane; r < n_in; r += 32) {
+        const TmaRow row = in_rows[r];
+        bulk_load(st + row.smem_off, reinterpret_cast<const void*>(row.gbase + (unsigned long long)tile * row.unit_stride),
+                  row.elem * cnt, &full[s]);
+      }
+    };
 #pragma unroll
     for (int s = 0; s < kTmaStages; ++s) {
       const int64_t tile = first + (int64_t)s * stride;
@@ -193,10 +204,11 @@ __global__ void __launch_bounds__(kTmaThreads, CAV_MIN_BLOCKS_TMA) step_tma_kern
       const int s = it % kTmaStages;
       const uint32_t parity = (uint32_t)(it / kTmaStages) & 1u;
       unsigned char* st = smem + s * L::kStageBytes;
+      const uint32_t cnt = envs_in(tile);
       mbar_wait(&done[s], parity);   // every consumer warp has written its results for this tile
       for (int r = lane; r < n_out; r += 32) {
         const TmaRow row = out_rows[r];
-        bulk_store(reinterpret_cast<void*>(row.gbase + (unsigned long long)tile * row.bytes), st + row.smem_off, row.bytes);
+        bulk_store(reinterpret_cast<void*>(row.gbase + (unsigned long long)tile * row.unit_stride), st + row.smem_off, row.elem * cnt);
       }
       bulk_commit();
       const int64_t next = tile + (int64_t)kTmaStages * stride;
@@ -217,75 +229,75 @@ __global__ void __launch_bounds__(kTmaThreads, CAV_MIN_BLOCKS_TMA) step_tma_kern
     const uint32_t parity = (uint32_t)(it / kTmaStages) & 1u;
     unsigned char* st = smem + s * L::kStageBytes;
     mbar_wait(&full[s], parity);
-
-    // ---- this thread's env: shared memory -> registers
-    const int64_t e = lo + tile * kTile + tid;
-    R* sS = reinterpret_cast<R*>(st + L::oState);
-    const R* sC = reinterpret_cast<const R*>(st + L::oCs);
-    const R* sA = reinterpret_cast<const R*>(st + L::oAct);
-    R* sRw = reinterpret_cast<R*>(st + L::oReward);
-    int32_t* sT = reinterpret_cast<int32_t*>(st + L::oTep);
-    const int32_t* sL = reinterpret_cast<const int32_t*>(st + L::oLive);
-    EnvRegs<R, M> env;
-    R ext[M][2];
-    env.done = st[L::oDone + tid];
-    env.t_ep = sT[tid];
-    env.winner = -1;
-    env.episode = 0;
-    env.ag_dirty = 0; env.cs_dirty = 0; env.live_dirty = 0;
-    env.live[0] = 0;
-#pragma unroll
-    for (int b = 0; b < M; ++b) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) env.s[b][c] = sS[(b * 4 + c) * kTile + tid];
-      env.cs[b][0] = sC[(b * 2 + 0) * kTile + tid];
-      env.cs[b][1] = sC[(b * 2 + 1) * kTile + tid];
-      ext[b][0] = sA[(b * 2 + 0) * kTile + tid];
-      ext[b][1] = sA[(b * 2 + 1) * kTile + tid];
-      env.held[b][0] = R(0); env.held[b][1] = R(0);
-      if (b > 0) env.live[b] = sL[(b - 1) * kTile + tid];
-    }
-
-    // ---- one transition (same bookkeeping as `advance` in kernels_small.cuh)
-    StepResult<R, M> res;
-    if (env.done) {  // frozen until reset
-#pragma unroll
-      for (int b = 0; b < M; ++b) res.reward[b] = R(0);
-      res.terminate = env.done == 1;
-      res.winner = reinterpret_cast<const int32_t*>(st + L::oWinner)[tid];
-      res.tangent = false;
-    } else {
-      // the new state goes back to shared memory as soon as the bodies have moved
-      auto moved = [&](const EnvRegs<R, M>& now) {
-#pragma unroll
-        for (int b = 0; b < M; ++b)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) sS[(b * 4 + c) * kTile + tid] = now.s[b][c];
-      };
-      transition<R, M, false, GENERIC>(sc, buf, e, t_global, env, ext, res, moved);
-      if (res.invalid) buf.err[e] = 1;
-      if (res.tangent) count_tangent(buf.stats);
-      if (env.done) {
-        score_episode<R, M>(buf, env);
-        buf.done[e] = env.done;
-        buf.winner[e] = env.winner;
-      }
+    if ((uint32_t)tid < envs_in(tile)) {
+      // ---- this thread's env: shared memory -> registers
+      const int64_t e = lo + tile * T + tid;
+      R* sS = reinterpret_cast<R*>(st + L::oState);
+      const R* sC = reinterpret_cast<const R*>(st + L::oCs);
+      const R* sA = reinterpret_cast<const R*>(st + L::oAct);
+      R* sRw = reinterpret_cast<R*>(st + L::oReward);
+      int32_t* sT = reinterpret_cast<int32_t*>(st + L::oTep);
+      const int32_t* sL = reinterpret_cast<const int32_t*>(st + L::oLive);
+      EnvRegs<R, M> env;
+      R ext[M][2];
+      env.done = st[L::oDone + tid];
+      env.t_ep = sT[tid];
+      env.winner = -1;
+      env.episode = 0;
+      env.ag_dirty = 0; env.cs_dirty = 0; env.live_dirty = 0;
+      env.live[0] = 0;
 #pragma unroll
       for (int b = 0; b < M; ++b) {
-        if (env.cs_dirty >> b & 1u) {   // heading changed: refresh the cached cos/sin (rare)
-          buf.cs[((int64_t)b * 2 + 0) * n + e] = env.cs[b][0];
-          buf.cs[((int64_t)b * 2 + 1) * n + e] = env.cs[b][1];
-        }
-        if (b > 0 && (env.live_dirty >> b & 1u)) buf.liveness[(int64_t)b * n + e] = env.live[b];
-      }
-      sT[tid] = env.t_ep;
-    }
 #pragma unroll
-    for (int b = 0; b < M; ++b) sRw[b * kTile + tid] = res.reward[b];
-    reinterpret_cast<int32_t*>(st + L::oWinner)[tid] = res.winner;
-    st[L::oDoneOut + tid] = res.terminate ? 1 : 0;
-    st[L::oTangent + tid] = res.tangent ? 1 : 0;
+        for (int c = 0; c < 4; ++c) env.s[b][c] = sS[(b * 4 + c) * T + tid];
+        env.cs[b][0] = sC[(b * 2 + 0) * T + tid];
+        env.cs[b][1] = sC[(b * 2 + 1) * T + tid];
+        ext[b][0] = sA[(b * 2 + 0) * T + tid];
+        ext[b][1] = sA[(b * 2 + 1) * T + tid];
+        env.held[b][0] = R(0); env.held[b][1] = R(0);
+        if (b > 0) env.live[b] = sL[(b - 1) * T + tid];
+      }
 
+      // ---- one transition (same bookkeeping as `advance` in kernels_small.cuh)
+      StepResult<R, M> res;
+      if (env.done) {  // frozen until reset
+#pragma unroll
+        for (int b = 0; b < M; ++b) res.reward[b] = R(0);
+        res.terminate = env.done == 1;
+        res.winner = reinterpret_cast<const int32_t*>(st + L::oWinner)[tid];
+        res.tangent = false;
+      } else {
+        // the new state goes back to shared memory as soon as the bodies have moved
+        auto moved = [&](const EnvRegs<R, M>& now) {
+#pragma unroll
+          for (int b = 0; b < M; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sS[(b * 4 + c) * T + tid] = now.s[b][c];
+        };
+        transition<R, M, false, GENERIC>(sc, buf, e, t_global, env, ext, res, moved);
+        if (res.invalid) buf.err[e] = 1;
+        if (res.tangent) count_tangent(buf.stats);
+        if (env.done) {
+          score_episode<R, M>(buf, env);
+          buf.done[e] = env.done;
+          buf.winner[e] = env.winner;
+        }
+#pragma unroll
+        for (int b = 0; b < M; ++b) {
+          if (env.cs_dirty >> b & 1u) {   // heading changed: refresh the cached cos/sin (rare)
+            buf.cs[((int64_t)b * 2 + 0) * n + e] = env.cs[b][0];
+            buf.cs[((int64_t)b * 2 + 1) * n + e] = env.cs[b][1];
+          }
+          if (b > 0 && (env.live_dirty >> b & 1u)) buf.liveness[(int64_t)b * n + e] = env.live[b];
+        }
+        sT[tid] = env.t_ep;
+      }
+#pragma unroll
+      for (int b = 0; b < M; ++b) sRw[b * T + tid] = res.reward[b];
+      reinterpret_cast<int32_t*>(st + L::oWinner)[tid] = res.winner;
+      st[L::oDoneOut + tid] = res.terminate ? 1 : 0;
+      st[L::oTangent + tid] = res.tangent ? 1 : 0;
+    }
     // ---- hand the tile to the producer: writes visible to the bulk-copy engine, one arrival per warp
     fence_async_smem();
     __syncwarp();
@@ -293,44 +305,253 @@ __global__ void __launch_bounds__(kTmaThreads, CAV_MIN_BLOCKS_TMA) step_tma_kern
   }
 }
 
-// Host side: can [lo, hi) of this engine be stepped by the TMA kernel?  Returns the number of whole tiles (0 = no).
+// ================================================================ cavgym_replay
+//   full[s]   producer -> consumers   actions of step t (stage s = t % S) have landed            (tx count)
+//   done[s]   consumers -> producer   step t computed: actions consumed, trajectory rows written (one arrival per warp)
+//   empty[s]  producer -> consumers   the bulk stores of the step that last used stage s have read it
+template <typename R, int M>
+struct ReplayLayout {
+  static constexpr int T = kReplayTile;
+  static constexpr int kRow = T * (int)sizeof(R);
+  static constexpr int oAct = 0;                          // R [M*2][T]   in
+  static constexpr int oState = oAct + M * 2 * kRow;      // R [M*4][T]   out
+  static constexpr int oReward = oState + M * 4 * kRow;   // R [M][T]     out
+  static constexpr int oWinner = oReward + M * kRow;      // i32 [T]      out
+  static constexpr int oDoneOut = oWinner + T * 4;        // u8 [T]       out
+  static constexpr int oTangent = oDoneOut + T;           // u8 [T]       out
+  static constexpr int kStageBytes = ((oTangent + T + 127) / 128) * 128;
+  static constexpr int kMaxRows = M * 4 + M * 2 + M + 4;
+  static constexpr int kBarOffset = kTmaStages * kStageBytes;
+  static constexpr int kTableOffset = kBarOffset + 128;
+  static constexpr int kSmemBytes = kTableOffset + 2 * kMaxRows * (int)sizeof(TmaRow);
+};
+
+#ifdef CAV_REPLAY_MAXNREG
+template <typename R, int M, bool GENERIC>
+__global__ void __maxnreg__(CAV_REPLAY_MAXNREG) replay_tma_kernel(
+#else
+template <typename R, int M, bool GENERIC>
+__global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) replay_tma_kernel(
+#endif
+
+    const __grid_constant__ DevScenario<R> sc, const __grid_constant__ EnvBuffers<R> buf, const __grid_constant__ StepIO<R> io,
+    int64_t t_global, int n_steps) {
+  using L = ReplayLayout<R, M>;
+  constexpr int T = kReplayTile;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* done = full + kTmaStages;
+  uint64_t* empty = done + kTmaStages;
+  TmaRow* in_rows = reinterpret_cast<TmaRow*>(smem + L::kTableOffset);
+  TmaRow* out_rows = in_rows + L::kMaxRows;
+  __shared__ int n_out_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n = buf.n;
+  const int64_t tile_lo = buf.lo + (int64_t)blockIdx.x * T;   // first env of this CTA's tile
+  const uint32_t cnt = (uint32_t)((buf.hi - tile_lo) < T ? (buf.hi - tile_lo) : T);
+  constexpr int n_in = M * 2;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kReplayWarps); mbar_init(&empty[s], 1); }
+    mbar_fence_init();
+    int no = 0;
+    auto out = [&](void* base, int64_t rows_per_step, int64_t row, int elem, int off) {
+      out_rows[no++] = {(unsigned long long)base + (unsigned long long)((row * n + tile_lo) * elem),
+                        (unsigned long long)(rows_per_step * n * elem), (uint32_t)off, (uint32_t)elem};
+    };
+    for (int k = 0; k < n_in; ++k)
+      in_rows[k] = {(unsigned long long)io.actions + (unsigned long long)((k * n + tile_lo) * (int64_t)sizeof(R)),
+                    (unsigned long long)((int64_t)M * 2 * n * (int64_t)sizeof(R)), (uint32_t)(L::oAct + k * L::kRow), (uint32_t)sizeof(R)};
+    if (io.state_out) for (int k = 0; k < M * 4; ++k) out(io.state_out, M * 4, k, sizeof(R), L::oState + k * L::kRow);
+    if (io.reward_out) for (int b = 0; b < M; ++b) out(io.reward_out, M, b, sizeof(R), L::oReward + b * L::kRow);
+    if (io.winner_out) out(io.winner_out, 1, 0, 4, L::oWinner);
+    if (io.done_out) out(io.done_out, 1, 0, 1, L::oDoneOut);
+    if (io.tangent_out) out(io.tangent_out, 1, 0, 1, L::oTangent);
+    n_out_s = no;
+  }
+  __syncthreads();
+  const int n_out = n_out_s;
+
+  if (warp == kReplayWarps) {
+    // ================= producer warp
+    auto issue_loads = [&](int s, int t) {
+      unsigned char* st = smem + s * L::kStageBytes;
+      if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(n_in * sizeof(R)) * cnt);
+      __syncwarp();
+      for (int r = lane; r < n_in; r += 32) {
+        const TmaRow row = in_rows[r];
+        bulk_load(st + row.smem_off, reinterpret_cast<const void*>(row.gbase + (unsigned long long)t * row.unit_stride), row.elem * cnt,
+                  &full[s]);
+      }
+    };
+    for (int t = 0; t < kTmaStages && t < n_steps; ++t) issue_loads(t, t);
+    for (int t = 0; t < n_steps; ++t) {
+      const int s = t % kTmaStages;
+      const uint32_t parity = (uint32_t)(t / kTmaStages) & 1u;
+      unsigned char* st = smem + s * L::kStageBytes;
+      mbar_wait(&done[s], parity);
+      for (int r = lane; r < n_out; r += 32) {
+        const TmaRow row = out_rows[r];
+        bulk_store(reinterpret_cast<void*>(row.gbase + (unsigned long long)t * row.unit_stride), st + row.smem_off, row.elem * cnt);
+      }
+      bulk_commit();
+      if (t + kTmaStages < n_steps) issue_loads(s, t + kTmaStages);   // the action rows of stage s were consumed
+      // every lane waits until all but the newest S - 2 of its store groups have read shared memory; then the stage of
+      // step t - (S - 2) may be written again
+      asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kTmaStages >= 2 ? kTmaStages - 2 : 0) : "memory");
+      __syncwarp();
+      const int freed = t - (kTmaStages >= 2 ? kTmaStages - 2 : 0);
+      if (freed >= 0 && lane == 0) mbar_arrive(&empty[freed % kTmaStages]);
+    }
+    bulk_wait_read_all();
+    return;
+  }
+
+  // ================= consumer warps
+  const bool active = (uint32_t)tid < cnt;
+  const int64_t e = tile_lo + (active ? tid : 0);
+#ifdef CAV_DEBUG_TIMES
+  unsigned long long t_start;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+#endif
+  EnvRegs<R, M> env;
+  load_env<R, M, false>(sc, buf, e, env);
+  const bool was_live = env.done == 0;
+  for (int t = 0; t < n_steps; ++t) {
+#ifdef CAV_DEBUG_TIMES
+    if (buf.uni_override && lane == 0 && blockIdx.x < 4 && t < 60) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      const_cast<double*>(buf.uni_override)[4096 + ((blockIdx.x * 8 + warp) * 60 + t)] = (double)(now - t_start);
+    }
+#endif
+    const int s = t % kTmaStages;
+    const uint32_t parity = (uint32_t)(t / kTmaStages) & 1u;
+    unsigned char* st = smem + s * L::kStageBytes;
+    mbar_wait(&full[s], parity);
+    StepResult<R, M> res;
+    if (active) {
+      const R* sA = reinterpret_cast<const R*>(st + L::oAct);
+      R ext[M][2];
+#pragma unroll
+      for (int b = 0; b < M; ++b) { ext[b][0] = sA[(b * 2 + 0) * T + tid]; ext[b][1] = sA[(b * 2 + 1) * T + tid]; }
+      if (env.done) {  // frozen until reset
+#pragma unroll
+        for (int b = 0; b < M; ++b) res.reward[b] = R(0);
+        res.terminate = env.done == 1;
+        res.winner = env.winner;
+        res.tangent = false;
+      } else {
+        transition<R, M, false, GENERIC>(sc, buf, e, t_global + t, env, ext, res);
+        if (res.invalid) buf.err[e] = 1;
+        if (res.tangent) count_tangent(buf.stats);
+        if (env.done) score_episode<R, M>(buf, env);
+      }
+    }
+    // the stage's output rows are free once the stores of the step that used it last have read them
+    mbar_wait(&empty[s], parity ^ 1u);
+    if (active && n_out > 0) {
+      R* sS = reinterpret_cast<R*>(st + L::oState);
+      R* sRw = reinterpret_cast<R*>(st + L::oReward);
+#pragma unroll
+      for (int b = 0; b < M; ++b) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sS[(b * 4 + c) * T + tid] = env.s[b][c];
+        sRw[b * T + tid] = res.reward[b];
+      }
+      reinterpret_cast<int32_t*>(st + L::oWinner)[tid] = res.winner;
+      st[L::oDoneOut + tid] = res.terminate ? 1 : 0;
+      st[L::oTangent + tid] = res.tangent ? 1 : 0;
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&done[s]);
+  }
+  if (active && was_live) store_env<R, M, false>(sc, buf, e, env, false);
+#ifdef CAV_DEBUG_TIMES
+  if (buf.uni_override && tid == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    const_cast<double*>(buf.uni_override)[blockIdx.x * 2] = (double)t_start;
+    const_cast<double*>(buf.uni_override)[blockIdx.x * 2 + 1] = (double)now;
+    if (blockIdx.x == 0) for (int i = 0; i < 16; ++i) const_cast<double*>(buf.uni_override)[2048 + i] = (double)g_dbg[i];
+  }
+#endif
+}
+
+// ================================================================ host side
+// Which part of [lo, hi) can a TMA kernel with `tile`-env tiles take?  Returns the number of envs (0 = none).
+// Every bulk copy must start and end on 16 bytes: rows of `elem`-byte words start at (row * n + lo + k * tile) * elem.
 template <typename R>
-inline int64_t tma_tiles(const EnvBuffers<R>& buf, const StepIO<R>& io) {
+inline int64_t tma_span(const EnvBuffers<R>& buf, const StepIO<R>& io, int tile, bool u8_rows_strided) {
   auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  if (!io.actions || buf.n % 4 != 0 || buf.lo % kTile != 0) return 0;
+  if (!io.actions || buf.n % 4 != 0 || buf.lo % 16 != 0) return 0;
   if (!aligned(io.actions) || !aligned(io.state_out) || !aligned(io.reward_out) || !aligned(io.done_out) || !aligned(io.winner_out) ||
       !aligned(io.tangent_out))
     return 0;
-  return (buf.hi - buf.lo) / kTile;
+  const int64_t span = buf.hi - buf.lo;
+  if (buf.n % 16 == 0 && span % 16 == 0) return span;   // ragged last tile handled in the kernel
+  if (u8_rows_strided) return 0;                         // u8 trajectory rows advance by n bytes per step
+  return span / tile * tile;
 }
 
 template <typename R, int M>
 bool launch_step_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t t_global, cudaStream_t stream,
                      int64_t* envs_done) {
-  using L = TmaLayout<R, M>;
+  using L = StepLayout<R, M>;
   *envs_done = 0;
-  const int64_t tiles = tma_tiles(buf, io);
-  if (tiles == 0) return true;
+  const int64_t span = tma_span(buf, io, kStepTile, false);
+  if (span == 0) return true;
+  const int64_t tiles = (span + kStepTile - 1) / kStepTile;
   static int resident[2] = {0, 0};  // [generic]: CTAs per SM, queried once per instantiation
   static int sms = 0;
   auto kernel = sc.homogeneous ? step_tma_kernel<R, M, false> : step_tma_kernel<R, M, true>;
   int& res = resident[sc.homogeneous ? 0 : 1];
   if (res == 0) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes) != cudaSuccess) return false;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, kernel, kTmaThreads, L::kSmemBytes) != cudaSuccess || res < 1) { res = 0; return false; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, kernel, kStepTile + 32, L::kSmemBytes) != cudaSuccess || res < 1) {
+      res = 0;
+      return false;
+    }
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  EnvBuffers<R> range = buf;
+  range.hi = buf.lo + span;
   const int64_t grid = tiles < (int64_t)sms * res ? tiles : (int64_t)sms * res;
-  kernel<<<(unsigned)grid, kTmaThreads, L::kSmemBytes, stream>>>(sc, buf, io, t_global, tiles);
-  *envs_done = tiles * kTile;
+  kernel<<<(unsigned)grid, kStepTile + 32, L::kSmemBytes, stream>>>(sc, range, io, t_global, tiles);
+  *envs_done = span;
+  return true;
+}
+
+template <typename R, int M>
+bool launch_replay_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t t_global, int n_steps,
+                       cudaStream_t stream, int64_t* envs_done) {
+  using L = ReplayLayout<R, M>;
+  *envs_done = 0;
+  const int64_t span = tma_span(buf, io, kReplayTile, io.done_out != nullptr || io.tangent_out != nullptr);
+  if (span == 0) return true;
+  static bool ready[2] = {false, false};
+  auto kernel = sc.homogeneous ? replay_tma_kernel<R, M, false> : replay_tma_kernel<R, M, true>;
+  bool& ok = ready[sc.homogeneous ? 0 : 1];
+  if (!ok) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes) != cudaSuccess) return false;
+    ok = true;
+  }
+  EnvBuffers<R> range = buf;
+  range.hi = buf.lo + span;
+  const int64_t tiles = (span + kReplayTile - 1) / kReplayTile;
+  kernel<<<(unsigned)tiles, kReplayTile + 32, L::kSmemBytes, stream>>>(sc, range, io, t_global, n_steps);
+  *envs_done = span;
   return true;
 }
 
 template <typename R, int M>
 constexpr SmallLaunchers<R> make_launchers() {
-  return {&launch_step<R, M>, &launch_replay<R, M>, &launch_rollout<R, M>, &launch_reset<R, M>, &launch_step_tma<R, M>};
+  return {&launch_step<R, M>, &launch_replay<R, M>, &launch_rollout<R, M>, &launch_reset<R, M>, &launch_step_tma<R, M>,
+          &launch_replay_tma<R, M>};
 }
 
 }  // namespace cav

@@ -95,7 +95,16 @@ __device__ __forceinline__ R road_share(const DevScenario<R>& sc, const EnvRegs<
     if (lo <= -tau && hi >= tau && opposite >= tau) {
       const R ac = rabs(env.cs[b][0]), as = rabs(env.cs[b][1]);
       const R hl = sc.bodies[b].k.hl, hw = sc.bodies[b].k.hw;
+      CAV_DBG(7);
       const R p = kerb_share(lo + (x_edge ? ex : ey), (x_edge ? ac : as) * hl, (x_edge ? as : ac) * hw);
+      if (rabs(p - R(0.5)) < tau) near = true;
+      return p;
+    }
+    // a corner of the road: one x-edge and one y-edge crossed (or touched), the opposite edges clearly inside
+    if (mx < tau && my < tau && rmax(m0, m1) >= tau && rmax(m2, m3) >= tau) {
+      const bool low_x = m0 < m1, low_y = m2 < m3;
+      const R p = corner_share(body_pose<R, M>(sc, env, b), low_x ? R(-1) : R(1), low_x ? -rd.x0 : rd.x1, low_y ? R(-1) : R(1),
+                               low_y ? -rd.y0 : rd.y1);
       if (rabs(p - R(0.5)) < tau) near = true;
       return p;
     }
@@ -226,6 +235,7 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
   {
     const R margin = (env.s[0][0] - ex[0]) - W;  // all four ego corners x > viewer_width  <=>  min corner x > W
     if (margin > -tau) {                         // only the last steps of an episode get here
+      CAV_DBG(9);
       if (margin < tau) tangent = true;
       if (margin > R(0)) { terminate = true; win_ego = true; }
     }
@@ -289,6 +299,7 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
       const EgoMargins<R> m = ego_margins(f, env.s[b][0], env.s[b][1], env.cs[b][0], env.cs[b][1], sc.bodies[b].k.hl,
                                           sc.bodies[b].k.hw, tau);
       if (m.all_clear) continue;
+      CAV_DBG(8);
       if (ego_mode) {   // environment.py:183-193: ego box, then the braking zone
         bool h = margin_hit(m.ego, tau, tangent);
         if (!h && f.have) h = margin_hit(m.braking, tau, tangent);

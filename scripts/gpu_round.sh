@@ -27,6 +27,6 @@ timeout 900 ncu --set full --clock-control none --import-source on --kernel-name
     python scripts/profile_kernels.py --mode step --envs 4194304 --launches 3 --advance 300 > $out/${tag}_ncu_step.log 2>&1
 echo "ncu step rc=$?"; cat $out/${tag}_prof_plain.log | tail -2
 has prof && timeout 300 python scripts/profile_kernels.py --mode replay --launches 2 > $out/${tag}_prof_plain2.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:replay_kernel<double' -s 1 -c 1 -f -o $out/${tag}_replay \
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:replay_tma_kernel<double' -s 1 -c 1 -f -o $out/${tag}_replay \
     python scripts/profile_kernels.py --mode replay --launches 2 > $out/${tag}_ncu_replay.log 2>&1
 echo "ncu replay rc=$?"; tail -1 $out/${tag}_prof_plain2.log

@@ -3,5 +3,5 @@
 for lib in "$@"; do
   echo "== $lib"
   CAVGYM_LIB=$PWD/$lib python scripts/quick_parity.py 2>&1 | tail -1
-  CAVGYM_LIB=$PWD/$lib python scripts/profile_kernels.py --mode step --envs 4194304 --launches 6 --advance 300 2>&1 | tail -1
+  CAVGYM_LIB=$PWD/$lib python scripts/replay_scaling.py 2>&1 | grep -E "steps   (10|50):"
 done

@@ -159,14 +159,15 @@ def test_missing_actions_is_an_error():
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("n", [128 * 5 + 52, 128 * 5 + 48])   # n % 16 != 0: whole tiles + plain tail; n % 16 == 0: ragged tile in-kernel
 @pytest.mark.parametrize("name", ["pedestrians_rc_seed0", "pedestrians3_rc_seed2", "crossroads_random_all_seed6", "pelican_random_all_seed10"])
-def test_tma_step_kernel_is_bitwise_equal_to_plain_kernel(name, dtype):
+def test_tma_step_kernel_is_bitwise_equal_to_plain_kernel(name, dtype, n):
     """cavgym_step on replayed actions runs the persistent TMA-staged kernel over whole 128-env tiles and the plain
     thread-per-env kernel over the ragged tail; both must produce the same bits as the plain kernel alone, every step,
     for every output (state, reward, done, winner, tangent, liveness, timestep)."""
     import torch
     meta, episodes = load_golden(name)
-    n, m, k = 128 * 5 + 52, meta["n_bodies"], len(episodes)     # 5 whole tiles + a 52-env tail, n % 4 == 0
+    m, k = meta["n_bodies"], len(episodes)
     t_max = min(400, max(ep["actions"].shape[0] for ep in episodes))
     init = soa(np.stack([episodes[e % k]["init_state"] for e in range(n)]))
     actions = np.zeros((t_max, m, 2, n))
@@ -186,4 +187,87 @@ def test_tma_step_kernel_is_bitwise_equal_to_plain_kernel(name, dtype):
     for attr in ("episode_liveness", "timestep", "done_latch", "winner_latch"):
         assert torch.equal(getattr(envs[0], attr), getattr(envs[1], attr)), attr
     assert envs[0].stats() == envs[1].stats()
-    assert envs[0].launch_count() > envs[1].launch_count()      # two launches per step (tiles + tail) vs one
+    if n % 16:
+        assert envs[0].launch_count() > envs[1].launch_count()  # two launches per step (tiles + tail) vs one
+    else:
+        assert envs[0].launch_count() == envs[1].launch_count()
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("n", [160 * 2 + 84, 160 * 2 + 96])   # n % 16 != 0 / == 0 (ragged last tile handled in-kernel)
+@pytest.mark.parametrize("name", ["pedestrians_rc_seed0", "busstop_random_all_seed8"])
+def test_tma_replay_kernel_is_bitwise_equal_to_plain_kernel(name, dtype, n):
+    """cavgym_replay: the time-pipelined TMA kernel (whole tiles) + plain kernel (tail) against the plain kernel alone,
+    in chunks of 1, 2, 3, 7 and 150 steps (fewer steps than pipeline stages included), with and without trajectories."""
+    import torch
+    meta, episodes = load_golden(name)
+    m, k = meta["n_bodies"], len(episodes)
+    t_max = min(320, max(ep["actions"].shape[0] for ep in episodes))
+    init = soa(np.stack([episodes[e % k]["init_state"] for e in range(n)]))
+    actions = np.zeros((t_max, m, 2, n))
+    for j, ep in enumerate(episodes):
+        a = ep["actions"][:t_max]
+        actions[:a.shape[0], :, :, j::k] = a[..., None]
+    envs = [make_env(meta, n, dtype), make_env(meta, n, dtype)]
+    envs[1].set_step_path(use_tma=False)
+    acts = torch.tensor(actions, dtype=envs[0].dtype, device=envs[0].device)
+    for env in envs:
+        env.reset(init_state=init)
+    t = 0
+    for chunk, record in ((1, ("state", "done")), (2, ()), (3, ("reward", "winner", "tangent")), (7, ("state",)),
+                          (150, ("state", "reward", "done", "winner", "tangent")), (10 ** 6, ("state", "reward", "done"))):
+        take = min(chunk, t_max - t)
+        outs = [env.replay(acts[t:t + take], record=record) for env in envs]
+        for key in record:
+            assert torch.equal(outs[0][key], outs[1][key]), (chunk, key)
+        assert torch.equal(envs[0].state, envs[1].state), chunk
+        t += take
+    for attr in ("episode_liveness", "timestep", "done_latch", "winner_latch"):
+        assert torch.equal(getattr(envs[0], attr), getattr(envs[1], attr)), attr
+    assert envs[0].stats() == envs[1].stats()
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_road_kerb_and_corner_shares_match_oracle(dtype):
+    """percentage_intersects (geometry.py:80-87) on the engine's closed-form paths: pedestrians are placed astride the
+    kerbs and the four corners of the road with random headings (and a few clear of it / inside it), stepped with small
+    steering so that the boxes rotate, and the road-share dependent outputs (reward, liveness) are compared with the
+    CPU oracle, whose clipping is the reference's formulation with exact predicates."""
+    from oracle.oracle import Oracle
+    meta, _ = load_golden("pedestrians_rc_seed0")
+    cfg = meta["config"]
+    cfg["terminate_collisions"], cfg["terminate_ego_zones"] = "none", False   # keep every env alive: only shares matter
+    comp = compile_from_meta(meta)
+    n, steps = 4096, 12
+    rng = np.random.default_rng(5)
+    x0, x1, y0, y1 = 0.0, 1584.0, -58.4, 58.4                           # the stock road rectangle (SURVEY appendix A)
+    where = rng.integers(0, 8, n)
+    px = np.where(where % 4 == 0, x0, np.where(where % 4 == 1, x1, rng.uniform(x0 + 30, x1 - 30, n))) + rng.uniform(-9, 9, n)
+    py = np.where(where < 6, np.where(rng.random(n) < 0.5, y0, y1), rng.uniform(-40, 40, n)) + rng.uniform(-9, 9, n)
+    init = np.zeros((2, 4, n))
+    init[0] = np.array([600.0, 29.2, 0.0, 0.0])[:, None]                # ego parked mid-road
+    init[1, 0], init[1, 1], init[1, 2], init[1, 3] = px, py, 22.4, rng.uniform(-np.pi, np.pi, n)
+    actions = np.zeros((steps, 2, 2, n))
+    actions[:, 1, 1] = rng.uniform(-0.4 * np.pi, 0.4 * np.pi, (steps, n)) * (rng.random((steps, n)) < 0.5)
+    from cavgym_b200 import BatchedCAVEnv
+    env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=comp)
+    oracle = Oracle(comp, n, threads=8)
+    if dtype == "float32":
+        init, actions = init.astype(np.float32).astype(np.float64), actions.astype(np.float32).astype(np.float64)
+    env.reset(init_state=init)
+    oracle.reset(init_state=init)
+    out = env.replay(actions)
+    want_state, want_reward, want_done, want_winner, _ = oracle.replay(actions)
+    reward = out["reward"].double().cpu().numpy()
+    tangent = out["tangent"].cpu().numpy().astype(bool)
+    tol = 1e-9 if dtype == "float64" else 2e-3
+    err = np.abs(reward - want_reward)
+    assert err[:, 1].max() < tol * 4.0, err[:, 1].max()                 # reward = cost_step (4) * share terms
+    live = env.episode_liveness.cpu().numpy()
+    mism = live[1] != oracle.liveness[1]
+    assert not np.any(mism & ~tangent.any(axis=0))                      # p > 0.5 events identical off flagged steps
+    if dtype == "float64":
+        assert mism.sum() == 0
+    # the placement really exercises every class of case: share 0, share 1 and > 1000 distinct fractional shares
+    share = ((1584.0 - 600.0) / 1584.0 * 4.0 - want_reward[0, 1]) / 4.0
+    assert (share < 1e-12).sum() > 100 and (share > 1 - 1e-12).sum() > 100 and len(np.unique(np.round(share, 9))) > 1000
