@@ -246,7 +246,8 @@ def run_ours(args):
         rs = 8 if dtype == "float64" else 4
         out["e2e"] = {"value": float(tot.item()) / float(tt.item()), "unit": "env-steps/s",
                       "h2d_bytes_per_step": m * 2 * n * rs, "d2h_bytes_per_step": m * 4 * n * rs + m * n * rs + n * 6,
-                      "steps": e2e_steps, "api": "cavgym_step_host (pinned host buffers, 8 env-chunks over 3 streams)"}
+                      "steps": e2e_steps, "api": "cavgym_step_host, pinned host buffers, zero copy: one TMA-staged launch per step reads the actions "
+                             "from and writes state/reward/done/winner/tangent to host memory over PCIe"}
 
     # ---- episode statistics: the single NCCL reduce over NVLink ---------------------
     stats = env.stats()

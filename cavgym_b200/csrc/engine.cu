@@ -273,6 +273,7 @@ struct CavEngine {
   uint64_t seed = 0;
   bool has_external = false, has_device_agents = false;
   bool use_tma = true;  // cavgym_set_step_path: 0 = plain thread-per-env kernel only
+  bool zero_copy_host = true;  // cavgym_set_host_path: 0 = always stage host buffers through device copies
   double tau = 1e-7;
   CavScenario host{};
   std::vector<CavBody> bodies;
@@ -555,6 +556,31 @@ int cavgym_step_host(CavEngine* eng, const void* actions, void* state_out, void*
     if ((rc = dev_alloc(eng, &eng->d_winner, (size_t)n))) return rc;
   }
   CUDA_TRY(cudaDeviceSynchronize());  // order after whatever the caller queued on other streams
+
+  // Zero-copy path: when every caller buffer is pinned (page-locked, mapped) host memory, the step kernel reads the
+  // actions and writes the results over PCIe itself — the TMA producer warp's bulk copies take host addresses just as
+  // they take HBM addresses — so the whole call is ONE launch with transfers and arithmetic overlapped tile by tile,
+  // instead of a chain of chunked cudaMemcpyAsync calls whose launch overheads dominate at this batch size.
+  if (eng->zero_copy_host) {
+    const void* host[6] = {actions, state_out, reward_out, done_out, winner_out, tangent_flag_out};
+    void* dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool all_mapped = true;
+    for (int i = 0; i < 6 && all_mapped; ++i) {
+      if (!host[i]) continue;
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, host[i]) != cudaSuccess) { cudaGetLastError(); all_mapped = false; break; }
+      if (attr.type == cudaMemoryTypeHost && attr.devicePointer) dev[i] = attr.devicePointer;
+      else all_mapped = false;
+    }
+    if (all_mapped) {
+      cudaStream_t s = eng->pipe[0];
+      rc = step_range(eng, 0, n, dev[0], dev[1], dev[2], (uint8_t*)dev[3], (int32_t*)dev[4], (uint8_t*)dev[5], s);
+      if (rc) return rc;
+      CUDA_TRY(cudaStreamSynchronize(s));
+      eng->t_global += 1;
+      return CAV_OK;
+    }
+  }
   const int64_t chunks = n >= (1 << 16) ? 8 : (n >= (1 << 12) ? 2 : 1);
   char* d_state = (char*)(eng->dtype == CAV_F64 ? (void*)eng->buf64.state : (void*)eng->buf32.state);
   for (int64_t c = 0; c < chunks; ++c) {
@@ -653,6 +679,12 @@ int cavgym_set_action_logging(CavEngine* eng, int enabled) {
 int cavgym_set_step_path(CavEngine* eng, int use_tma) {
   if (!eng) return fail(CAV_EINVAL, "engine is NULL");
   eng->use_tma = use_tma != 0;
+  return CAV_OK;
+}
+
+int cavgym_set_host_path(CavEngine* eng, int zero_copy) {
+  if (!eng) return fail(CAV_EINVAL, "engine is NULL");
+  eng->zero_copy_host = zero_copy != 0;
   return CAV_OK;
 }
 

@@ -165,6 +165,10 @@ class BatchedCAVEnv:
         """False forces the plain thread-per-env step kernel (the TMA-staged kernel is the default where it applies)."""
         _native.check(self._lib.cavgym_set_step_path(self._handle, int(bool(use_tma))))
 
+    def set_host_path(self, zero_copy=True):
+        """False makes step_host stage pinned buffers through device copies instead of the zero-copy launch."""
+        _native.check(self._lib.cavgym_set_host_path(self._handle, int(bool(zero_copy))))
+
     def set_tangent_tolerance(self, tau):
         _native.check(self._lib.cavgym_set_tangent_tolerance(self._handle, float(tau)))
 

@@ -176,8 +176,9 @@ int cavgym_rollout(CavEngine* engine, int n_steps, int auto_reset, cudaStream_t 
 int cavgym_replay(CavEngine* engine, int n_steps, const void* actions, void* state_traj, void* reward_traj,
                   uint8_t* done_traj, int32_t* winner_traj, uint8_t* tangent_traj, cudaStream_t stream);
 
-/* cavgym_step with HOST buffers (same shapes): copies in, steps and copies out in
- * env-chunks pipelined over internal streams; returns when the outputs are on the host. */
+/* cavgym_step with HOST buffers (same shapes); returns when the outputs are on the host.  Pinned buffers
+ * (cudaHostAlloc / cudaHostRegister / torch pin_memory) are read and written by the step kernel itself, zero copy;
+ * pageable buffers are copied in and out in env-chunks pipelined over internal streams. */
 int cavgym_step_host(CavEngine* engine, const void* actions, void* state_out, void* reward_out,
                      uint8_t* done_out, int32_t* winner_out, uint8_t* tangent_flag_out);
 
@@ -219,6 +220,11 @@ int cavgym_set_action_logging(CavEngine* engine, int enabled);
  * aligned buffers) and the plain thread-per-env kernel for whatever is left; use_tma = 0 forces the plain kernel
  * everywhere (A/B measurements, parity of the two paths). */
 int cavgym_set_step_path(CavEngine* engine, int use_tma);
+
+/* cavgym_step_host with pinned (page-locked, mapped) buffers runs as one launch that reads and writes host memory
+ * directly over PCIe; zero_copy = 0 forces the staged path (chunked async copies through device buffers), which is also
+ * what pageable buffers get. */
+int cavgym_set_host_path(CavEngine* engine, int zero_copy);
 
 /* CAVEnv.current_timestep (environment.py:90,222) is never reset by the reference;
  * the engine keeps ONE counter of step calls for the whole batch. */

@@ -271,3 +271,36 @@ def test_road_kerb_and_corner_shares_match_oracle(dtype):
     # the placement really exercises every class of case: share 0, share 1 and > 1000 distinct fractional shares
     share = ((1584.0 - 600.0) / 1584.0 * 4.0 - want_reward[0, 1]) / 4.0
     assert (share < 1e-12).sum() > 100 and (share > 1 - 1e-12).sum() > 100 and len(np.unique(np.round(share, 9))) > 1000
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_step_host_zero_copy_equals_staged_copies_and_device_step(dtype):
+    """cavgym_step_host with pinned buffers (one launch reading / writing host memory over PCIe) against the staged
+    path (chunked async copies) and against cavgym_step on device tensors: identical bits in every output."""
+    import torch
+    meta, episodes = load_golden("pedestrians_rc_seed0")
+    n, m, k, t_max = 128 * 4 + 64, meta["n_bodies"], len(episodes), 60
+    init = soa(np.stack([episodes[e % k]["init_state"] for e in range(n)]))
+    actions = np.zeros((t_max, m, 2, n))
+    for j, ep in enumerate(episodes):
+        actions[:, :, :, j::k] = ep["actions"][:t_max, :, :, None]
+    envs = [make_env(meta, n, dtype) for _ in range(3)]
+    envs[1].set_host_path(zero_copy=False)
+    tdtype = envs[0].dtype
+    host = [{"actions": torch.empty((m, 2, n), dtype=tdtype).pin_memory(), "state": torch.empty((m, 4, n), dtype=tdtype).pin_memory(),
+             "reward": torch.empty((m, n), dtype=tdtype).pin_memory(), "done": torch.empty(n, dtype=torch.uint8).pin_memory(),
+             "winner": torch.empty(n, dtype=torch.int32).pin_memory(), "tangent": torch.empty(n, dtype=torch.uint8).pin_memory()}
+            for _ in range(2)]
+    acts = torch.tensor(actions, dtype=tdtype)
+    for env in envs:
+        env.reset(init_state=init)
+    for t in range(t_max):
+        for env, h in zip(envs[:2], host):
+            h["actions"].copy_(acts[t])
+            env.step_host(h["actions"], h["state"], h["reward"], h["done"], h["winner"], h["tangent"])
+        state, reward, done, winner, tangent = envs[2].step(acts[t].to(envs[2].device))
+        for key, dev in (("state", state), ("reward", reward), ("done", done), ("winner", winner), ("tangent", tangent)):
+            assert torch.equal(host[0][key], host[1][key]), (t, key)
+            assert torch.equal(host[0][key], dev.cpu()), (t, key)
+    assert envs[0].stats() == envs[1].stats() == envs[2].stats()
+    assert envs[0].launch_count() <= envs[1].launch_count()  # one launch per step; the staged path launches one per env-chunk
