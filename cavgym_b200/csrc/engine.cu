@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "kernels_dense.cuh"
 #include "kernels_small.cuh"
 
 namespace cav {
@@ -179,8 +180,38 @@ static void convert(const CavScenario& in, double tau, DevScenario<R>& out) {
   };
   for (int s = 0; s < in.n_spawns; ++s)
     for (int i = 0; i < in.spawns[s].n_orientations; ++i) remember(in.spawns[s].orientations[i]);
-  for (int b = 0; b < in.n_bodies && b < CAV_SMALL_M; ++b)
+  for (int b = 0; b < in.n_bodies; ++b)
     if (in.bodies[b].kind == CAV_BODY_DYNAMIC) remember(in.bodies[b].init_state[3]);
+}
+
+// Per-body rows of the warp-per-env path (kernels_dense.cuh): any number of bodies, kept in device memory.
+template <typename R>
+static void convert_dense(const CavScenario& in, double tau, DenseTables<R>& tb, std::vector<DenseBody<R>>& rows) {
+  std::memset(&tb, 0, sizeof(tb));
+  for (int t = 0; t < in.n_types; ++t) tb.types[t] = to_type<R>(in.types[t]);
+  Quad<R> roads[CAV_MAX_ROADS];
+  for (int i = 0; i < in.n_roads; ++i) roads[i] = to_quad<R>(in.roads[i]);
+  rows.assign((size_t)in.n_bodies, DenseBody<R>{});
+  for (int b = 0; b < in.n_bodies; ++b) {
+    const CavBody& src = in.bodies[b];
+    DenseBody<R>& dst = rows[(size_t)b];
+    dst.meta = (src.kind == CAV_BODY_DYNAMIC ? (src.type_id & DM_TYPE_MASK) : 0) | (src.kind == CAV_BODY_PELICAN ? DM_PELICAN : 0) |
+               ((src.flags & CAV_FLAG_PEDESTRIAN) ? DM_PEDESTRIAN : 0) | ((src.flags & CAV_FLAG_SPAWN) ? DM_SPAWN : 0) |
+               ((src.agent & DM_AGENT_MASK) << DM_AGENT_SHIFT);
+    dst.spawn_id = src.spawn_id;
+    dst.epsilon = src.agent_epsilon;
+    dst.threshold = (R)src.agent_threshold;
+    for (int c = 0; c < 4; ++c) dst.init[c] = (R)src.init_state[c];
+    dst.static_share = (R)0;
+    if (src.kind == CAV_BODY_PELICAN) {
+      const Quad<R> box = to_quad<R>(src.static_box);
+      for (int r = 0; r < in.n_roads; ++r) {
+        const R q = percentage_of(box, roads[r], (R)tau).value;
+        if (r == 0 || q > dst.static_share) dst.static_share = q;
+      }
+    }
+    if (src.agent == CAV_AGENT_EXTERNAL) tb.has_external = 1;
+  }
 }
 
 template <typename R>
@@ -274,6 +305,10 @@ struct CavEngine {
   bool has_external = false, has_device_agents = false;
   bool use_tma = true;  // cavgym_set_step_path: 0 = plain thread-per-env kernel only
   bool zero_copy_host = true;  // cavgym_set_host_path: 0 = always stage host buffers through device copies
+  bool dense = false;          // warp-per-env kernels (kernels_dense.cuh): always for m > CAV_SMALL_M, cavgym_set_dense_path otherwise
+  DenseTables<double> tb64;
+  DenseTables<float> tb32;
+  void* d_dense_bodies = nullptr;
   double tau = 1e-7;
   CavScenario host{};
   std::vector<CavBody> bodies;
@@ -339,11 +374,22 @@ static int setup_buffers(CavEngine* eng, EnvBuffers<R>& buf) {
   return CAV_OK;
 }
 
-static void rebuild_tables(CavEngine* eng) {
+static int rebuild_tables(CavEngine* eng) {
   convert<double>(eng->host, eng->tau, eng->sc64);
   convert<float>(eng->host, eng->tau, eng->sc32);
   eng->sc64.quads = (const Quad<double>*)eng->d_quads;  // only the table of the engine's own type is dereferenced
   eng->sc32.quads = (const Quad<float>*)eng->d_quads;
+  std::vector<DenseBody<double>> rows64;
+  std::vector<DenseBody<float>> rows32;
+  convert_dense<double>(eng->host, eng->tau, eng->tb64, rows64);
+  convert_dense<float>(eng->host, eng->tau, eng->tb32, rows32);
+  if (eng->d_dense_bodies) {   // allocated by cavgym_create once the device is selected
+    if (eng->dtype == CAV_F64) CUDA_TRY(cudaMemcpy(eng->d_dense_bodies, rows64.data(), rows64.size() * sizeof(DenseBody<double>), cudaMemcpyHostToDevice));
+    else CUDA_TRY(cudaMemcpy(eng->d_dense_bodies, rows32.data(), rows32.size() * sizeof(DenseBody<float>), cudaMemcpyHostToDevice));
+  }
+  eng->tb64.bodies = (const DenseBody<double>*)eng->d_dense_bodies;
+  eng->tb32.bodies = (const DenseBody<float>*)eng->d_dense_bodies;
+  return CAV_OK;
 }
 
 static int check_engine(CavEngine* eng) {
@@ -361,13 +407,31 @@ static int launch_check(CavEngine* eng, const char* what, int n_launches = 1) {
 }
 
 static int do_reset(CavEngine* eng, const uint8_t* mask, const void* init, int first_time, cudaStream_t stream) {
+  if (eng->dense) {
+    if (eng->dtype == CAV_F64) dense_launchers<double>()->reset(eng->sc64, eng->tb64, eng->buf64, mask, (const double*)init, first_time, stream);
+    else dense_launchers<float>()->reset(eng->sc32, eng->tb32, eng->buf32, mask, (const float*)init, first_time, stream);
+    return launch_check(eng, "dense reset kernel");
+  }
   if (eng->dtype == CAV_F64) small_launchers<double>(eng->m)->reset(eng->sc64, eng->buf64, mask, (const double*)init, first_time, stream);
   else small_launchers<float>(eng->m)->reset(eng->sc32, eng->buf32, mask, (const float*)init, first_time, stream);
   return launch_check(eng, "reset kernel");
 }
 
+template <typename R> static const DenseTables<R>& dense_tables(const CavEngine* eng);
+template <> const DenseTables<double>& dense_tables<double>(const CavEngine* eng) { return eng->tb64; }
+template <> const DenseTables<float>& dense_tables<float>(const CavEngine* eng) { return eng->tb32; }
+
+template <typename R>
+static int dense_run(CavEngine* eng, const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepIO<R>& io, int n_steps, int auto_reset,
+                     int traj, cudaStream_t stream) {
+  if (!dense_launchers<R>()->run(sc, dense_tables<R>(eng), buf, io, eng->t_global, n_steps, auto_reset, traj, eng->has_device_agents, stream))
+    return fail(CAV_ECUDA, "dense kernel set-up failed (shared memory opt-in)");
+  return launch_check(eng, "dense kernel");
+}
+
 template <typename R>
 static int step_range_typed(CavEngine* eng, const DevScenario<R>& sc, EnvBuffers<R> buf, const StepIO<R>& io, cudaStream_t stream) {
+  if (eng->dense) return dense_run(eng, sc, buf, io, 1, 0, 0, stream);
   const SmallLaunchers<R>* k = small_launchers<R>(eng->m);
   int launches = 0;
   if (!eng->has_device_agents && eng->use_tma) {   // replayed actions: persistent TMA-staged kernel over the whole tiles
@@ -384,6 +448,7 @@ static int step_range_typed(CavEngine* eng, const DevScenario<R>& sc, EnvBuffers
 template <typename R>
 static int replay_typed(CavEngine* eng, const DevScenario<R>& sc, EnvBuffers<R> buf, const StepIO<R>& io, int n_steps,
                         cudaStream_t stream, int* launches) {
+  if (eng->dense) return dense_run(eng, sc, buf, io, n_steps, 0, 1, stream);
   const SmallLaunchers<R>* k = small_launchers<R>(eng->m);
   if (eng->use_tma) {
     int64_t taken = 0;
@@ -405,9 +470,8 @@ int cavgym_create(const CavScenario* tables, int64_t n_envs, int dtype, int devi
   if (n_envs <= 0) return fail(CAV_EINVAL, "n_envs must be positive");
   if (dtype != CAV_F64 && dtype != CAV_F32) return fail(CAV_EINVAL, "dtype must be CAV_F64 or CAV_F32");
   if (tables->n_bodies < 1 || !tables->bodies) return fail(CAV_EINVAL, "scenario has no bodies");
-  if (tables->n_bodies > CAV_SMALL_M)
-    return fail(CAV_EINVAL, "more than CAV_SMALL_M bodies: the dense block-per-environment path is not built in this library");
-  if ((dtype == CAV_F64 ? (const void*)small_launchers<double>(tables->n_bodies)->step : (const void*)small_launchers<float>(tables->n_bodies)->step) == nullptr)
+  if (tables->n_bodies > CAV_MAX_BODIES) return fail(CAV_EINVAL, "more than CAV_MAX_BODIES bodies");
+  if (tables->n_bodies <= CAV_SMALL_M && (dtype == CAV_F64 ? (const void*)small_launchers<double>(tables->n_bodies)->step : (const void*)small_launchers<float>(tables->n_bodies)->step) == nullptr)
     return fail(CAV_EINVAL, "this development build of the library was compiled without this body count (CAVGYM_ONLY_M)");
   if (tables->n_roads < 1 || tables->n_roads > CAV_MAX_ROADS || tables->n_statics < 0 || tables->n_statics > CAV_MAX_STATICS ||
       tables->n_types < 0 || tables->n_types > CAV_MAX_TYPES)
@@ -437,9 +501,15 @@ int cavgym_create(const CavScenario* tables, int64_t n_envs, int dtype, int devi
   for (const CavBody& body : eng->bodies) {
     if (body.agent == CAV_AGENT_EXTERNAL) eng->has_external = true; else eng->has_device_agents = true;
   }
-  rebuild_tables(eng);
+  eng->dense = eng->m > CAV_SMALL_M;
   int rc = dtype == CAV_F64 ? setup_buffers(eng, eng->buf64) : setup_buffers(eng, eng->buf32);
-  if (rc == CAV_OK) { rebuild_tables(eng); rc = dev_alloc(eng, &eng->d_scratch, 2); }
+  if (rc == CAV_OK) {
+    char* rows = nullptr;
+    rc = dev_alloc(eng, &rows, (size_t)eng->m * (dtype == CAV_F64 ? sizeof(DenseBody<double>) : sizeof(DenseBody<float>)));
+    eng->d_dense_bodies = rows;
+  }
+  if (rc == CAV_OK) rc = rebuild_tables(eng);
+  if (rc == CAV_OK) rc = dev_alloc(eng, &eng->d_scratch, 2);
   if (rc == CAV_OK) rc = do_reset(eng, nullptr, nullptr, 1, nullptr);  // constructor-time spawn (bodies.py:296)
   if (rc == CAV_OK) {
     cudaError_t err = cudaDeviceSynchronize();
@@ -506,6 +576,15 @@ int cavgym_rollout(CavEngine* eng, int n_steps, int auto_reset, cudaStream_t str
   if (n_steps < 0) return fail(CAV_EINVAL, "n_steps must be >= 0");
   if (eng->has_external) return fail(CAV_ESTATE, "cavgym_rollout needs an on-device agent for every body");
   if (n_steps == 0) return CAV_OK;
+  if (eng->dense) {
+    const StepIO<double> io64{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const StepIO<float> io32{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    rc = eng->dtype == CAV_F64 ? dense_run(eng, eng->sc64, eng->buf64, io64, n_steps, auto_reset, 0, stream)
+                               : dense_run(eng, eng->sc32, eng->buf32, io32, n_steps, auto_reset, 0, stream);
+    if (rc) return rc;
+    eng->t_global += n_steps;
+    return CAV_OK;
+  }
   if (eng->dtype == CAV_F64) small_launchers<double>(eng->m)->rollout(eng->sc64, eng->buf64, eng->t_global, n_steps, auto_reset, stream);
   else small_launchers<float>(eng->m)->rollout(eng->sc32, eng->buf32, eng->t_global, n_steps, auto_reset, stream);
   rc = launch_check(eng, "rollout kernel");
@@ -531,7 +610,7 @@ int cavgym_replay(CavEngine* eng, int n_steps, const void* actions, void* state_
     rc = replay_typed(eng, eng->sc32, eng->buf32, io, n_steps, stream, &launches);
   }
   if (rc) return rc;
-  rc = launch_check(eng, "replay kernel", launches);
+  if (!eng->dense) rc = launch_check(eng, "replay kernel", launches);
   if (rc) return rc;
   eng->t_global += n_steps;
   return CAV_OK;
@@ -682,6 +761,13 @@ int cavgym_set_step_path(CavEngine* eng, int use_tma) {
   return CAV_OK;
 }
 
+int cavgym_set_dense_path(CavEngine* eng, int force) {
+  if (!eng) return fail(CAV_EINVAL, "engine is NULL");
+  if (eng->m > CAV_SMALL_M && !force) return fail(CAV_EINVAL, "more than CAV_SMALL_M bodies: only the warp-per-environment kernels apply");
+  eng->dense = force != 0 || eng->m > CAV_SMALL_M;
+  return CAV_OK;
+}
+
 int cavgym_set_host_path(CavEngine* eng, int zero_copy) {
   if (!eng) return fail(CAV_EINVAL, "engine is NULL");
   eng->zero_copy_host = zero_copy != 0;
@@ -698,8 +784,7 @@ int cavgym_set_tangent_tolerance(CavEngine* eng, double tau) {
   if (!eng) return fail(CAV_EINVAL, "engine is NULL");
   if (!(tau >= 0)) return fail(CAV_EINVAL, "tau must be >= 0");
   eng->tau = tau;
-  rebuild_tables(eng);
-  return CAV_OK;
+  return rebuild_tables(eng);
 }
 
 int cavgym_bodies_step(const CavBodyType* type, void* state, const void* actions, int64_t n, double time_resolution, int dtype,

@@ -1,0 +1,644 @@
+// kernels_dense.cuh — warp-per-environment kernels for scenarios with many bodies (CAV_SMALL_M < M <= CAV_MAX_BODIES),
+// e.g. the dense-traffic stress configuration: 64 cars + 256 spawned pedestrians per env, terminate_collisions = "all",
+// 51,040 box pairs per env-step (environment.py:156-177 is O(M^2)).
+//
+//   dense_kernel        n_steps of CAVEnv.step (environment.py:119-223) for one env per WARP: replayed actions or
+//                       on-device agents, optional trajectory slabs, optional auto-reset (cavgym_step / _replay / _rollout)
+//   dense_reset_kernel  CAVEnv.reset (environment.py:225-229) per warp
+//
+// Work split inside a warp: body b belongs to lane b % 32.  Per-body work (agents, DynamicBody.step, road share,
+// reward, liveness, ego / stopping-zone tests) is a lane-strided loop; the per-environment reductions — any collision,
+// any near-tangent decision, lowest-index pedestrian in the reaction zone (environment.py:198-200), action validity —
+// are warp votes (__any_sync / __all_sync / __reduce_min_sync).  There is no block-wide barrier after the prologue.
+//
+// Shared memory (per env = per warp): the stepped bodies in centre-extent form, x, y, cos, sin, theta in the engine's
+// type R (what the exact separating-axis test and the road share read) and a float4 {x, y, ex, ey} per body for the
+// BROAD PHASE: the axis-aligned extent test of every pair runs in fp32 on outward-rounded extents (a strict superset of
+// the pairs the R-precision test passes — see `broad_entry`), one broadcast LDS.128 + 8 fp32 instructions per 32 pairs.
+// Survivors (a few per env-step) take exactly the test sequence of the thread-per-env path (transition.cuh): R-precision
+// AABB gap, then the four-axis margin, so results — including near-tangent flags — are bitwise those of the small-M
+// kernels on the same scenario (tests/test_gpu_dense.py).  Per-body metadata (type, class flags, agent kind) is staged
+// once per CTA and shared by its envs.
+//
+// Bound: ALU (fp32 pair tests), not HBM: an env-step moves 88 B per body but tests M(M-1)/2 pairs.  DESIGN.md §4.4.
+#pragma once
+#include "transition.cuh"
+
+namespace cav {
+
+#ifndef CAV_DENSE_WARPS
+#define CAV_DENSE_WARPS 4
+#endif
+constexpr int kDenseWarps = CAV_DENSE_WARPS;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+enum { DM_TYPE_MASK = 7, DM_PELICAN = 8, DM_PEDESTRIAN = 16, DM_SPAWN = 32, DM_AGENT_SHIFT = 8, DM_AGENT_MASK = 7, DM_ABSENT = 1 << 15 };
+
+template <typename R>
+struct DenseBody {       // CavBody (include/cavgym.h) in the engine's type, 64 B
+  int32_t meta;          // DM_* bits
+  int32_t spawn_id;
+  double epsilon;
+  R threshold;
+  R init[4];
+  R static_share;        // PelicanCrossing: percentage_intersects(static box, road), a scenario constant
+};
+
+template <typename R>
+struct DenseTables {
+  DevType<R> types[CAV_MAX_TYPES];
+  const DenseBody<R>* bodies;   // device, [M]
+  int32_t has_external;         // some body takes its action from the `actions` buffer
+  int32_t pad;
+};
+
+__device__ __forceinline__ int dm_agent(int32_t mt) { return (mt >> DM_AGENT_SHIFT) & DM_AGENT_MASK; }
+
+template <typename R>
+struct DenseSmem {
+  float4* bp;              // [Mp] broad-phase entries
+  R *x, *y, *c, *s, *th;   // [Mp] stepped bodies
+  const int32_t* meta;     // [Mp], shared by the CTA
+};
+
+template <typename R>
+__host__ __device__ inline size_t dense_smem_bytes(int m, int warps) {
+  const size_t mp = (size_t)((m + 31) & ~31);
+  return (size_t)warps * mp * (sizeof(float4) + 5 * sizeof(R)) + mp * sizeof(int32_t);
+}
+
+// Broad-phase entry of a box: centre and AABB half extents in fp32, the extents rounded OUTWARD by more than every
+// rounding error of the fp32 test  |xf_i - xf_j| - (Ex_i + Ex_j) > 0  =>  |x_i - x_j| - (ex_i + ex_j) > tau  in R:
+// converting a coordinate costs <= 2^-24 |x|, the subtraction and the sum another 2^-24 relative each; the slack below is
+// 4e-7 (|x| + ex) + 2 tau, i.e. > 6 x 2^-24 relative plus the tangent tolerance.  An absent / static body gets
+// -infinity extents: it is "separated" from everything.
+template <typename R>
+__device__ __forceinline__ float4 broad_entry(R x, R y, R ex, R ey, R tau) {
+  const float xf = (float)x, yf = (float)y;
+  const float exf = __double2float_ru((double)ex), eyf = __double2float_ru((double)ey);
+  const float tf = 2.0f * __double2float_ru((double)tau);
+  return make_float4(xf, yf, exf + ((fabsf(xf) + exf) * 4e-7f + tf), eyf + ((fabsf(yf) + eyf) * 4e-7f + tf));
+}
+__device__ __forceinline__ float4 broad_absent() { return make_float4(0.f, 0.f, -INFINITY, -INFINITY); }
+
+template <typename R>
+__device__ __forceinline__ Box<R> dense_box(const DenseSmem<R>& sm, const DevType<R>& k, int b) {
+  return {sm.x[b], sm.y[b], sm.c[b], sm.s[b], k.hl, k.hw};
+}
+template <typename R>
+__device__ __forceinline__ Pose<R> dense_pose(const DenseSmem<R>& sm, const DevType<R>& k, int b) {
+  return {sm.x[b], sm.y[b], sm.th[b], sm.c[b], sm.s[b], k.length, k.width};
+}
+
+// road_share of transition.cuh on an explicit pose (same cases, same order, same arithmetic).
+template <typename R>
+__device__ __forceinline__ R dense_road_share(const DevScenario<R>& sc, const DenseSmem<R>& sm, const DevType<R>& k, int b, int r,
+                                              R ex, R ey, R tau, bool& near) {
+  const Aabb<R> rd = sc.road_bb[r];
+  const R px = sm.x[b], py = sm.y[b];
+  const R m0 = (px - ex) - rd.x0, m1 = rd.x1 - (px + ex), m2 = (py - ey) - rd.y0, m3 = rd.y1 - (py + ey);
+  const R mx = rmin(m0, m1), my = rmin(m2, m3);
+  if (mx < -((ex + ex) + tau) || my < -((ey + ey) + tau)) return R(0);
+  if (sc.road_axis[r]) {
+    const bool x_edge = mx < my;
+    const R lo = x_edge ? mx : my, hi = x_edge ? my : mx;
+    if (lo >= tau) return R(1);
+    const R opposite = x_edge ? rmax(m0, m1) : rmax(m2, m3);
+    if (lo <= -tau && hi >= tau && opposite >= tau) {
+      const R ac = rabs(sm.c[b]), as = rabs(sm.s[b]);
+      const R p = kerb_share(lo + (x_edge ? ex : ey), (x_edge ? ac : as) * k.hl, (x_edge ? as : ac) * k.hw);
+      if (rabs(p - R(0.5)) < tau) near = true;
+      return p;
+    }
+    if (mx < tau && my < tau && rmax(m0, m1) >= tau && rmax(m2, m3) >= tau) {
+      const bool low_x = m0 < m1, low_y = m2 < m3;
+      const R p = corner_share(dense_pose(sm, k, b), low_x ? R(-1) : R(1), low_x ? -rd.x0 : rd.x1, low_y ? R(-1) : R(1),
+                               low_y ? -rd.y0 : rd.y1);
+      if (rabs(p - R(0.5)) < tau) near = true;
+      return p;
+    }
+  }
+  const Share<R> share = road_share_general(dense_pose(sm, k, b), &sc.quads[r], tau);
+  near |= (share.tangent != 0) || (rabs(share.value - R(0.5)) < tau);
+  return share.value;
+}
+
+// Warp-uniform per-env scalars.
+struct DenseEnv {
+  int32_t t_ep, episode, winner;
+  uint8_t done;
+};
+
+// CAVEnv.reset for env e by its warp (reset_env of transition.cuh, lane-strided over bodies).
+template <typename R>
+__device__ __forceinline__ void dense_reset_env(const DevScenario<R>& sc, const DenseTables<R>& tb, const EnvBuffers<R>& buf,
+                                                const R* init, int64_t e, int lane, DenseEnv& env) {
+  const int M = sc.n_bodies;
+  const int64_t n = buf.n;
+  env.episode += 1;
+  for (int b = lane; b < M; b += 32) {
+    const DenseBody<R>& body = tb.bodies[b];
+    const int32_t mt = body.meta;
+    R st[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) st[c] = body.init[c];
+    if (init) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) st[c] = init[((int64_t)b * 4 + c) * n + e];
+    } else if ((mt & DM_SPAWN) && body.spawn_id >= 0) {
+      double u[5];
+      if (buf.spawn_override) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) u[c] = buf.spawn_override[((int64_t)b * 5 + c) * n + e];
+      } else {
+        double w[2];
+        const uint64_t g = (uint64_t)(buf.shard + e);
+        draw_block(buf.seed, g, b, KIND_SPAWN0, (uint32_t)env.episode, 0u, w); u[0] = w[0]; u[1] = w[1];
+        draw_block(buf.seed, g, b, KIND_SPAWN1, (uint32_t)env.episode, 0u, w); u[2] = w[0]; u[3] = w[1];
+        draw_block(buf.seed, g, b, KIND_SPAWN2, (uint32_t)env.episode, 0u, w); u[4] = w[0];
+      }
+      spawn_body(buf.spawns[body.spawn_id], u, st);
+    }
+    R c = R(1), s = R(0);
+    if (!(mt & DM_PELICAN)) heading_cs(sc, st[3], c, s);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) buf.state[((int64_t)b * 4 + w) * n + e] = st[w];
+    buf.action[((int64_t)b * 2 + 0) * n + e] = R(0);
+    buf.action[((int64_t)b * 2 + 1) * n + e] = R(0);
+    buf.cs[((int64_t)b * 2 + 0) * n + e] = c;
+    buf.cs[((int64_t)b * 2 + 1) * n + e] = s;
+#pragma unroll
+    for (int w = 0; w < CAV_AGENT_WORDS; ++w) buf.agent[((int64_t)b * CAV_AGENT_WORDS + w) * n + e] = nan_<R>();
+    buf.liveness[(int64_t)b * n + e] = 0;
+  }
+  env.t_ep = 0;
+  env.done = 0;
+  env.winner = -1;
+  if (lane == 0) {
+    buf.t_ep[e] = 0; buf.done[e] = 0; buf.winner[e] = -1; buf.episode[e] = env.episode;
+  }
+  __syncwarp();
+}
+
+// Exact stage of one candidate pair (i < j): the test sequence of transition.cuh's all-pairs loop.
+template <typename R>
+__device__ __forceinline__ bool dense_pair(const DenseSmem<R>& sm, const DenseTables<R>& tb, int i, int j, R tau, bool& tangent) {
+  const DevType<R>& ki = tb.types[sm.meta[i] & DM_TYPE_MASK];
+  const DevType<R>& kj = tb.types[sm.meta[j] & DM_TYPE_MASK];
+  R exi, eyi, exj, eyj;
+  box_extents(sm.c[i], sm.s[i], ki.hl, ki.hw, exi, eyi);
+  box_extents(sm.c[j], sm.s[j], kj.hl, kj.hw, exj, eyj);
+  const bool apart = rabs(sm.x[i] - sm.x[j]) - (exi + exj) > tau || rabs(sm.y[i] - sm.y[j]) - (eyi + eyj) > tau;
+  if (apart) return false;
+  return margin_hit(box_margin(dense_box(sm, ki, i), dense_box(sm, kj, j)), tau, tangent);
+}
+
+// One joint transition of env e by its warp.  `actions` = this step's [M][2][N] rows (nullable when every body has an
+// on-device agent).  Returns with env updated; outputs written through `io`.
+template <typename R, bool AGENTS>
+__device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const DenseTables<R>& tb, const EnvBuffers<R>& buf,
+                                                 const StepIO<R>& io, const R* actions, int64_t e, int64_t t_global, int lane,
+                                                 const DenseSmem<R>& sm, DenseEnv& env) {
+  const int M = sc.n_bodies, Mp = (M + 31) & ~31;
+  const int64_t n = buf.n;
+  const R tau = sc.tau, dt = sc.dt;
+  bool tangent = false;
+
+  // ---- action_space.contains for the replayed actions (environment.py:120): before any mutation
+  if (!AGENTS || tb.has_external) {
+    bool valid = true;
+    for (int b = lane; b < M; b += 32) {
+      const int32_t mt = sm.meta[b];
+      if (AGENTS && dm_agent(mt) != CAV_AGENT_EXTERNAL) continue;
+      const R a0 = actions[((int64_t)b * 2 + 0) * n + e], a1 = actions[((int64_t)b * 2 + 1) * n + e];
+      if (mt & DM_PELICAN) {
+        valid = valid && (a0 == R(0) || a0 == R(1) || a0 == R(2) || a0 == R(3));
+      } else {
+        const DevType<R>& k = tb.types[mt & DM_TYPE_MASK];
+        valid = valid && (a0 >= k.amin && a0 <= k.amax && a1 >= k.smin && a1 <= k.smax);
+      }
+    }
+    if (!__all_sync(kFull, valid)) {
+      for (int b = lane; b < M; b += 32) {
+        if (io.reward_out) io.reward_out[(int64_t)b * n + e] = R(0);
+        if (io.state_out && io.state_out != buf.state) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) io.state_out[((int64_t)b * 4 + c) * n + e] = buf.state[((int64_t)b * 4 + c) * n + e];
+        }
+      }
+      if (lane == 0) {
+        buf.err[e] = 1;
+        if (io.done_out) io.done_out[e] = 0;
+        if (io.winner_out) io.winner_out[e] = -1;
+        if (io.tangent_out) io.tangent_out[e] = 0;
+      }
+      return;
+    }
+  }
+
+  // ---- agents, body.step (environment.py:122-123), process_feedback (simulation.py:86-87: a function of the body's own
+  //      new state only), staging of the stepped bodies
+  const R ego_pre_x = buf.state[e], ego_pre_y = buf.state[n + e];   // ProximityAgent looks at the ego BEFORE it moves
+  __syncwarp();
+  R ego_steer = R(0), ego_v = R(0);
+  bool agent_invalid = false;
+  for (int b = lane; b < Mp; b += 32) {
+    if (b >= M) { sm.bp[b] = broad_absent(); continue; }
+    const int32_t mt = sm.meta[b];
+    const int agent = dm_agent(mt);
+    const bool pelican = (mt & DM_PELICAN) != 0;
+    const DevType<R>& k = tb.types[mt & DM_TYPE_MASK];
+    R st[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) st[c] = buf.state[((int64_t)b * 4 + c) * n + e];
+    R a0 = R(0), a1 = R(0);
+    R ag[CAV_AGENT_WORDS];
+    bool ag_dirty = false;
+    const bool crossing = AGENTS && (agent == CAV_AGENT_RANDOM_CONSTRAINED || agent == CAV_AGENT_PROXIMITY);
+    if (!AGENTS || agent == CAV_AGENT_EXTERNAL) {
+      a0 = actions[((int64_t)b * 2 + 0) * n + e]; a1 = actions[((int64_t)b * 2 + 1) * n + e];
+    } else {
+      const DenseBody<R>& body = tb.bodies[b];
+      if (agent == CAV_AGENT_RANDOM) {  // holds its last action (template.py:52-56)
+        a0 = buf.action[((int64_t)b * 2 + 0) * n + e]; a1 = buf.action[((int64_t)b * 2 + 1) * n + e];
+      }
+      if (crossing) {
+#pragma unroll
+        for (int w = 0; w < CAV_AGENT_WORDS; ++w) ag[w] = buf.agent[((int64_t)b * CAV_AGENT_WORDS + w) * n + e];
+      }
+      double u[CAV_DRAWS] = {0.0, 0.0, 0.0};
+      if (agent == CAV_AGENT_RANDOM || agent == CAV_AGENT_RANDOM_CONSTRAINED) {
+        if (buf.uni_override) {
+#pragma unroll
+          for (int c = 0; c < CAV_DRAWS; ++c) u[c] = buf.uni_override[((int64_t)b * CAV_DRAWS + c) * n + e];
+        } else {
+          draw_block(buf.seed, (uint64_t)(buf.shard + e), b, KIND_AGENT0, (uint32_t)env.episode, (uint32_t)env.t_ep, u);
+        }
+      }
+      if (agent == CAV_AGENT_NOOP) {
+        a0 = R(0); a1 = R(0);
+      } else if (agent == CAV_AGENT_RANDOM) {
+        if (u[0] < body.epsilon) {
+          if (pelican) {
+            a0 = R(floor(u[1] * 4.0)); if (a0 > R(3)) a0 = R(3);
+            a1 = R(0);
+          } else {
+            if (!buf.uni_override) {
+              double w[2];
+              draw_block(buf.seed, (uint64_t)(buf.shard + e), b, KIND_AGENT1, (uint32_t)env.episode, (uint32_t)env.t_ep, w);
+              u[2] = w[0];
+            }
+            a0 = R(double(k.amin) + (double(k.amax) - double(k.amin)) * u[1]);
+            a1 = R(double(k.smin) + (double(k.smax) - double(k.smin)) * u[2]);
+          }
+        }
+      } else if (agent == CAV_AGENT_RANDOM_CONSTRAINED) {
+        a0 = R(0);
+        a1 = choose_crossing_action(sc, k, st, ag, u[0] < body.epsilon, ag_dirty);
+      } else if (agent == CAV_AGENT_PROXIMITY) {
+        const bool trigger = point_distance(st[0], st[1], ego_pre_x, ego_pre_y) < body.threshold;
+        a0 = R(0);
+        a1 = choose_crossing_action(sc, k, st, ag, trigger, ag_dirty);
+      }
+      if (pelican) agent_invalid |= !(a0 == R(0) || a0 == R(1) || a0 == R(2) || a0 == R(3));
+      else agent_invalid |= !(a0 >= k.amin && a0 <= k.amax && a1 >= k.smin && a1 <= k.smax);
+      if (buf.log_actions || agent == CAV_AGENT_RANDOM) {
+        buf.action[((int64_t)b * 2 + 0) * n + e] = a0; buf.action[((int64_t)b * 2 + 1) * n + e] = a1;
+      }
+    }
+    if (pelican) {  // PelicanCrossing.step (bodies.py:450-461)
+      if (a0 == R(1)) st[0] = R(0);
+      else if (a0 == R(2)) st[0] = R(1);
+      else if (a0 == R(3)) st[0] = R(2);
+      buf.state[((int64_t)b * 4) * n + e] = st[0];
+      sm.x[b] = R(0); sm.y[b] = R(0); sm.c[b] = R(1); sm.s[b] = R(0); sm.th[b] = R(0);
+      sm.bp[b] = broad_absent();
+    } else {
+      R c = buf.cs[((int64_t)b * 2 + 0) * n + e], s = buf.cs[((int64_t)b * 2 + 1) * n + e], snapped;
+#ifdef CAV_DENSE_DEBUG
+      if (e == 1 && b == 1 && t_global < 3) printf("t=%lld a0=%g a1=%g actions=%p n=%lld st=%g %g %g %g c=%g s=%g smax=%g\n", (long long)t_global, (double)a0, (double)a1, (const void*)actions, (long long)n, (double)st[0], (double)st[1], (double)st[2], (double)st[3], (double)c, (double)s, (double)k.smax);
+#endif
+      if (body_step(k, st, a0, a1, dt, c, s, snapped)) {
+        buf.cs[((int64_t)b * 2 + 0) * n + e] = c; buf.cs[((int64_t)b * 2 + 1) * n + e] = s;
+      }
+      if (b == 0) { ego_steer = snapped; ego_v = st[2]; }
+      if (crossing) crossing_feedback(sc, st, ag, ag_dirty);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) buf.state[((int64_t)b * 4 + w) * n + e] = st[w];
+      sm.x[b] = st[0]; sm.y[b] = st[1]; sm.c[b] = c; sm.s[b] = s; sm.th[b] = st[3];
+      R ex, ey;
+      box_extents(c, s, k.hl, k.hw, ex, ey);
+      sm.bp[b] = broad_entry(st[0], st[1], ex, ey, tau);
+    }
+    if (crossing && ag_dirty) {
+#pragma unroll
+      for (int w = 0; w < CAV_AGENT_WORDS; ++w) buf.agent[((int64_t)b * CAV_AGENT_WORDS + w) * n + e] = ag[w];
+    }
+    if (io.state_out && io.state_out != buf.state) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w) io.state_out[((int64_t)b * 4 + w) * n + e] = st[w];
+    }
+  }
+  __syncwarp();
+  ego_steer = __shfl_sync(kFull, ego_steer, 0);
+  ego_v = __shfl_sync(kFull, ego_v, 0);
+  if (AGENTS && __any_sync(kFull, agent_invalid) && lane == 0) buf.err[e] = 1;   // cannot happen with the stock agents
+
+  // ---- termination cascade (environment.py:148-206)
+  const DevType<R>& k0 = tb.types[sm.meta[0] & DM_TYPE_MASK];
+  const R x0 = sm.x[0], y0 = sm.y[0], c0 = sm.c[0], s0 = sm.s[0];
+  R ex0, ey0;
+  box_extents(c0, s0, k0.hl, k0.hw, ex0, ey0);
+  const R W = sc.W;
+  bool terminate = false, win_ego = false;
+  int win_tester = -1;
+  {
+    const R margin = (x0 - ex0) - W;  // all four ego corners beyond the viewer width
+    if (margin > -tau) {
+      if (margin < tau) tangent = true;
+      if (margin > R(0)) { terminate = true; win_ego = true; }
+    }
+  }
+  if (!terminate && sc.collisions == CAV_COLLISIONS_ALL) {
+    bool hit = false;
+    // dynamic vs dynamic: lane owns body j = jt + lane and meets every i < j; the entry of body i is a broadcast read
+    for (int jt = 0; jt < Mp; jt += 32) {
+      const int j = jt + lane;
+      const float4 pj = sm.bp[j];
+      const int iend = jt + 32 < M ? jt + 32 : M;
+      for (int i0 = 0; i0 < iend; i0 += 8) {
+        unsigned cand = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 pi = sm.bp[i0 + u];
+          const float gx = fabsf(pi.x - pj.x) - (pi.z + pj.z), gy = fabsf(pi.y - pj.y) - (pi.w + pj.w);
+          if (!(fmaxf(gx, gy) > 0.f) && i0 + u < j) cand |= 1u << u;
+        }
+        if (__any_sync(kFull, cand != 0)) {
+          while (cand) {
+            const int u = __ffs(cand) - 1;
+            cand &= cand - 1;
+            hit |= dense_pair(sm, tb, i0 + u, j, tau, tangent);
+          }
+        }
+      }
+    }
+    // dynamic vs static collidables (traffic lights, obstacle: environment.py:94-101)
+    for (int i = lane; i < M; i += 32) {
+      const int32_t mt = sm.meta[i];
+      if (mt & DM_PELICAN) continue;
+      const DevType<R>& ki = tb.types[mt & DM_TYPE_MASK];
+      R exi, eyi;
+      box_extents(sm.c[i], sm.s[i], ki.hl, ki.hw, exi, eyi);
+      const R px = sm.x[i], py = sm.y[i];
+      for (int s = 0; s < sc.n_statics; ++s) {
+        const Aabb<R> sb = sc.static_bb[s];
+        const bool apart = (px - exi) - sb.x1 > tau || sb.x0 - (px + exi) > tau || (py - eyi) - sb.y1 > tau || sb.y0 - (py + eyi) > tau;
+        if (!apart) {
+          if (sc.static_rect[s]) hit |= margin_hit(box_margin(dense_box(sm, ki, i), sc.static_box[s]), tau, tangent);
+          else hit |= geo_hit(sat_pose_quad(dense_pose(sm, ki, i), &sc.quads[CAV_MAX_ROADS + s], tau), tangent);
+        }
+      }
+    }
+    terminate = __any_sync(kFull, hit);
+  }
+  if (!terminate && sc.offroad) {   // ego only: evaluated by every lane alike
+    bool on_road = false;
+    for (int r = 0; r < sc.n_roads; ++r) {
+      const Aabb<R> rd = sc.road_bb[r];
+      const bool apart = (x0 - ex0) - rd.x1 > tau || rd.x0 - (x0 + ex0) > tau || (y0 - ey0) - rd.y1 > tau || rd.y0 - (y0 + ey0) > tau;
+      if (!apart) {
+        if (sc.road_rect[r]) on_road |= margin_hit(box_margin(dense_box(sm, k0, 0), sc.road_box[r]), tau, tangent);
+        else on_road |= geo_hit(sat_pose_quad(dense_pose(sm, k0, 0), &sc.quads[r], tau), tangent);
+      }
+    }
+    terminate = !on_road;
+  }
+  if (!terminate && (sc.collisions == CAV_COLLISIONS_EGO || sc.zones)) {
+    EgoFrame<R> f;
+    f.x = x0; f.y = y0; f.c = c0; f.s = s0; f.hl = k0.hl; f.hw = k0.hw;
+    f.bd = (ego_v * ego_v) * k0.inv_2brake;
+    f.td = f.bd + ego_v * R(0.675);
+    f.have = !(f.td == R(0)) && (ego_steer == R(0));
+    const bool ego_mode = sc.collisions == CAV_COLLISIONS_EGO;
+    // The reference walks the pedestrians in index order: ego box / braking zone for each (environment.py:183-193), and
+    // the reaction zone only while nothing has hit and nobody has won yet (:195-206).  In parallel: every lane evaluates
+    // its pedestrians, then the first hit and the first winner are warp minima, and a reaction-zone decision counts
+    // towards the near-tangent flag only if the sequential walk would have made it.
+    unsigned first_hit = 0xFFFFFFFFu, first_win = 0xFFFFFFFFu;
+    uint32_t near_bits = 0;   // bit k: the reaction-zone margin of body lane + 32 k is within tau
+    for (int b = lane; b < M; b += 32) {
+      const int32_t mt = sm.meta[b];
+      if (b == 0 || !(mt & DM_PEDESTRIAN) || (mt & DM_PELICAN)) continue;
+      const DevType<R>& k = tb.types[mt & DM_TYPE_MASK];
+      const EgoMargins<R> m = ego_margins(f, sm.x[b], sm.y[b], sm.c[b], sm.s[b], k.hl, k.hw, tau);
+      if (m.all_clear) continue;
+      if (ego_mode) {
+        bool h = margin_hit(m.ego, tau, tangent);
+        if (!h && f.have) h = margin_hit(m.braking, tau, tangent);
+        if (h && (unsigned)b < first_hit) first_hit = (unsigned)b;
+      }
+      if (sc.zones && f.have) {
+        if (rabs(m.reaction) < tau) near_bits |= 1u << (b >> 5);
+        if (!(m.reaction > R(0)) && (unsigned)b < first_win) first_win = (unsigned)b;
+      }
+    }
+    first_hit = __reduce_min_sync(kFull, first_hit);
+    // The walk tests the reaction zone for body b iff nothing has hit among bodies <= b (b < first_hit) and nobody before
+    // b has won (b <= first_win).  A lane's lowest winner is its only candidate: if that one is not below first_hit,
+    // none of its later ones is.
+    first_win = __reduce_min_sync(kFull, first_win < first_hit ? first_win : 0xFFFFFFFFu);
+    for (int b = lane, kbit = 0; b < M; b += 32, ++kbit)
+      if ((near_bits >> kbit & 1u) && (unsigned)b < first_hit && (unsigned)b <= first_win) tangent = true;
+    if (first_hit != 0xFFFFFFFFu) { terminate = true; win_tester = -1; }
+    else { win_tester = first_win == 0xFFFFFFFFu ? -1 : (int)first_win; terminate = win_tester >= 0; }
+  }
+
+  // ---- rewards, liveness (environment.py:131-146), terminal rewards and winner (:208-220)
+  const R cstep = sc.cost_step;
+  const R ego_rel = rmax(R(0), rmin(R(1), (W - x0) * sc.inv_W));
+  const bool terminal = terminate || t_global == sc.max_timesteps - 1;
+  for (int b = lane; b < M; b += 32) {
+    R rb = R(0);
+    if (b == 0) {
+      const R voff = rabs(ego_v - sc.v_maint) * sc.inv_v_off;
+      rb -= voff * cstep;
+      rb += (R(1) - ego_rel) * cstep;
+      if (terminal) rb += win_ego ? sc.reward_win : (win_tester >= 0 ? -sc.reward_win : sc.reward_draw);
+    } else {
+      const int32_t mt = sm.meta[b];
+      R p = R(0);
+      if (mt & DM_PELICAN) {
+        p = tb.bodies[b].static_share;
+      } else {
+        const DevType<R>& k = tb.types[mt & DM_TYPE_MASK];
+        R ex, ey;
+        box_extents(sm.c[b], sm.s[b], k.hl, k.hw, ex, ey);
+        for (int r = 0; r < sc.n_roads; ++r) {
+          const R q = dense_road_share(sc, sm, k, b, r, ex, ey, tau, tangent);
+          if (r == 0 || q > p) p = q;
+        }
+      }
+      rb -= p * cstep;
+      rb += ego_rel * cstep;
+      if (p > R(0.5)) buf.liveness[(int64_t)b * n + e] += 1;
+      if (terminal) rb += win_ego ? -sc.reward_win : (win_tester < 0 ? sc.reward_draw : (win_tester == b ? sc.reward_win : sc.reward_draw));
+    }
+    if (io.reward_out) io.reward_out[(int64_t)b * n + e] = rb;
+  }
+  tangent = __any_sync(kFull, tangent);
+
+  int32_t winner = -1;
+  if (terminal) { if (win_ego) winner = 0; else if (win_tester >= 0) winner = win_tester; }
+  env.t_ep += 1;
+  env.winner = winner;
+  if (terminate) env.done = 1;
+  else if (env.t_ep >= sc.max_timesteps) env.done = 2;
+  if (lane == 0) {
+    buf.t_ep[e] = env.t_ep;
+    if (env.done) { buf.done[e] = env.done; buf.winner[e] = env.winner; }
+    if (tangent) count_tangent(buf.stats);
+    if (io.done_out) io.done_out[e] = terminate ? 1 : 0;
+    if (io.winner_out) io.winner_out[e] = winner;
+    if (io.tangent_out) io.tangent_out[e] = tangent ? 1 : 0;
+  }
+  if (env.done) {   // reporting.analyse_episode (reporting.py:227-243)
+    __syncwarp();   // liveness increments of this step are visible to the lanes that sum them
+    long long sum = 0;
+    for (int b = lane; b < M; b += 32) if (b > 0) sum += buf.liveness[(int64_t)b * n + e];
+    sum = (long long)warp_sum((unsigned long long)sum);
+    if (lane == 0) score_episode<R, 1>(buf.stats, env.t_ep, env.winner, sum);
+  }
+}
+
+template <typename R>
+__device__ __forceinline__ StepIO<R> io_at(const StepIO<R>& io, int64_t t, int64_t m, int64_t n) {
+  const int64_t per_env = t * n;
+  StepIO<R> at;
+  at.actions = io.actions ? io.actions + per_env * m * 2 : nullptr;
+  at.state_out = io.state_out ? io.state_out + per_env * m * 4 : nullptr;
+  at.reward_out = io.reward_out ? io.reward_out + per_env * m : nullptr;
+  at.done_out = io.done_out ? io.done_out + per_env : nullptr;
+  at.winner_out = io.winner_out ? io.winner_out + per_env : nullptr;
+  at.tangent_out = io.tangent_out ? io.tangent_out + per_env : nullptr;
+  return at;
+}
+
+// traj != 0: io.* are [T] slabs (cavgym_replay); otherwise the same buffers are used by every step.
+template <typename R, bool AGENTS>
+__global__ void __launch_bounds__(kDenseWarps * 32) dense_kernel(const __grid_constant__ DevScenario<R> sc,
+                                                                 const __grid_constant__ DenseTables<R> tb,
+                                                                 const __grid_constant__ EnvBuffers<R> buf,
+                                                                 const __grid_constant__ StepIO<R> io, int64_t t_global, int n_steps,
+                                                                 int auto_reset, int traj) {
+  extern __shared__ __align__(16) unsigned char dense_smem[];
+  const int M = sc.n_bodies, Mp = (M + 31) & ~31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* bp_all = reinterpret_cast<float4*>(dense_smem);
+  R* geo_all = reinterpret_cast<R*>(dense_smem + sizeof(float4) * kDenseWarps * Mp);
+  int32_t* meta = reinterpret_cast<int32_t*>(geo_all + (size_t)kDenseWarps * 5 * Mp);
+  for (int b = threadIdx.x; b < Mp; b += blockDim.x) meta[b] = b < M ? tb.bodies[b].meta : (int32_t)DM_ABSENT;
+  __syncthreads();
+  const int64_t e = buf.lo + (int64_t)blockIdx.x * kDenseWarps + warp;
+  if (e >= buf.hi) return;
+  DenseSmem<R> sm;
+  sm.bp = bp_all + (size_t)warp * Mp;
+  R* geo = geo_all + (size_t)warp * 5 * Mp;
+  sm.x = geo; sm.y = geo + Mp; sm.c = geo + 2 * Mp; sm.s = geo + 3 * Mp; sm.th = geo + 4 * Mp;
+  sm.meta = meta;
+  const int64_t n = buf.n;
+
+  DenseEnv env;
+  env.done = buf.done[e];
+  env.t_ep = buf.t_ep[e];
+  env.winner = env.done ? buf.winner[e] : -1;
+  env.episode = AGENTS ? buf.episode[e] : 0;
+  for (int t = 0; t < n_steps; ++t) {
+    const StepIO<R> at = traj ? io_at(io, (int64_t)t, (int64_t)M, n) : io;
+#ifdef CAV_DENSE_DEBUG
+    if (e == 1 && lane == 1 && t < 3) printf("loop t=%d n_steps=%d traj=%d io.actions=%p at.actions=%p io.state=%p at.state=%p M=%d n=%lld\n", t, n_steps, traj, (const void*)io.actions, (const void*)(io.actions + (traj ? (int64_t)t * M * 2 * n : 0)), (void*)io.state_out, (void*)at.state_out, M, (long long)n);
+#endif
+    if (env.done && AGENTS && auto_reset) dense_reset_env<R>(sc, tb, buf, nullptr, e, lane, env);
+    if (env.done) {   // frozen until reset: reward 0, latched done / winner
+      for (int b = lane; b < M; b += 32) {
+        if (at.reward_out) at.reward_out[(int64_t)b * n + e] = R(0);
+        if (at.state_out && at.state_out != buf.state) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) at.state_out[((int64_t)b * 4 + c) * n + e] = buf.state[((int64_t)b * 4 + c) * n + e];
+        }
+      }
+      if (lane == 0) {
+        if (at.done_out) at.done_out[e] = env.done == 1 ? 1 : 0;
+        if (at.winner_out) at.winner_out[e] = env.winner;
+        if (at.tangent_out) at.tangent_out[e] = 0;
+      }
+      continue;
+    }
+    // (the actions pointer travels on its own: nvcc 12.9 folds `at.actions` back to `io.actions` when it is a member of the
+    //  copied struct — seen in the PTX — while the output members are advanced correctly)
+    const R* actions_t = io.actions;
+    if (traj && actions_t) actions_t += (int64_t)t * M * 2 * n;
+    dense_transition<R, AGENTS>(sc, tb, buf, at, actions_t, e, t_global + t, lane, sm, env);
+    __syncwarp();
+  }
+  if (AGENTS && auto_reset && env.done) dense_reset_env<R>(sc, tb, buf, nullptr, e, lane, env);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kDenseWarps * 32) dense_reset_kernel(const __grid_constant__ DevScenario<R> sc,
+                                                                       const __grid_constant__ DenseTables<R> tb,
+                                                                       const __grid_constant__ EnvBuffers<R> buf, const uint8_t* mask,
+                                                                       const R* init, int first_time) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = buf.lo + (int64_t)blockIdx.x * kDenseWarps + warp;
+  if (e >= buf.hi || (mask && !mask[e])) return;
+  DenseEnv env;
+  env.episode = first_time ? -1 : buf.episode[e];
+  if (!first_time && !buf.done[e] && lane == 0) {  // an unfinished episode is abandoned: keep its steps in the env-step total
+    const int32_t t = buf.t_ep[e];
+    if (t > 0) atomicAdd(&buf.stats[CAV_STAT_ENV_STEPS], (unsigned long long)t);
+  }
+  __syncwarp();
+  dense_reset_env<R>(sc, tb, buf, init, e, lane, env);
+  if (first_time && lane == 0) buf.err[e] = 0;
+}
+
+// ---------------------------------------------------------------- host-side launch table
+template <typename R>
+struct DenseLaunchers {
+  // false = launch set-up failed (shared-memory opt-in)
+  bool (*run)(const DevScenario<R>&, const DenseTables<R>&, const EnvBuffers<R>&, const StepIO<R>&, int64_t t_global, int n_steps,
+              int auto_reset, int traj, bool agents, cudaStream_t);
+  void (*reset)(const DevScenario<R>&, const DenseTables<R>&, const EnvBuffers<R>&, const uint8_t* mask, const R* init, int first_time,
+                cudaStream_t);
+};
+
+template <typename R, bool AGENTS>
+bool launch_dense_typed(const DevScenario<R>& sc, const DenseTables<R>& tb, const EnvBuffers<R>& buf, const StepIO<R>& io,
+                        int64_t t_global, int n_steps, int auto_reset, int traj, cudaStream_t stream) {
+  const size_t smem = dense_smem_bytes<R>(sc.n_bodies, kDenseWarps);
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(dense_kernel<R, AGENTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return false;
+  const unsigned grid = (unsigned)((buf.hi - buf.lo + kDenseWarps - 1) / kDenseWarps);
+  dense_kernel<R, AGENTS><<<grid, kDenseWarps * 32, smem, stream>>>(sc, tb, buf, io, t_global, n_steps, auto_reset, traj);
+  return true;
+}
+
+template <typename R>
+bool launch_dense(const DevScenario<R>& sc, const DenseTables<R>& tb, const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t t_global,
+                  int n_steps, int auto_reset, int traj, bool agents, cudaStream_t stream) {
+  return agents ? launch_dense_typed<R, true>(sc, tb, buf, io, t_global, n_steps, auto_reset, traj, stream)
+                : launch_dense_typed<R, false>(sc, tb, buf, io, t_global, n_steps, auto_reset, traj, stream);
+}
+
+template <typename R>
+void launch_dense_reset(const DevScenario<R>& sc, const DenseTables<R>& tb, const EnvBuffers<R>& buf, const uint8_t* mask, const R* init,
+                        int first_time, cudaStream_t stream) {
+  const unsigned grid = (unsigned)((buf.hi - buf.lo + kDenseWarps - 1) / kDenseWarps);
+  dense_reset_kernel<R><<<grid, kDenseWarps * 32, 0, stream>>>(sc, tb, buf, mask, init, first_time);
+}
+
+template <typename R> const DenseLaunchers<R>* dense_launchers();   // defined in dense.cu
+
+}  // namespace cav

@@ -165,6 +165,10 @@ class BatchedCAVEnv:
         """False forces the plain thread-per-env step kernel (the TMA-staged kernel is the default where it applies)."""
         _native.check(self._lib.cavgym_set_step_path(self._handle, int(bool(use_tma))))
 
+    def set_dense_path(self, force=True):
+        """True runs a small scenario through the warp-per-env kernels that scenarios with > CAV_SMALL_M bodies always use."""
+        _native.check(self._lib.cavgym_set_dense_path(self._handle, int(bool(force))))
+
     def set_host_path(self, zero_copy=True):
         """False makes step_host stage pinned buffers through device copies instead of the zero-copy launch."""
         _native.check(self._lib.cavgym_set_host_path(self._handle, int(bool(zero_copy))))

@@ -41,8 +41,8 @@ typedef struct CUstream_st* cudaStream_t;
 #define CAV_MAX_SPAWN_BOXES 2   /* pedestrians.py:45-68 */
 #define CAV_MAX_SPAWN_ORIENT 4
 #define CAV_MAX_TYPES 8
-#define CAV_SMALL_M 8           /* thread-per-env fused kernel up to this many bodies */
-#define CAV_MAX_BODIES 512      /* block-per-env dense kernel up to this many bodies */
+#define CAV_SMALL_M 8           /* thread-per-env fused kernels up to this many bodies */
+#define CAV_MAX_BODIES 512      /* warp-per-env dense kernels (bodies staged in shared memory) up to this many bodies */
 #define CAV_AGENT_WORDS 5       /* CrossingAgent state (pedestrian.py:14-31); NaN = None */
 #define CAV_DRAWS 3             /* [0,1) draws an agent may consume per step */
 
@@ -220,6 +220,11 @@ int cavgym_set_action_logging(CavEngine* engine, int enabled);
  * aligned buffers) and the plain thread-per-env kernel for whatever is left; use_tma = 0 forces the plain kernel
  * everywhere (A/B measurements, parity of the two paths). */
 int cavgym_set_step_path(CavEngine* engine, int use_tma);
+
+/* Scenarios with more than CAV_SMALL_M bodies always run the warp-per-environment kernels (one env per warp, bodies
+ * staged in shared memory, fp32 broad phase + exact narrow phase for the all-pairs collision test of
+ * environment.py:156-177); force = 1 selects them for a small scenario too (parity of the two paths), 0 goes back. */
+int cavgym_set_dense_path(CavEngine* engine, int force);
 
 /* cavgym_step_host with pinned (page-locked, mapped) buffers runs as one launch that reads and writes host memory
  * directly over PCIe; zero_copy = 0 forces the staged path (chunked async copies through device buffers), which is also

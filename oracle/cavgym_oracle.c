@@ -144,6 +144,17 @@ static int separates(const CavQuad* A, const CavQuad* B, double* margin) {
 /* Shape.intersects (geometry.py:74-75): closed-set intersection of two convex quads.
  * *tangent is set when the float separation margin is within tau of zero. */
 static int quad_intersects(const CavQuad* A, const CavQuad* B, double tau, int* tangent) {
+  /* Bounding boxes more than a pixel apart: disjoint, and nowhere near tangent (for the rectangles of this path the
+   * largest edge-normal separation is >= gap / sqrt(2) >> tau).  Purely an early-out of the all-pairs loop
+   * (environment.py:156-177 at M = 320 meets 51,040 pairs per step); the decision and the flag are unchanged. */
+  {
+    double ax0 = A->x[0], ax1 = A->x[0], ay0 = A->y[0], ay1 = A->y[0], bx0 = B->x[0], bx1 = B->x[0], by0 = B->y[0], by1 = B->y[0];
+    for (int i = 1; i < 4; ++i) {
+      ax0 = fmin(ax0, A->x[i]); ax1 = fmax(ax1, A->x[i]); ay0 = fmin(ay0, A->y[i]); ay1 = fmax(ay1, A->y[i]);
+      bx0 = fmin(bx0, B->x[i]); bx1 = fmax(bx1, B->x[i]); by0 = fmin(by0, B->y[i]); by1 = fmax(by1, B->y[i]);
+    }
+    if (ax0 - bx1 > 1.0 || bx0 - ax1 > 1.0 || ay0 - by1 > 1.0 || by0 - ay1 > 1.0) return 0;
+  }
   double margin = -INFINITY;
   int sep = separates(A, B, &margin) | separates(B, A, &margin);
   if (fabs(margin) < tau) *tangent = 1;
