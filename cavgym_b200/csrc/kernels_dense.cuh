@@ -29,8 +29,12 @@ namespace cav {
 #ifndef CAV_DENSE_WARPS
 #define CAV_DENSE_WARPS 4
 #endif
+#ifndef CAV_DENSE_MIN_BLOCKS
+#define CAV_DENSE_MIN_BLOCKS 1
+#endif
 constexpr int kDenseWarps = CAV_DENSE_WARPS;
 constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kDenseTiles = CAV_MAX_BODIES / 32;
 
 enum { DM_TYPE_MASK = 7, DM_PELICAN = 8, DM_PEDESTRIAN = 16, DM_SPAWN = 32, DM_AGENT_SHIFT = 8, DM_AGENT_MASK = 7, DM_ABSENT = 1 << 15 };
 
@@ -57,29 +61,38 @@ __device__ __forceinline__ int dm_agent(int32_t mt) { return (mt >> DM_AGENT_SHI
 template <typename R>
 struct DenseSmem {
   float4* bp;              // [Mp] broad-phase entries
-  R *x, *y, *c, *s, *th;   // [Mp] stepped bodies
+  float4* tu;              // [kDenseTiles] union of the entries of each 32-body tile
+  R *x, *y, *v, *c, *s, *th;   // [Mp] bodies (resident for the whole launch)
   const int32_t* meta;     // [Mp], shared by the CTA
 };
 
 template <typename R>
 __host__ __device__ inline size_t dense_smem_bytes(int m, int warps) {
   const size_t mp = (size_t)((m + 31) & ~31);
-  return (size_t)warps * mp * (sizeof(float4) + 5 * sizeof(R)) + mp * sizeof(int32_t);
+  return (size_t)warps * ((mp + kDenseTiles) * sizeof(float4) + mp * 6 * sizeof(R)) + mp * sizeof(int32_t);
 }
 
-// Broad-phase entry of a box: centre and AABB half extents in fp32, the extents rounded OUTWARD by more than every
-// rounding error of the fp32 test  |xf_i - xf_j| - (Ex_i + Ex_j) > 0  =>  |x_i - x_j| - (ex_i + ex_j) > tau  in R:
-// converting a coordinate costs <= 2^-24 |x|, the subtraction and the sum another 2^-24 relative each; the slack below is
-// 4e-7 (|x| + ex) + 2 tau, i.e. > 6 x 2^-24 relative plus the tangent tolerance.  An absent / static body gets
-// -infinity extents: it is "separated" from everything.
-template <typename R>
-__device__ __forceinline__ float4 broad_entry(R x, R y, R ex, R ey, R tau) {
-  const float xf = (float)x, yf = (float)y;
-  const float exf = __double2float_ru((double)ex), eyf = __double2float_ru((double)ey);
-  const float tf = 2.0f * __double2float_ru((double)tau);
-  return make_float4(xf, yf, exf + ((fabsf(xf) + exf) * 4e-7f + tf), eyf + ((fabsf(yf) + eyf) * 4e-7f + tf));
+// Broad-phase entry of a box: its axis-aligned bounds {x lo, x hi, y lo, y hi} in fp32, widened by the tangent tolerance and
+// rounded OUTWARD (round-down for lo, round-up for hi, every operation), so that
+//     R-precision test not "apart"  (|x_i - x_j| - (ex_i + ex_j) <= tau and the same in y)
+//  => lo_i <= hi_j and lo_j <= hi_i in both axes            (four fp32 compares, no arithmetic, hence no rounding)
+// i.e. the fp32 filter passes a superset of the pairs the exact stage wants to see.  An absent / static body gets the
+// empty interval (+inf, -inf): it overlaps nothing.
+__device__ __forceinline__ float4 broad_entry(double x, double y, double ex, double ey, double tau) {
+  return make_float4(__double2float_rd(__dsub_rd(__dsub_rd(x, ex), tau)), __double2float_ru(__dadd_ru(__dadd_ru(x, ex), tau)),
+                     __double2float_rd(__dsub_rd(__dsub_rd(y, ey), tau)), __double2float_ru(__dadd_ru(__dadd_ru(y, ey), tau)));
 }
-__device__ __forceinline__ float4 broad_absent() { return make_float4(0.f, 0.f, -INFINITY, -INFINITY); }
+__device__ __forceinline__ float4 broad_entry(float x, float y, float ex, float ey, float tau) {
+  return make_float4(__fsub_rd(__fsub_rd(x, ex), tau), __fadd_ru(__fadd_ru(x, ex), tau),
+                     __fsub_rd(__fsub_rd(y, ey), tau), __fadd_ru(__fadd_ru(y, ey), tau));
+}
+__device__ __forceinline__ float4 broad_absent() { return make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY); }
+// float <-> int with the same order (for the warp-wide REDUX min / max, which exist for integers only)
+__device__ __forceinline__ int ordered_int(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+__device__ __forceinline__ bool broad_overlap(const float4& a, const float4& b) {
+  return a.x <= b.y && b.x <= a.y && a.z <= b.w && b.z <= a.w;
+}
 
 template <typename R>
 __device__ __forceinline__ Box<R> dense_box(const DenseSmem<R>& sm, const DevType<R>& k, int b) {
@@ -127,11 +140,82 @@ __device__ __forceinline__ R dense_road_share(const DevScenario<R>& sc, const De
 struct DenseEnv {
   int32_t t_ep, episode, winner;
   uint8_t done;
+  // lane-private, bit k = body lane + 32 k:
+  uint32_t busy;      // its crossing agent has a waypoint or a target orientation (state words worth reading)
+  uint32_t v_dirty;   // its velocity changed since it was staged
+  uint32_t h_dirty;   // its heading (theta, cos, sin) changed since it was staged
+  bool moved;         // some transition ran since the bodies were staged
 };
+
+// Bodies of env e, global -> shared, by their lanes (lane-private: the same lane reads them back).  Loads go out in
+// batches of four bodies before any of them is used: 24 independent loads in flight per lane instead of one memory
+// latency per body.  Also finds which crossing agents are mid-crossing (DenseEnv::busy).
+template <typename R, bool AGENTS>
+__device__ __noinline__ void dense_stage_env(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, int lane,
+                                                const DenseSmem<R>& sm, DenseEnv& env) {
+  __builtin_assume(__isShared(sm.bp)); __builtin_assume(__isShared(sm.tu)); __builtin_assume(__isShared(sm.x)); __builtin_assume(__isShared(sm.y));
+  __builtin_assume(__isShared(sm.v)); __builtin_assume(__isShared(sm.c)); __builtin_assume(__isShared(sm.s));
+  __builtin_assume(__isShared(sm.th)); __builtin_assume(__isShared(sm.meta));
+  const int M = sc.n_bodies;
+  const int64_t n = buf.n;
+  env.busy = 0; env.v_dirty = 0; env.h_dirty = 0; env.moved = false;
+  for (int b0 = lane, k0 = 0; b0 < M; b0 += 128, k0 += 4) {
+    R tmp[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int b = b0 + 32 * u;
+      if (b < M) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) tmp[u][w] = buf.state[((int64_t)b * 4 + w) * n + e];
+        tmp[u][4] = buf.cs[((int64_t)b * 2 + 0) * n + e];
+        tmp[u][5] = buf.cs[((int64_t)b * 2 + 1) * n + e];
+        const int agent = dm_agent(sm.meta[b]);
+        tmp[u][6] = tmp[u][7] = nan_<R>();
+        if (AGENTS && (agent == CAV_AGENT_RANDOM_CONSTRAINED || agent == CAV_AGENT_PROXIMITY)) {
+          tmp[u][6] = buf.agent[((int64_t)b * CAV_AGENT_WORDS + 1) * n + e];
+          tmp[u][7] = buf.agent[((int64_t)b * CAV_AGENT_WORDS + 3) * n + e];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int b = b0 + 32 * u;
+      if (b < M) {
+        sm.x[b] = tmp[u][0]; sm.y[b] = tmp[u][1]; sm.v[b] = tmp[u][2]; sm.th[b] = tmp[u][3]; sm.c[b] = tmp[u][4]; sm.s[b] = tmp[u][5];
+        if (!isnan_(tmp[u][6]) || !isnan_(tmp[u][7])) env.busy |= 1u << (k0 + u);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Shared -> global for what changed since staging.
+template <typename R>
+__device__ __noinline__ void dense_writeback_env(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, int lane,
+                                                    const DenseSmem<R>& sm, DenseEnv& env) {
+  __builtin_assume(__isShared(sm.bp)); __builtin_assume(__isShared(sm.tu)); __builtin_assume(__isShared(sm.x)); __builtin_assume(__isShared(sm.y));
+  __builtin_assume(__isShared(sm.v)); __builtin_assume(__isShared(sm.c)); __builtin_assume(__isShared(sm.s));
+  __builtin_assume(__isShared(sm.th)); __builtin_assume(__isShared(sm.meta));
+  if (!env.moved) return;
+  const int M = sc.n_bodies;
+  const int64_t n = buf.n;
+  for (int b = lane, k = 0; b < M; b += 32, ++k) {
+    if (sm.meta[b] & DM_PELICAN) continue;   // its light state is written when it changes
+    buf.state[((int64_t)b * 4 + 0) * n + e] = sm.x[b];
+    buf.state[((int64_t)b * 4 + 1) * n + e] = sm.y[b];
+    if (env.v_dirty >> k & 1u) buf.state[((int64_t)b * 4 + 2) * n + e] = sm.v[b];
+    if (env.h_dirty >> k & 1u) {
+      buf.state[((int64_t)b * 4 + 3) * n + e] = sm.th[b];
+      buf.cs[((int64_t)b * 2 + 0) * n + e] = sm.c[b];
+      buf.cs[((int64_t)b * 2 + 1) * n + e] = sm.s[b];
+    }
+  }
+  env.v_dirty = 0; env.h_dirty = 0; env.moved = false;
+}
 
 // CAVEnv.reset for env e by its warp (reset_env of transition.cuh, lane-strided over bodies).
 template <typename R>
-__device__ __forceinline__ void dense_reset_env(const DevScenario<R>& sc, const DenseTables<R>& tb, const EnvBuffers<R>& buf,
+__device__ __noinline__ void dense_reset_env(const DevScenario<R>& sc, const DenseTables<R>& tb, const EnvBuffers<R>& buf,
                                                 const R* init, int64_t e, int lane, DenseEnv& env) {
   const int M = sc.n_bodies;
   const int64_t n = buf.n;
@@ -180,9 +264,14 @@ __device__ __forceinline__ void dense_reset_env(const DevScenario<R>& sc, const 
   __syncwarp();
 }
 
-// Exact stage of one candidate pair (i < j): the test sequence of transition.cuh's all-pairs loop.
+// Exact stage of one candidate pair (i < j): the test sequence of transition.cuh's all-pairs loop.  Out of line: it runs a
+// few times per env-step and is referenced from six places of the sweep, which must stay small enough for the
+// instruction cache.
 template <typename R>
-__device__ __forceinline__ bool dense_pair(const DenseSmem<R>& sm, const DenseTables<R>& tb, int i, int j, R tau, bool& tangent) {
+__device__ __noinline__ bool dense_pair(const DenseSmem<R>& sm, const DenseTables<R>& tb, int i, int j, R tau, bool& tangent) {
+  __builtin_assume(__isShared(sm.bp)); __builtin_assume(__isShared(sm.tu)); __builtin_assume(__isShared(sm.x)); __builtin_assume(__isShared(sm.y));
+  __builtin_assume(__isShared(sm.v)); __builtin_assume(__isShared(sm.c)); __builtin_assume(__isShared(sm.s));
+  __builtin_assume(__isShared(sm.th)); __builtin_assume(__isShared(sm.meta));
   const DevType<R>& ki = tb.types[sm.meta[i] & DM_TYPE_MASK];
   const DevType<R>& kj = tb.types[sm.meta[j] & DM_TYPE_MASK];
   R exi, eyi, exj, eyj;
@@ -203,6 +292,11 @@ __device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const
   const int64_t n = buf.n;
   const R tau = sc.tau, dt = sc.dt;
   bool tangent = false;
+  // the staging arrays reach this function through a struct of generic pointers: tell the compiler they are shared memory
+  // (LDS / STS instead of generic LD / ST in the pair sweep)
+  __builtin_assume(__isShared(sm.bp)); __builtin_assume(__isShared(sm.tu)); __builtin_assume(__isShared(sm.x)); __builtin_assume(__isShared(sm.y));
+  __builtin_assume(__isShared(sm.v)); __builtin_assume(__isShared(sm.c)); __builtin_assume(__isShared(sm.s));
+  __builtin_assume(__isShared(sm.th)); __builtin_assume(__isShared(sm.meta));
 
   // ---- action_space.contains for the replayed actions (environment.py:120): before any mutation
   if (!AGENTS || tb.has_external) {
@@ -222,8 +316,10 @@ __device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const
       for (int b = lane; b < M; b += 32) {
         if (io.reward_out) io.reward_out[(int64_t)b * n + e] = R(0);
         if (io.state_out && io.state_out != buf.state) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) io.state_out[((int64_t)b * 4 + c) * n + e] = buf.state[((int64_t)b * 4 + c) * n + e];
+          io.state_out[((int64_t)b * 4 + 0) * n + e] = sm.x[b];
+          io.state_out[((int64_t)b * 4 + 1) * n + e] = sm.y[b];
+          io.state_out[((int64_t)b * 4 + 2) * n + e] = sm.v[b];
+          io.state_out[((int64_t)b * 4 + 3) * n + e] = sm.th[b];
         }
       }
       if (lane == 0) {
@@ -236,35 +332,44 @@ __device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const
     }
   }
 
-  // ---- agents, body.step (environment.py:122-123), process_feedback (simulation.py:86-87: a function of the body's own
-  //      new state only), staging of the stepped bodies
-  const R ego_pre_x = buf.state[e], ego_pre_y = buf.state[n + e];   // ProximityAgent looks at the ego BEFORE it moves
+  const R ego_pre_x = sm.x[0], ego_pre_y = sm.y[0];   // ProximityAgent looks at the ego BEFORE it moves
   __syncwarp();
+
+  // ---- agents, body.step (environment.py:122-123), process_feedback (simulation.py:86-87: a function of the body's own
+  //      new state only).  The bodies live in shared memory; a replayed action is fetched one iteration ahead; an idle
+  //      crossing agent (DenseEnv::busy clear) that is not triggered touches no memory at all.
   R ego_steer = R(0), ego_v = R(0);
   bool agent_invalid = false;
-  for (int b = lane; b < Mp; b += 32) {
+  R w0_next = R(0), w1_next = R(0);
+  auto prefetch = [&](int b) {
+    if (b >= M) return;
+    if (!AGENTS || dm_agent(sm.meta[b]) == CAV_AGENT_EXTERNAL) {
+      w0_next = actions[((int64_t)b * 2 + 0) * n + e]; w1_next = actions[((int64_t)b * 2 + 1) * n + e];
+    }
+  };
+  prefetch(lane);
+  env.moved = true;
+  for (int b = lane, kbit = 0; b < Mp; b += 32, ++kbit) {
     if (b >= M) { sm.bp[b] = broad_absent(); continue; }
     const int32_t mt = sm.meta[b];
     const int agent = dm_agent(mt);
     const bool pelican = (mt & DM_PELICAN) != 0;
     const DevType<R>& k = tb.types[mt & DM_TYPE_MASK];
-    R st[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) st[c] = buf.state[((int64_t)b * 4 + c) * n + e];
+    const R w0 = w0_next, w1 = w1_next;
+    prefetch(b + 32);
+    const R v_old = sm.v[b];
+    R st[4] = {sm.x[b], sm.y[b], v_old, sm.th[b]};
     R a0 = R(0), a1 = R(0);
     R ag[CAV_AGENT_WORDS];
-    bool ag_dirty = false;
+    bool ag_dirty = false, ag_loaded = false;
     const bool crossing = AGENTS && (agent == CAV_AGENT_RANDOM_CONSTRAINED || agent == CAV_AGENT_PROXIMITY);
     if (!AGENTS || agent == CAV_AGENT_EXTERNAL) {
-      a0 = actions[((int64_t)b * 2 + 0) * n + e]; a1 = actions[((int64_t)b * 2 + 1) * n + e];
+      a0 = w0; a1 = w1;
     } else {
       const DenseBody<R>& body = tb.bodies[b];
+      R held0 = R(0), held1 = R(0);
       if (agent == CAV_AGENT_RANDOM) {  // holds its last action (template.py:52-56)
-        a0 = buf.action[((int64_t)b * 2 + 0) * n + e]; a1 = buf.action[((int64_t)b * 2 + 1) * n + e];
-      }
-      if (crossing) {
-#pragma unroll
-        for (int w = 0; w < CAV_AGENT_WORDS; ++w) ag[w] = buf.agent[((int64_t)b * CAV_AGENT_WORDS + w) * n + e];
+        held0 = a0 = buf.action[((int64_t)b * 2 + 0) * n + e]; held1 = a1 = buf.action[((int64_t)b * 2 + 1) * n + e];
       }
       double u[CAV_DRAWS] = {0.0, 0.0, 0.0};
       if (agent == CAV_AGENT_RANDOM || agent == CAV_AGENT_RANDOM_CONSTRAINED) {
@@ -292,47 +397,53 @@ __device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const
             a1 = R(double(k.smin) + (double(k.smax) - double(k.smin)) * u[2]);
           }
         }
-      } else if (agent == CAV_AGENT_RANDOM_CONSTRAINED) {
-        a0 = R(0);
-        a1 = choose_crossing_action(sc, k, st, ag, u[0] < body.epsilon, ag_dirty);
-      } else if (agent == CAV_AGENT_PROXIMITY) {
-        const bool trigger = point_distance(st[0], st[1], ego_pre_x, ego_pre_y) < body.threshold;
-        a0 = R(0);
-        a1 = choose_crossing_action(sc, k, st, ag, trigger, ag_dirty);
+      } else if (crossing) {
+        const bool trigger = agent == CAV_AGENT_RANDOM_CONSTRAINED
+                                 ? u[0] < body.epsilon
+                                 : point_distance(st[0], st[1], ego_pre_x, ego_pre_y) < body.threshold;
+        // An idle agent (no waypoint, no target orientation) that is not triggered chooses steering 0 and its
+        // process_feedback is a no-op (pedestrian.py:36-69): its state words are read only when a crossing starts or is
+        // under way.
+        a0 = R(0); a1 = R(0);
+        if (trigger || (env.busy >> kbit & 1u)) {
+#pragma unroll
+          for (int w = 0; w < CAV_AGENT_WORDS; ++w) ag[w] = buf.agent[((int64_t)b * CAV_AGENT_WORDS + w) * n + e];
+          ag_loaded = true;
+          a1 = choose_crossing_action(sc, k, st, ag, trigger, ag_dirty);
+        } else {
+          a1 = rmin(k.smax, rmax(k.smin, R(0)));   // make_steering_action with no target (dynamic_body.py:33-49)
+        }
       }
       if (pelican) agent_invalid |= !(a0 == R(0) || a0 == R(1) || a0 == R(2) || a0 == R(3));
       else agent_invalid |= !(a0 >= k.amin && a0 <= k.amax && a1 >= k.smin && a1 <= k.smax);
-      if (buf.log_actions || agent == CAV_AGENT_RANDOM) {
+      if (buf.log_actions || (agent == CAV_AGENT_RANDOM && (a0 != held0 || a1 != held1))) {
         buf.action[((int64_t)b * 2 + 0) * n + e] = a0; buf.action[((int64_t)b * 2 + 1) * n + e] = a1;
       }
     }
-    if (pelican) {  // PelicanCrossing.step (bodies.py:450-461)
+    if (pelican) {  // PelicanCrossing.step (bodies.py:450-461): the light state lives in the x slot
+      const R light = st[0];
       if (a0 == R(1)) st[0] = R(0);
       else if (a0 == R(2)) st[0] = R(1);
       else if (a0 == R(3)) st[0] = R(2);
-      buf.state[((int64_t)b * 4) * n + e] = st[0];
-      sm.x[b] = R(0); sm.y[b] = R(0); sm.c[b] = R(1); sm.s[b] = R(0); sm.th[b] = R(0);
+      if (!(st[0] == light)) buf.state[((int64_t)b * 4) * n + e] = st[0];
+      sm.x[b] = st[0];
       sm.bp[b] = broad_absent();
     } else {
-      R c = buf.cs[((int64_t)b * 2 + 0) * n + e], s = buf.cs[((int64_t)b * 2 + 1) * n + e], snapped;
-#ifdef CAV_DENSE_DEBUG
-      if (e == 1 && b == 1 && t_global < 3) printf("t=%lld a0=%g a1=%g actions=%p n=%lld st=%g %g %g %g c=%g s=%g smax=%g\n", (long long)t_global, (double)a0, (double)a1, (const void*)actions, (long long)n, (double)st[0], (double)st[1], (double)st[2], (double)st[3], (double)c, (double)s, (double)k.smax);
-#endif
-      if (body_step(k, st, a0, a1, dt, c, s, snapped)) {
-        buf.cs[((int64_t)b * 2 + 0) * n + e] = c; buf.cs[((int64_t)b * 2 + 1) * n + e] = s;
-      }
+      R c = sm.c[b], s = sm.s[b], snapped;
+      const bool turned = body_step(k, st, a0, a1, dt, c, s, snapped);
       if (b == 0) { ego_steer = snapped; ego_v = st[2]; }
-      if (crossing) crossing_feedback(sc, st, ag, ag_dirty);
-#pragma unroll
-      for (int w = 0; w < 4; ++w) buf.state[((int64_t)b * 4 + w) * n + e] = st[w];
-      sm.x[b] = st[0]; sm.y[b] = st[1]; sm.c[b] = c; sm.s[b] = s; sm.th[b] = st[3];
+      if (ag_loaded) crossing_feedback(sc, st, ag, ag_dirty);
+      sm.x[b] = st[0]; sm.y[b] = st[1];
+      if (!(st[2] == v_old)) { sm.v[b] = st[2]; env.v_dirty |= 1u << kbit; }
+      if (turned) { sm.c[b] = c; sm.s[b] = s; sm.th[b] = st[3]; env.h_dirty |= 1u << kbit; }
       R ex, ey;
       box_extents(c, s, k.hl, k.hw, ex, ey);
       sm.bp[b] = broad_entry(st[0], st[1], ex, ey, tau);
     }
-    if (crossing && ag_dirty) {
+    if (ag_loaded && ag_dirty) {
 #pragma unroll
       for (int w = 0; w < CAV_AGENT_WORDS; ++w) buf.agent[((int64_t)b * CAV_AGENT_WORDS + w) * n + e] = ag[w];
+      if (!isnan_(ag[1]) || !isnan_(ag[3])) env.busy |= 1u << kbit; else env.busy &= ~(1u << kbit);
     }
     if (io.state_out && io.state_out != buf.state) {
 #pragma unroll
@@ -361,26 +472,73 @@ __device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const
   }
   if (!terminate && sc.collisions == CAV_COLLISIONS_ALL) {
     bool hit = false;
-    // dynamic vs dynamic: lane owns body j = jt + lane and meets every i < j; the entry of body i is a broadcast read
-    for (int jt = 0; jt < Mp; jt += 32) {
-      const int j = jt + lane;
-      const float4 pj = sm.bp[j];
-      const int iend = jt + 32 < M ? jt + 32 : M;
-      for (int i0 = 0; i0 < iend; i0 += 8) {
-        unsigned cand = 0;
+    // dynamic vs dynamic, two levels.
+    // Tiles: the union of the entries of every 32-body tile (four warp-wide REDUX each).  A whole tile of i's is skipped
+    // when no lane's body overlaps its union — exact, never changes a result; how much it saves depends on how
+    // spatially coherent the body order is (dense_traffic.py orders bodies along the road).
+    // Bodies: a lane owns two bodies per pass, jA = jt + lane and jB = jt + 32 + lane, and meets every i below them; the
+    // entry of body i is one broadcast LDS.128 shared by both tests.
+    // Candidates are rare (a few per env-step): eight tests are folded into one vote, and only a vote that fires looks at
+    // them one by one.
+    for (int tile = 0; tile * 32 < Mp; ++tile) {
+      const float4 p = sm.bp[tile * 32 + lane];
+      const int x0 = __reduce_min_sync(kFull, ordered_int(p.x)), x1 = __reduce_max_sync(kFull, ordered_int(p.y));
+      const int y0 = __reduce_min_sync(kFull, ordered_int(p.z)), y1 = __reduce_max_sync(kFull, ordered_int(p.w));
+      if (lane == 0) sm.tu[tile] = make_float4(ordered_float(x0), ordered_float(x1), ordered_float(y0), ordered_float(y1));
+    }
+    __syncwarp();
+    for (int jt = 0; jt < Mp; jt += 64) {
+      const int jA = jt + lane, jB = jt + 32 + lane;
+      const bool haveB = jt + 32 < Mp;
+      const float4 pA = sm.bp[jA], pB = haveB ? sm.bp[jB] : broad_absent();
+      // every body of tiles [lo, hi) against this lane's jA and jB (all of them lie below both): broadcast reads
+      auto sweep = [&](int lo, int hi, const bool useA) {
+        for (int i0 = lo; i0 < hi; i0 += 8) {
+          bool any = false;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float4 pi = sm.bp[i0 + u];
-          const float gx = fabsf(pi.x - pj.x) - (pi.z + pj.z), gy = fabsf(pi.y - pj.y) - (pi.w + pj.w);
-          if (!(fmaxf(gx, gy) > 0.f) && i0 + u < j) cand |= 1u << u;
-        }
-        if (__any_sync(kFull, cand != 0)) {
-          while (cand) {
-            const int u = __ffs(cand) - 1;
-            cand &= cand - 1;
-            hit |= dense_pair(sm, tb, i0 + u, j, tau, tangent);
+          for (int u = 0; u < 8; ++u) {
+            const float4 pi = sm.bp[i0 + u];
+            if (useA) any |= broad_overlap(pi, pA);
+            any |= broad_overlap(pi, pB);
+          }
+          if (__any_sync(kFull, any)) {
+            if (any) {
+              for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u;
+                const float4 pi = sm.bp[i];
+                if (useA && broad_overlap(pi, pA)) hit |= dense_pair(sm, tb, i, jA, tau, tangent);
+                if (broad_overlap(pi, pB)) hit |= dense_pair(sm, tb, i, jB, tau, tangent);
+              }
+            }
           }
         }
+      };
+      // the pairs INSIDE one tile, by rotation: in round r lane l meets the body of lane (l + r) mod 32, so rounds 1..15 meet
+      // every unordered pair once and round 16 meets the remaining sixteen (lanes 0..15 only) — no index compare per test
+      auto within = [&](int base, const float4& pj, int j) {
+        bool any = false;
+#pragma unroll
+        for (int r = 1; r <= 16; ++r) {
+          const float4 pi = sm.bp[base + ((lane + r) & 31)];
+          any |= broad_overlap(pi, pj) && (r < 16 || lane < 16);
+        }
+        if (__any_sync(kFull, any)) {
+          if (any) {
+            for (int r = 1; r <= 16; ++r) {
+              const int i = base + ((lane + r) & 31);
+              if ((r < 16 || lane < 16) && broad_overlap(sm.bp[i], pj)) hit |= dense_pair(sm, tb, i < j ? i : j, i < j ? j : i, tau, tangent);
+            }
+          }
+        }
+      };
+      for (int it = 0; it < jt; it += 32) {                      // tiles wholly below both of this pass's tiles
+        const float4 ui = sm.tu[it >> 5];
+        if (__any_sync(kFull, broad_overlap(ui, pA) || broad_overlap(ui, pB))) sweep(it, it + 32, true);
+      }
+      within(jt, pA, jA);
+      if (haveB) {
+        sweep(jt, jt + 32, false);                               // all of tile A is below tile B
+        within(jt + 32, pB, jB);
       }
     }
     // dynamic vs static collidables (traffic lights, obstacle: environment.py:94-101)
@@ -481,7 +639,7 @@ __device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const
       }
       rb -= p * cstep;
       rb += ego_rel * cstep;
-      if (p > R(0.5)) buf.liveness[(int64_t)b * n + e] += 1;
+      if (p > R(0.5)) atomicAdd(&buf.liveness[(int64_t)b * n + e], 1);   // result unused: a fire-and-forget RED
       if (terminal) rb += win_ego ? -sc.reward_win : (win_tester < 0 ? sc.reward_draw : (win_tester == b ? sc.reward_win : sc.reward_draw));
     }
     if (io.reward_out) io.reward_out[(int64_t)b * n + e] = rb;
@@ -526,7 +684,7 @@ __device__ __forceinline__ StepIO<R> io_at(const StepIO<R>& io, int64_t t, int64
 
 // traj != 0: io.* are [T] slabs (cavgym_replay); otherwise the same buffers are used by every step.
 template <typename R, bool AGENTS>
-__global__ void __launch_bounds__(kDenseWarps * 32) dense_kernel(const __grid_constant__ DevScenario<R> sc,
+__global__ void __launch_bounds__(kDenseWarps * 32, CAV_DENSE_MIN_BLOCKS) dense_kernel(const __grid_constant__ DevScenario<R> sc,
                                                                  const __grid_constant__ DenseTables<R> tb,
                                                                  const __grid_constant__ EnvBuffers<R> buf,
                                                                  const __grid_constant__ StepIO<R> io, int64_t t_global, int n_steps,
@@ -535,16 +693,17 @@ __global__ void __launch_bounds__(kDenseWarps * 32) dense_kernel(const __grid_co
   const int M = sc.n_bodies, Mp = (M + 31) & ~31;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4* bp_all = reinterpret_cast<float4*>(dense_smem);
-  R* geo_all = reinterpret_cast<R*>(dense_smem + sizeof(float4) * kDenseWarps * Mp);
-  int32_t* meta = reinterpret_cast<int32_t*>(geo_all + (size_t)kDenseWarps * 5 * Mp);
+  R* geo_all = reinterpret_cast<R*>(dense_smem + sizeof(float4) * kDenseWarps * (Mp + kDenseTiles));
+  int32_t* meta = reinterpret_cast<int32_t*>(geo_all + (size_t)kDenseWarps * 6 * Mp);
   for (int b = threadIdx.x; b < Mp; b += blockDim.x) meta[b] = b < M ? tb.bodies[b].meta : (int32_t)DM_ABSENT;
   __syncthreads();
   const int64_t e = buf.lo + (int64_t)blockIdx.x * kDenseWarps + warp;
   if (e >= buf.hi) return;
   DenseSmem<R> sm;
-  sm.bp = bp_all + (size_t)warp * Mp;
-  R* geo = geo_all + (size_t)warp * 5 * Mp;
-  sm.x = geo; sm.y = geo + Mp; sm.c = geo + 2 * Mp; sm.s = geo + 3 * Mp; sm.th = geo + 4 * Mp;
+  sm.bp = bp_all + (size_t)warp * (Mp + kDenseTiles);
+  sm.tu = sm.bp + Mp;
+  R* geo = geo_all + (size_t)warp * 6 * Mp;
+  sm.x = geo; sm.y = geo + Mp; sm.v = geo + 2 * Mp; sm.c = geo + 3 * Mp; sm.s = geo + 4 * Mp; sm.th = geo + 5 * Mp;
   sm.meta = meta;
   const int64_t n = buf.n;
 
@@ -553,18 +712,23 @@ __global__ void __launch_bounds__(kDenseWarps * 32) dense_kernel(const __grid_co
   env.t_ep = buf.t_ep[e];
   env.winner = env.done ? buf.winner[e] : -1;
   env.episode = AGENTS ? buf.episode[e] : 0;
+  // The bodies are staged ONCE per launch and stay in shared memory across the fused steps; what changed goes back to
+  // global memory at the end of the launch (or is discarded when the episode ends and the env is reset in-kernel).
+  dense_stage_env<R, AGENTS>(sc, buf, e, lane, sm, env);
   for (int t = 0; t < n_steps; ++t) {
     const StepIO<R> at = traj ? io_at(io, (int64_t)t, (int64_t)M, n) : io;
-#ifdef CAV_DENSE_DEBUG
-    if (e == 1 && lane == 1 && t < 3) printf("loop t=%d n_steps=%d traj=%d io.actions=%p at.actions=%p io.state=%p at.state=%p M=%d n=%lld\n", t, n_steps, traj, (const void*)io.actions, (const void*)(io.actions + (traj ? (int64_t)t * M * 2 * n : 0)), (void*)io.state_out, (void*)at.state_out, M, (long long)n);
-#endif
-    if (env.done && AGENTS && auto_reset) dense_reset_env<R>(sc, tb, buf, nullptr, e, lane, env);
+    if (env.done && AGENTS && auto_reset) {
+      dense_reset_env<R>(sc, tb, buf, nullptr, e, lane, env);
+      dense_stage_env<R, AGENTS>(sc, buf, e, lane, sm, env);
+    }
     if (env.done) {   // frozen until reset: reward 0, latched done / winner
       for (int b = lane; b < M; b += 32) {
         if (at.reward_out) at.reward_out[(int64_t)b * n + e] = R(0);
         if (at.state_out && at.state_out != buf.state) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) at.state_out[((int64_t)b * 4 + c) * n + e] = buf.state[((int64_t)b * 4 + c) * n + e];
+          at.state_out[((int64_t)b * 4 + 0) * n + e] = sm.x[b];
+          at.state_out[((int64_t)b * 4 + 1) * n + e] = sm.y[b];
+          at.state_out[((int64_t)b * 4 + 2) * n + e] = sm.v[b];
+          at.state_out[((int64_t)b * 4 + 3) * n + e] = sm.th[b];
         }
       }
       if (lane == 0) {
@@ -582,6 +746,7 @@ __global__ void __launch_bounds__(kDenseWarps * 32) dense_kernel(const __grid_co
     __syncwarp();
   }
   if (AGENTS && auto_reset && env.done) dense_reset_env<R>(sc, tb, buf, nullptr, e, lane, env);
+  else dense_writeback_env<R>(sc, buf, e, lane, sm, env);
 }
 
 template <typename R>

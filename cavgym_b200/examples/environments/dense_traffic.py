@@ -52,7 +52,9 @@ def make_bodies(num_cars=64, num_pedestrians=256, length_m=400, lanes_per_direct
     cars = []
     for i in range(num_cars):
         lane, orientation = lanes[i % len(lanes)]
-        along = (i // len(lanes)) * (length / per_lane)          # distance from the lane's own rear edge
+        # distance from the lane's own rear edge: the ego starts ON the edge like the stock ego; every other car starts a
+        # car length inside, so that no road share sits exactly on the 0.5 liveness threshold (environment.py:144)
+        along = (i // len(lanes)) * (length / per_lane) + (0 if i == 0 else car_constants.length)
         position = geometry.Point(along, 0.0).rotate(orientation).translate(lane.spawn)
         cars.append(Car(init_state=DynamicBodyState(position=position, velocity=cruise, orientation=orientation),
                         constants=car_constants))
@@ -76,7 +78,17 @@ def make_bodies(num_cars=64, num_pedestrians=256, length_m=400, lanes_per_direct
                 orientations=[orientation]),
             constants=pedestrian_constants,
             np_random=np_random))
-    return cars + pedestrians
+    # Body order: the ego first (environment.py:86), then everything by position along the road, so that consecutive
+    # bodies are neighbours in space (the engine's collision broad phase culls whole groups of 32 consecutive bodies).
+    rest = sorted(cars[1:] + pedestrians, key=lambda body: _along(body))
+    return [cars[0]] + rest
+
+
+def _along(body):
+    if isinstance(body, SpawnPedestrian):
+        box = body.spawn_init_state.position_boxes[0]
+        return sum(x for x, _ in box) / 4
+    return body.init_state.position.x
 
 
 class DenseTrafficEnv(CAVEnv):

@@ -18,15 +18,16 @@ from cavgym_b200.examples.environments import dense_traffic  # noqa: E402
 from cavgym_b200.scenario import AgentSpec, compile_scenario  # noqa: E402
 
 
-def scenario(cars, peds, epsilon, external=False):
+def scenario(cars, peds, epsilon, external=False, collisions="all"):
     road_map, constants = dense_traffic.make_world()
     bodies = dense_traffic.make_bodies(cars, peds, np_random=np.random.RandomState(0), road_map=road_map)
-    cfg = SimpleNamespace(terminate_collisions="all", terminate_ego_zones=True, terminate_ego_offroad=False, max_timesteps=1000,
+    cfg = SimpleNamespace(terminate_collisions=collisions, terminate_ego_zones=True, terminate_ego_offroad=False, max_timesteps=1000,
                           reward_win=6000.0, reward_draw=2000.0, cost_step=4.0)
     if external:
         specs = [AgentSpec("external") for _ in bodies]
     else:
-        specs = [AgentSpec("noop") for _ in range(cars)] + [AgentSpec("random-constrained", epsilon=epsilon) for _ in range(peds)]
+        from cavgym_b200.library.bodies import Pedestrian
+        specs = [AgentSpec("random-constrained", epsilon=epsilon) if isinstance(body, Pedestrian) else AgentSpec("noop") for body in bodies]
     return compile_scenario(bodies, constants, cfg, specs)
 
 
@@ -40,10 +41,11 @@ def main():
     ap.add_argument("--chunk", type=int, default=5, help="env-steps per launch")
     ap.add_argument("--warm", type=int, default=60, help="untimed env-steps first (crossings under way)")
     ap.add_argument("--epsilon", type=float, default=2e-4)
+    ap.add_argument("--collisions", default="all")
     ap.add_argument("--replay", action="store_true", help="cavgym_step with a (noop) actions buffer instead of on-device agents")
     args = ap.parse_args()
     m = args.cars + args.peds
-    env = BatchedCAVEnv(None, None, None, num_envs=args.envs, dtype=args.dtype, compiled=scenario(args.cars, args.peds, args.epsilon, args.replay),
+    env = BatchedCAVEnv(None, None, None, num_envs=args.envs, dtype=args.dtype, compiled=scenario(args.cars, args.peds, args.epsilon, args.replay, args.collisions),
                         device="cuda:0", seed=1)
     env.reset()
     if args.replay:
@@ -68,7 +70,7 @@ def main():
     env_steps = after["env_steps"] - before["env_steps"]
     pairs = m * (m - 1) // 2
     real = 8 if args.dtype == "float64" else 4
-    out = {"workload": f"dense traffic: {args.cars} cars + {args.peds} spawned pedestrians x {args.envs} envs, collisions=all, "
+    out = {"workload": f"dense traffic: {args.cars} cars + {args.peds} spawned pedestrians x {args.envs} envs, collisions={args.collisions}, "
                        + ("replayed noop actions, cavgym_step" if args.replay else f"on-device agents (eps={args.epsilon}), auto-reset, {args.chunk} steps/launch"),
            "dtype": args.dtype, "ms_per_env_step_batch": ms / (args.steps * args.chunk), "env_steps_per_sec": env_steps / ms * 1e3,
            "body_steps_per_sec": env_steps * m / ms * 1e3, "pair_tests_per_sec": env_steps * pairs / ms * 1e3,

@@ -23,28 +23,32 @@ def dense_config(collisions="all"):
 
 def dense_scenario(mode, num_cars=64, num_pedestrians=256, epsilon=0.002, collisions="all"):
     from cavgym_b200.examples.environments import dense_traffic
+    from cavgym_b200.library.bodies import Pedestrian
     from cavgym_b200.scenario import AgentSpec, compile_scenario
     road_map, constants = dense_traffic.make_world()
     bodies = dense_traffic.make_bodies(num_cars, num_pedestrians, np_random=np.random.RandomState(0), road_map=road_map)
     if mode == "external":
         specs = [AgentSpec("external") for _ in bodies]
-    else:
-        specs = [AgentSpec("noop")] + [AgentSpec("random", epsilon=epsilon) for _ in range(num_cars - 1)] + \
-                [AgentSpec("random-constrained", epsilon=epsilon) for _ in range(num_pedestrians)]
-    return compile_scenario(bodies, constants, dense_config(collisions), specs)
+    else:   # bodies are ordered along the road, cars and pedestrians interleaved: the agent follows the body's class
+        specs = [AgentSpec("noop") if i == 0 else
+                 AgentSpec("random-constrained", epsilon=epsilon) if isinstance(body, Pedestrian) else
+                 AgentSpec("random", epsilon=epsilon) for i, body in enumerate(bodies)]
+    comp = compile_scenario(bodies, constants, dense_config(collisions), specs)
+    comp.is_car = np.array([not isinstance(body, Pedestrian) for body in bodies])
+    return comp
 
 
-def random_actions(rng, t_len, n, num_cars, num_pedestrians):
+def random_actions(rng, t_len, n, is_car):
     """Valid joint actions [T, M, 2, N]: cars brake / accelerate and steer a little, pedestrians wander."""
-    m = num_cars + num_pedestrians
+    m = len(is_car)
+    car = is_car[None, :, None]
     actions = np.zeros((t_len, m, 2, n))
     hold = rng.random((t_len, m, n)) < 0.1
     throttle = rng.uniform(-140.0, 140.0, (t_len, m, n))
     steer_car = rng.uniform(-0.3, 0.3, (t_len, m, n))
     steer_ped = rng.uniform(-0.4 * np.pi, 0.4 * np.pi, (t_len, m, n))
-    actions[:, :num_cars, 0] = np.where(hold, throttle, 0.0)[:, :num_cars]
-    actions[:, :num_cars, 1] = np.where(hold, steer_car, 0.0)[:, :num_cars]
-    actions[:, num_cars:, 1] = np.where(rng.random((t_len, m, n)) < 0.3, steer_ped, 0.0)[:, num_cars:]
+    actions[:, :, 0] = np.where(hold & car, throttle, 0.0)
+    actions[:, :, 1] = np.where(car, np.where(hold, steer_car, 0.0), np.where(rng.random((t_len, m, n)) < 0.3, steer_ped, 0.0))
     return actions
 
 
@@ -143,7 +147,7 @@ def test_dense_traffic_replay_matches_oracle(dtype):
     n, t_len, cars, peds = 10, 120, 64, 256
     comp = dense_scenario("external")
     rng = np.random.RandomState(5)
-    actions = random_actions(rng, t_len, n, cars, peds)
+    actions = random_actions(rng, t_len, n, comp.is_car)
     oracle = Oracle(dense_scenario("external"), n, seed=9, threads=8)
     oracle.reset()
     init = oracle.state.copy()          # the oracle's Philox spawn draws, replayed as initial states
@@ -198,7 +202,7 @@ def test_dense_invalid_action_sets_error_flag_and_leaves_state():
     env.reset()
     before = env.state.clone()
     actions = torch.zeros((cars + peds, 2, n), dtype=torch.float64, device=env.device)
-    actions[300, 1, 4] = 10.0    # steering far outside +-0.4 pi, one body of one env
+    actions[300, 1, 4] = 10.0    # steering far outside every body's limits, one body of one env
     state, reward, done, winner, _ = env.step(actions)
     torch.cuda.synchronize()
     err = env.error.cpu().numpy()
