@@ -44,13 +44,23 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get(kernel, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons with NVML while the timed region runs."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._halt = threading.Event()
+        self._halt, self.ready = threading.Event(), threading.Event()
 
     def run(self):
         try:
@@ -62,13 +72,17 @@ class ClockSampler(threading.Thread):
                      pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                      pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                      pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
-            while not self._halt.is_set():
+            self.ready.set()
+            while True:   # at least one sample, even when the timed region lasts a few milliseconds
                 self.samples.append(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
                 mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
                 self.reasons.update(name for bit, name in names.items() if mask & bit)
-                time.sleep(0.02)
+                if self._halt.is_set():
+                    break
+                time.sleep(0.001)
         except Exception as exc:  # NVML missing: report nothing rather than guess
             self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+            self.ready.set()
 
     def stop(self):
         self._halt.set()
@@ -111,8 +125,8 @@ def run_ours(args):
     import torch.distributed as dist
     from cavgym_b200 import BatchedCAVEnv
 
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
+    from cavgym_b200 import sharding
+    rank, world, local = sharding.rank_world()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     device = torch.device("cuda", local)
@@ -121,9 +135,9 @@ def run_ours(args):
     bytes_env_step = m * BYTES_PER_BODY_STEP[dtype] + BYTES_PER_ENV_STEP_EXTRA
     peak_gbs, peak_src = peaks()
 
-    init, actions = make_trace(torch, device, n, SEGMENT, dtype, env_offset=rank * n)
+    init, actions = make_trace(torch, device, n, SEGMENT, dtype, env_offset=sharding.shard_offset(rank, n))
     env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=scenario("external"), device=device,
-                        env_offset=rank * n)
+                        env_offset=sharding.shard_offset(rank, n))
     slab = {"state": torch.empty((CHUNK, m, 4, n), dtype=env.dtype, device=device),
             "reward": torch.empty((CHUNK, m, n), dtype=env.dtype, device=device),
             "done": torch.empty((CHUNK, n), dtype=torch.uint8, device=device),
@@ -169,12 +183,17 @@ def run_ours(args):
     before, launches_before = env.stats(), env.launch_count()
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.ready.wait(timeout=10)    # NVML initialised before the timed region starts
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.profile_region:      # ncu --profile-from-start off: capture exactly the timed region
+        torch.cuda.profiler.start()
     start.record()
     cursor = advance(args.steps, cursor, True)
     stop.record()
     barrier()
+    if args.profile_region:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop()
     elapsed_ms = start.elapsed_time(stop)
     after, launches_after = env.stats(), env.launch_count()
@@ -185,21 +204,20 @@ def run_ours(args):
     kernel_steps = sum(k for _, _, k in kernel_events)
     replay_launches = len(kernel_events)
 
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
-    total = torch.tensor([float(live_env_steps)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(total, op=dist.ReduceOp.SUM)
-    elapsed_ms, total_env_steps = float(t.item()), float(total.item())
+    elapsed_ms, total_env_steps = sharding.reduce_timing(elapsed_ms, live_env_steps, device)   # MAX time, SUM units
     value = total_env_steps / (elapsed_ms * 1e-3)
 
     # roofline of the dominant kernel (replay_kernel): algorithmic bytes per launch / mean launch duration
     live_fraction = live_env_steps / float(n * args.steps)
     bytes_per_launch = bytes_env_step * n * (kernel_steps / replay_launches) * live_fraction
     achieved = bytes_per_launch / (kernel_ms / replay_launches * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": f"replay_kernel<{'double' if dtype == 'float64' else 'float'},2>",
+    kernel_name = f"replay_tma_kernel<{'double' if dtype == 'float64' else 'float'},2,false>"
+    roofline = {"bound": "hbm", "kernel": kernel_name,
                 "achieved": round(achieved, 1), "peak": peak_gbs, "peak_source": peak_src, "unit": "GB/s",
-                "frac": round(achieved / peak_gbs, 4), "traffic": None,
+                "frac": round(achieved / peak_gbs, 4), "traffic": measured_traffic(kernel_name),
+                "traffic_note": "DRAM bytes per 50-step launch (ncu); below the algorithmic figure because the fused kernel keeps "
+                                "the state in registers between steps: only actions in and trajectories out touch HBM",
+                "algorithmic_bytes_per_launch": int(bytes_per_launch),
                 "algorithmic_bytes_per_env_step": bytes_env_step, "launches": replay_launches,
                 "avg_launch_ms": round(kernel_ms / replay_launches, 4),
                 "note": "65,536 envs: state (4 MiB) stays in L2/registers, only actions and trajectories stream"}
@@ -238,30 +256,24 @@ def run_ours(args):
         torch.cuda.synchronize(device)
         e2e_s = time.perf_counter() - t0
         s1 = env.stats()
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-        tot = torch.tensor([float(s1["env_steps"] - s0["env_steps"])], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        e2e_time, e2e_units = sharding.reduce_timing(e2e_s, s1["env_steps"] - s0["env_steps"], device)
         rs = 8 if dtype == "float64" else 4
-        out["e2e"] = {"value": float(tot.item()) / float(tt.item()), "unit": "env-steps/s",
+        out["e2e"] = {"value": e2e_units / e2e_time, "unit": "env-steps/s",
                       "h2d_bytes_per_step": m * 2 * n * rs, "d2h_bytes_per_step": m * 4 * n * rs + m * n * rs + n * 6,
                       "steps": e2e_steps, "api": "cavgym_step_host, pinned host buffers, zero copy: one TMA-staged launch per step reads the actions "
                              "from and writes state/reward/done/winner/tangent to host memory over PCIe"}
 
     # ---- episode statistics: the single NCCL reduce over NVLink ---------------------
-    stats = env.stats()
-    vec = torch.tensor([stats[k] for k in ("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2",
-                                           "env_steps", "body_steps", "tangent", "errors")], dtype=torch.int64, device=device)
-    if world > 1:
-        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
-    out["episode_stats"] = dict(zip(("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2", "env_steps",
-                                     "body_steps", "tangent", "errors"), [int(v) for v in vec.tolist()]))
+    out["episode_stats"] = sharding.reduce_stats(env.stats(), device)
     env.close()
 
     if rank == 0:
         if not args.skip_hbm:
             out["hbm_config"] = hbm_config(torch, device, dtype, peak_gbs)
+        if not args.skip_configs:   # the other BASELINE configs on this one GPU: reported beside the headline, not as it
+            out["scenario_configs"] = scenario_configs(torch, device, dtype)
+            out["dense_config"] = dense_config(torch, device, dtype)
+            out["sweep_config"] = sweep_config(torch, device, dtype)
         if not args.skip_cpu:
             out["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_seconds)
         print(json.dumps(out))
@@ -300,6 +312,106 @@ def hbm_config(torch, device, dtype, peak_gbs):
             "env_steps_per_sec": n / (mean_ms * 1e-3), "body_steps_per_sec": n * m / (mean_ms * 1e-3),
             "avg_launch_ms": round(mean_ms, 4), "min_launch_ms": round(ms[0], 4), "algorithmic_bytes_per_launch": bytes_launch,
             "achieved_gbs": round(achieved, 1), "peak_gbs": peak_gbs, "frac": round(achieved / peak_gbs, 4)}
+
+
+def timed(torch, fn, repeats):
+    """Mean milliseconds of fn() over `repeats` calls, CUDA events on the current stream."""
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(repeats):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / repeats
+
+
+def scenario_configs(torch, device, dtype, n=131072, steps=1000, chunk=100):
+    """BASELINE config C3, one GPU's share (1,048,576 envs over 8 GPUs = 131,072 per GPU): each of the four
+    examples/environments scenarios with the on-device agents Config.setup would build (ego noop; tester
+    random-constrained on the pedestrians scenario, random elsewhere — config.py:358-396), auto-reset, cavgym_rollout."""
+    from helpers import compile_from_meta, load_golden
+    from cavgym_b200 import BatchedCAVEnv
+    out = {}
+    for name, golden in (("pedestrians", "pedestrians_rc_seed0"), ("crossroads", "crossroads_random_all_seed6"),
+                         ("bus-stop", "busstop_random_all_seed8"), ("pelican-crossing", "pelican_random_all_seed10")):
+        meta, _ = load_golden(golden)
+        meta["config"]["tester_config"]["epsilon"] = EPSILON
+        env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=compile_from_meta(meta, mode="device"), device=device, seed=0)
+        env.reset()
+        env.rollout(chunk, auto_reset=True)
+        torch.cuda.synchronize(device)
+        before = env.stats()
+        ms = timed(torch, lambda: env.rollout(chunk, auto_reset=True), steps // chunk) * (steps // chunk)
+        after = env.stats()
+        live = after["env_steps"] - before["env_steps"]
+        out[name] = {"bodies": env.num_bodies, "envs": n, "steps": steps, "env_steps_per_sec": live / (ms * 1e-3),
+                     "body_steps_per_sec": live * env.num_bodies / (ms * 1e-3), "episodes": after["episodes"] - before["episodes"],
+                     "collisions": meta["config"]["terminate_collisions"]}
+        env.close()
+    return {"workload": "C3 share of one GPU: 131,072 envs per scenario, on-device Philox agents (eps=0.01), auto-reset, "
+                        f"cavgym_rollout {chunk} steps/launch, {steps} steps", "scenarios": out}
+
+
+def dense_config(torch, device, dtype, n=100000, steps=40, chunk=10):
+    """BASELINE config C4: 64 cars + 256 spawned pedestrians per env (51,040 box pairs per env-step), 100,000 envs,
+    terminate_collisions = all; warp-per-env kernels (kernels_dense.cuh), on-device agents, auto-reset."""
+    from types import SimpleNamespace
+    import numpy as np
+    from cavgym_b200 import BatchedCAVEnv
+    from cavgym_b200.examples.environments import dense_traffic
+    from cavgym_b200.library.bodies import Pedestrian
+    from cavgym_b200.scenario import AgentSpec, compile_scenario
+    road_map, constants = dense_traffic.make_world()
+    bodies = dense_traffic.make_bodies(np_random=np.random.RandomState(0), road_map=road_map)
+    cfg = SimpleNamespace(terminate_collisions="all", terminate_ego_zones=True, terminate_ego_offroad=False, max_timesteps=1000,
+                          reward_win=6000.0, reward_draw=2000.0, cost_step=4.0)
+    specs = [AgentSpec("random-constrained", epsilon=2e-4) if isinstance(b, Pedestrian) else AgentSpec("noop") for b in bodies]
+    m = len(bodies)
+    env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=compile_scenario(bodies, constants, cfg, specs), device=device, seed=1)
+    env.reset()
+    for _ in range(6):
+        env.rollout(chunk, auto_reset=True)
+    torch.cuda.synchronize(device)
+    before = env.stats()
+    ms = timed(torch, lambda: env.rollout(chunk, auto_reset=True), steps // chunk) * (steps // chunk)
+    after = env.stats()
+    live = after["env_steps"] - before["env_steps"]
+    env.close()
+    rate = live / (ms * 1e-3)
+    real = 8 if dtype == "float64" else 4
+    return {"workload": f"C4: 64 cars + 256 spawned pedestrians x {n} envs, terminate_collisions=all, on-device agents "
+                        f"(noop cars, random-constrained pedestrians eps=2e-4), auto-reset, {chunk} steps/launch",
+            "kernel": f"dense_kernel<{'double' if dtype == 'float64' else 'float'},true>", "envs": n, "bodies": m,
+            "env_steps_per_sec": rate, "body_steps_per_sec": rate * m, "pair_tests_per_sec": rate * (m * (m - 1) // 2),
+            "ms_per_batch_step": ms / steps, "episodes": after["episodes"] - before["episodes"], "tangent": after["tangent"] - before["tangent"],
+            "algorithmic_gbs": rate * m * 11 * real / 1e9, "bound": "latency / ALU (see DESIGN.md 4.4), not HBM"}
+
+
+def sweep_config(torch, device, dtype, n=1048576, steps=1000, chunk=100):
+    """BASELINE config C5 (experiments.py-style seed sweep): RandomConstrained testers searching for 'interesting' episodes,
+    one wave of 1,048,576 concurrent envs with auto-reset; episodes/s and the projected time for 10 M episodes."""
+    from helpers import compile_from_meta, load_golden
+    from cavgym_b200 import BatchedCAVEnv
+    out = {}
+    for eps in (0.5, 0.01):
+        meta, _ = load_golden("pedestrians_rc_seed0")
+        meta["config"]["tester_config"]["epsilon"] = eps
+        env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=compile_from_meta(meta, mode="device"), device=device, seed=0)
+        env.reset()
+        env.rollout(chunk, auto_reset=True)
+        torch.cuda.synchronize(device)
+        before = env.stats()
+        ms = timed(torch, lambda: env.rollout(chunk, auto_reset=True), steps // chunk) * (steps // chunk)
+        after = env.stats()
+        episodes = after["episodes"] - before["episodes"]
+        live = after["env_steps"] - before["env_steps"]
+        out[f"epsilon={eps}"] = {"episodes": episodes, "interesting": after["interesting"] - before["interesting"],
+                                 "env_steps_per_sec": live / (ms * 1e-3), "body_steps_per_sec": 2 * live / (ms * 1e-3),
+                                 "episodes_per_sec": episodes / (ms * 1e-3),
+                                 "seconds_for_10M_episodes": 1e7 / (episodes / (ms * 1e-3)) if episodes else None}
+        env.close()
+    return {"workload": f"C5: pedestrians scenario, {n} concurrent envs, on-device RandomConstrained testers, auto-reset, "
+                        f"cavgym_rollout {chunk} steps/launch, {steps} steps timed", "runs": out}
 
 
 def oracle_trace(n_envs, n_steps, threads):
@@ -396,6 +508,8 @@ def main():
     parser.add_argument("--cpu-seconds", type=float, default=15.0)
     parser.add_argument("--skip-hbm", action="store_true")
     parser.add_argument("--skip-cpu", action="store_true")
+    parser.add_argument("--skip-configs", action="store_true", help="skip the C3 / C4 / C5 side measurements")
+    parser.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     args = parser.parse_args()
     if args.warmup < 3:
         args.warmup = 3

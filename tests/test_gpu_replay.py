@@ -304,3 +304,25 @@ def test_step_host_zero_copy_equals_staged_copies_and_device_step(dtype):
             assert torch.equal(host[0][key], dev.cpu()), (t, key)
     assert envs[0].stats() == envs[1].stats() == envs[2].stats()
     assert envs[0].launch_count() <= envs[1].launch_count()  # one launch per step; the staged path launches one per env-chunk
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_sharded_engines_match_one_engine(dtype):
+    """Env-sharding: two engines holding global envs [0, n) and [n, 2n) give exactly the states and episode
+    counters of one engine holding [0, 2n) — Philox is keyed by the global env id (cavgym_set_shard).  The CPU twin with
+    two gloo ranks and the all-reduce is tests/test_distributed.py."""
+    meta, _ = load_golden("pedestrians_rc_eps05_seed1")
+    n, steps = 3000, 700
+    whole = make_env(meta, 2 * n, dtype, mode="device", seed=5)
+    whole.reset()
+    whole.rollout(steps, auto_reset=True)
+    want_state, want = whole.state.cpu().numpy(), whole.stats()
+    total = None
+    for r in range(2):
+        part = make_env(meta, n, dtype, mode="device", seed=5, env_offset=r * n)
+        part.reset()
+        part.rollout(steps, auto_reset=True)
+        assert np.array_equal(part.state.cpu().numpy(), want_state[:, :, r * n:(r + 1) * n])
+        got = part.stats()
+        total = got if total is None else {k: total[k] + got[k] for k in got}
+    assert total == want and want["episodes"] > n
