@@ -1,0 +1,98 @@
+"""Episode loops over the engine.
+
+  Simulation          the reference's driver (simulation.py:9-118) on the single-environment compat view: host-side agents
+                      choose the joint action, `env.step` is one CUDA launch on a batch of one.  Same console / log lines.
+  BatchedSimulation   the same experiment at batch scale: N concurrent copies of the config's scenario, on-device agents,
+                      scoring and auto-reset inside the rollout kernel (cavgym_rollout); the run summary comes from the
+                      ten device counters (cavgym_stats), optionally summed over ranks with one all-reduce.
+"""
+import timeit
+
+from . import reporting
+from .config import AgentType, Mode
+
+
+class Simulation:
+    def __init__(self, env, agents, config, keyboard_agent=None):
+        assert len(env.bodies) == len(agents), "each body must be assigned an agent and vice versa"
+        if keyboard_agent is not None or config.mode_config.mode is Mode.RENDER:
+            raise NotImplementedError("render mode / keyboard agents are outside the batched stepping engine")
+        if config.tester_config.agent is AgentType.ELECTION:
+            raise NotImplementedError("the election tester is not provided by cavgym_b200")
+        self.env, self.agents, self.config = env, agents, config
+        self.console = reporting.get_console(config.verbosity)
+        self.episode_file = reporting.get_episode_file_logger(config.episode_log) if config.episode_log is not None else None
+        self.run_file = reporting.get_run_file_logger(config.run_log) if config.run_log is not None else None
+
+    def run(self):
+        """Runs config.episodes episodes (each cut off at config.max_timesteps); returns (episode_results, run_summary)."""
+        env, agents, config = self.env, self.agents, self.config
+        episode_data = []
+        run_start = timeit.default_timer()
+        for episode in range(1, config.episodes + 1):
+            episode_start = timeit.default_timer()
+            state = env.reset()
+            info = env.info()
+            self.console.debug(f"state={state}")
+            for agent in agents:
+                agent.reset()
+            final_timestep = config.max_timesteps
+            for timestep in range(1, config.max_timesteps + 1):
+                joint_action = [agent.choose_action(state, space, info) for agent, space in zip(agents, env.action_space)]
+                previous_state = state
+                state, joint_reward, done, info = env.step(joint_action)
+                self.console.debug(f"timestep={timestep}")
+                self.console.debug(f"action={joint_action}")
+                self.console.debug(f"state={state}")
+                self.console.debug(f"reward={joint_reward}")
+                self.console.debug(f"done={done}")
+                for agent, action, reward in zip(agents, joint_action, joint_reward):
+                    agent.process_feedback(previous_state, action, state, reward)
+                if done:
+                    final_timestep = timestep
+                    break
+            results = reporting.analyse_episode(episode, episode_start, timeit.default_timer(), final_timestep, info, config, env)
+            episode_data.append(results)
+            self.console.info(results.console_message())
+            if self.episode_file:
+                self.episode_file.info(results.file_message())
+        summary = reporting.RunSummary.from_episodes(episode_data, run_start, timeit.default_timer(), env.time_resolution)
+        self.console.info(summary.console_message())
+        if self.run_file:
+            self.run_file.info(summary.file_message())
+        env.close()
+        return episode_data, summary
+
+
+class BatchedSimulation:
+    def __init__(self, config, num_envs, device=None, dtype="float64", env_offset=0, chunk=100):
+        self.config, self.chunk = config, int(chunk)
+        self.env = config.batched(num_envs, device=device, dtype=dtype, env_offset=env_offset)
+        self.console = reporting.get_console(config.verbosity)
+        self.run_file = reporting.get_run_file_logger(config.run_log) if config.run_log is not None else None
+
+    def run(self, episodes=None, reduce=True):
+        """Rolls every env forward (auto-reset) until at least `episodes` (default: config.episodes) episodes have finished
+        on this rank; returns the RunSummary of everything finished so far (summed over ranks when a process group is up)."""
+        import torch
+        from . import sharding
+        target = self.config.episodes if episodes is None else int(episodes)
+        env = self.env
+        env.reset()
+        self.steps_run = 0
+        start = timeit.default_timer()
+        while True:
+            env.rollout(self.chunk, auto_reset=True)
+            self.steps_run += self.chunk
+            stats = env.stats()          # synchronises
+            if stats["episodes"] >= target:
+                break
+        torch.cuda.synchronize(env.device)
+        runtime_ms = (timeit.default_timer() - start) * 1000
+        if reduce:
+            stats = sharding.reduce_stats(stats, env.device)
+        summary = reporting.RunSummary.from_stats(stats, runtime_ms, env.time_resolution)
+        self.console.info(summary.console_message())
+        if self.run_file:
+            self.run_file.info(summary.file_message())
+        return summary
