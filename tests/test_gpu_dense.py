@@ -274,3 +274,30 @@ def test_dense_collision_flags_match_all_pairs_reference_at_scale(dtype):
     # zone-free env must report not done -> compare on envs where no pedestrian is anywhere near the ego's lane ahead
     quiet = ~want & clear & (winner < 0)
     assert not got[quiet].any()
+
+
+def test_maximum_body_count_matches_oracle():
+    """CAV_MAX_BODIES = 512 bodies per env (128 cars + 384 pedestrians, 130,816 pairs per step), a ragged batch of 5 envs,
+    on-device agents: engine vs oracle on every counter and on the final state."""
+    from oracle.oracle import Oracle
+    n, steps = 5, 120
+    env = make(dense_scenario("device", num_cars=128, num_pedestrians=384, epsilon=0.003), n, "float64", seed=8)
+    assert env.num_bodies == 512
+    env.reset()
+    oracle = Oracle(dense_scenario("device", num_cars=128, num_pedestrians=384, epsilon=0.003), n, seed=8, threads=8)
+    oracle.reset()
+    assert np.array_equal(env.state.cpu().numpy(), oracle.state)
+    env.rollout(steps, auto_reset=True)
+    oracle.rollout(steps, auto_reset=True)
+    got, want = env.stats(), oracle.stats()
+    if got["tangent"] == 0 and want["tangent"] == 0:
+        for key in ("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2", "env_steps"):
+            assert got[key] == want[key], key
+        assert state_err(np.moveaxis(env.state.cpu().numpy(), 1, -1), np.moveaxis(oracle.state, 1, -1)) < 1e-9
+    assert want["episodes"] >= 2
+
+
+def test_more_than_maximum_bodies_is_rejected():
+    from cavgym_b200 import _native
+    with pytest.raises((ValueError, _native.CavgymError)):
+        make(dense_scenario("external", num_cars=130, num_pedestrians=384), 2, "float64")
