@@ -40,7 +40,7 @@ def make_world(length_m=400, lanes_per_direction=4, rows=2, row_pitch_m=2.5):
 
 
 def make_bodies(num_cars=64, num_pedestrians=256, length_m=400, lanes_per_direction=4, rows=2, row_pitch_m=2.5,
-                spawn_box_m=(2.5, 0.6), np_random=None, road_map=None):
+                spawn_box_m=(2.5, 0.6), np_random=None, road_map=None, order="class"):
     if road_map is None:
         road_map, _ = make_world(length_m, lanes_per_direction, rows, row_pitch_m)
     road = road_map.major_road
@@ -78,8 +78,12 @@ def make_bodies(num_cars=64, num_pedestrians=256, length_m=400, lanes_per_direct
                 orientations=[orientation]),
             constants=pedestrian_constants,
             np_random=np_random))
-    # Body order: the ego first (environment.py:86), then everything by position along the road, so that consecutive
-    # bodies are neighbours in space (the engine's collision broad phase culls whole groups of 32 consecutive bodies).
+    # Body order: the ego first (environment.py:86), then by position along the road, so that consecutive bodies are
+    # neighbours in space (the engine's collision broad phase culls whole groups of 32 consecutive bodies).
+    # order="class" (default): cars along the road, then pedestrians along the road — groups of 32 are also of one class, so
+    # the lanes of a warp run the same agent code (measured 6 % faster than order="road", everything interleaved).
+    if order == "class":
+        return [cars[0]] + sorted(cars[1:], key=_along) + sorted(pedestrians, key=_along)
     rest = sorted(cars[1:] + pedestrians, key=lambda body: _along(body))
     return [cars[0]] + rest
 

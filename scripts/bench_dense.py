@@ -18,9 +18,9 @@ from cavgym_b200.examples.environments import dense_traffic  # noqa: E402
 from cavgym_b200.scenario import AgentSpec, compile_scenario  # noqa: E402
 
 
-def scenario(cars, peds, epsilon, external=False, collisions="all"):
+def scenario(cars, peds, epsilon, external=False, collisions="all", order="class"):
     road_map, constants = dense_traffic.make_world()
-    bodies = dense_traffic.make_bodies(cars, peds, np_random=np.random.RandomState(0), road_map=road_map)
+    bodies = dense_traffic.make_bodies(cars, peds, np_random=np.random.RandomState(0), road_map=road_map, order=order)
     cfg = SimpleNamespace(terminate_collisions=collisions, terminate_ego_zones=True, terminate_ego_offroad=False, max_timesteps=1000,
                           reward_win=6000.0, reward_draw=2000.0, cost_step=4.0)
     if external:
@@ -42,10 +42,11 @@ def main():
     ap.add_argument("--warm", type=int, default=60, help="untimed env-steps first (crossings under way)")
     ap.add_argument("--epsilon", type=float, default=2e-4)
     ap.add_argument("--collisions", default="all")
+    ap.add_argument("--order", default="class")
     ap.add_argument("--replay", action="store_true", help="cavgym_step with a (noop) actions buffer instead of on-device agents")
     args = ap.parse_args()
     m = args.cars + args.peds
-    env = BatchedCAVEnv(None, None, None, num_envs=args.envs, dtype=args.dtype, compiled=scenario(args.cars, args.peds, args.epsilon, args.replay, args.collisions),
+    env = BatchedCAVEnv(None, None, None, num_envs=args.envs, dtype=args.dtype, compiled=scenario(args.cars, args.peds, args.epsilon, args.replay, args.collisions, args.order),
                         device="cuda:0", seed=1)
     env.reset()
     if args.replay:
