@@ -130,18 +130,9 @@ __device__ __forceinline__ void heading_cs(const DevScenario<R>& sc, R th, R& c,
 // which is the same map without the cancellation of two ~kk-sized world coordinates (that cancellation costs the
 // reference ~1e-11 px per step at small steering angles in fp64 and would cost whole pixels in fp32), and without
 // sqrt, division, or atan2: the new heading's cos/sin follow by the angle-addition formulas.
+// The turning branch (bodies.py:241-275): d = v dt with the OLD velocity; st[2] has already been updated.
 template <typename R>
-__device__ __forceinline__ bool body_step(const DevType<R>& k, R st[4], R throttle, R steer, R dt, R& c, R& s, R& snapped) {
-  if (rabs(steer) < R(0.0000000000001)) steer = R(0);
-  snapped = steer;
-  const R v = st[2];
-  const R d = v * dt;
-  st[2] = rmax(k.vmin, rmin(k.vmax, v + (throttle * dt)));
-  if (steer == R(0)) {
-    st[0] = st[0] + d * c;
-    st[1] = st[1] + d * s;
-    return false;
-  }
+__device__ __forceinline__ void body_turn(const DevType<R>& k, R st[4], R steer, R d, R& c, R& s) {
   // The turn increment is evaluated in double in BOTH modes: a steering angle is held for many steps, so a few-ulp
   // float error in wb / tan(steer) would be a systematic heading drift (1e-5 rad over an episode), not a random one.
   double kk, inv_r;
@@ -160,6 +151,27 @@ __device__ __forceinline__ bool body_step(const DevType<R>& k, R st[4], R thrott
   const R c2 = c + (c * cm1 - s * sn), s2 = s + (s * cm1 + c * sn);
   c = c2; s = s2;
   st[3] = wrap_angle(st[3] + (R)phi);
+}
+// One out-of-line copy for kernels whose hot loop must stay small (kernels_dense.cuh): same arithmetic.
+template <typename R>
+__device__ __noinline__ void body_turn_outlined(const DevType<R>& k, R st[4], R steer, R d, R* c, R* s) {
+  body_turn(k, st, steer, d, *c, *s);
+}
+
+template <typename R, bool OUTLINE_TURN = false>
+__device__ __forceinline__ bool body_step(const DevType<R>& k, R st[4], R throttle, R steer, R dt, R& c, R& s, R& snapped) {
+  if (rabs(steer) < R(0.0000000000001)) steer = R(0);
+  snapped = steer;
+  const R v = st[2];
+  const R d = v * dt;
+  st[2] = rmax(k.vmin, rmin(k.vmax, v + (throttle * dt)));
+  if (steer == R(0)) {
+    st[0] = st[0] + d * c;
+    st[1] = st[1] + d * s;
+    return false;
+  }
+  if (OUTLINE_TURN) body_turn_outlined(k, st, steer, d, &c, &s);
+  else body_turn(k, st, steer, d, c, s);
   return true;
 }
 

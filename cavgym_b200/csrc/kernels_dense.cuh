@@ -103,7 +103,46 @@ __device__ __forceinline__ Pose<R> dense_pose(const DenseSmem<R>& sm, const DevT
   return {sm.x[b], sm.y[b], sm.th[b], sm.c[b], sm.s[b], k.length, k.width};
 }
 
-// road_share of transition.cuh on an explicit pose (same cases, same order, same arithmetic).
+// road_share of transition.cuh on an explicit pose (same cases, same order, same arithmetic), in two parts: the two
+// answers almost every body gets — clear of the road's bounding box: 0; axis-aligned road, clearly inside: 1 — stay inline,
+// kerbs, corners and general quads are one out-of-line function (the hot loop must stay small: the kernel is bound by
+// instruction fetch).
+template <typename R>
+__device__ __noinline__ R dense_road_share_edge(const DevScenario<R>& sc, const DenseSmem<R>& sm, const DevType<R>& k, int b, int r,
+                                                R ex, R ey, R tau, bool* near_out) {
+  bool near = false;
+  const Aabb<R> rd = sc.road_bb[r];
+  const R px = sm.x[b], py = sm.y[b];
+  const R m0 = (px - ex) - rd.x0, m1 = rd.x1 - (px + ex), m2 = (py - ey) - rd.y0, m3 = rd.y1 - (py + ey);
+  const R mx = rmin(m0, m1), my = rmin(m2, m3);
+  R result;
+  bool settled = false;
+  if (sc.road_axis[r]) {
+    const bool x_edge = mx < my;
+    const R lo = x_edge ? mx : my, hi = x_edge ? my : mx;
+    const R opposite = x_edge ? rmax(m0, m1) : rmax(m2, m3);
+    if (lo <= -tau && hi >= tau && opposite >= tau) {
+      const R ac = rabs(sm.c[b]), as = rabs(sm.s[b]);
+      const R p = kerb_share(lo + (x_edge ? ex : ey), (x_edge ? ac : as) * k.hl, (x_edge ? as : ac) * k.hw);
+      if (rabs(p - R(0.5)) < tau) near = true;
+      result = p; settled = true;
+    } else if (mx < tau && my < tau && rmax(m0, m1) >= tau && rmax(m2, m3) >= tau) {
+      const bool low_x = m0 < m1, low_y = m2 < m3;
+      const R p = corner_share(dense_pose(sm, k, b), low_x ? R(-1) : R(1), low_x ? -rd.x0 : rd.x1, low_y ? R(-1) : R(1),
+                               low_y ? -rd.y0 : rd.y1);
+      if (rabs(p - R(0.5)) < tau) near = true;
+      result = p; settled = true;
+    }
+  }
+  if (!settled) {
+    const Share<R> share = road_share_general(dense_pose(sm, k, b), &sc.quads[r], tau);
+    near = (share.tangent != 0) || (rabs(share.value - R(0.5)) < tau);
+    result = share.value;
+  }
+  *near_out = near;
+  return result;
+}
+
 template <typename R>
 __device__ __forceinline__ R dense_road_share(const DevScenario<R>& sc, const DenseSmem<R>& sm, const DevType<R>& k, int b, int r,
                                               R ex, R ey, R tau, bool& near) {
@@ -112,28 +151,57 @@ __device__ __forceinline__ R dense_road_share(const DevScenario<R>& sc, const De
   const R m0 = (px - ex) - rd.x0, m1 = rd.x1 - (px + ex), m2 = (py - ey) - rd.y0, m3 = rd.y1 - (py + ey);
   const R mx = rmin(m0, m1), my = rmin(m2, m3);
   if (mx < -((ex + ex) + tau) || my < -((ey + ey) + tau)) return R(0);
-  if (sc.road_axis[r]) {
-    const bool x_edge = mx < my;
-    const R lo = x_edge ? mx : my, hi = x_edge ? my : mx;
-    if (lo >= tau) return R(1);
-    const R opposite = x_edge ? rmax(m0, m1) : rmax(m2, m3);
-    if (lo <= -tau && hi >= tau && opposite >= tau) {
-      const R ac = rabs(sm.c[b]), as = rabs(sm.s[b]);
-      const R p = kerb_share(lo + (x_edge ? ex : ey), (x_edge ? ac : as) * k.hl, (x_edge ? as : ac) * k.hw);
-      if (rabs(p - R(0.5)) < tau) near = true;
-      return p;
-    }
-    if (mx < tau && my < tau && rmax(m0, m1) >= tau && rmax(m2, m3) >= tau) {
-      const bool low_x = m0 < m1, low_y = m2 < m3;
-      const R p = corner_share(dense_pose(sm, k, b), low_x ? R(-1) : R(1), low_x ? -rd.x0 : rd.x1, low_y ? R(-1) : R(1),
-                               low_y ? -rd.y0 : rd.y1);
-      if (rabs(p - R(0.5)) < tau) near = true;
-      return p;
-    }
+  if (sc.road_axis[r] && rmin(mx, my) >= tau) return R(1);
+  bool edge_near = false;
+  const R p = dense_road_share_edge(sc, sm, k, b, r, ex, ey, tau, &edge_near);
+  near |= edge_near;
+  return p;
+}
+
+// RandomAgent.choose_action when its epsilon test fires (template.py:52-56): Box.sample / Discrete.sample.  Out of line: rare.
+template <typename R>
+__device__ __noinline__ void dense_random_sample(const EnvBuffers<R>& buf, const DevType<R>& k, int64_t e, int b, bool pelican,
+                                                 uint32_t episode, uint32_t t_ep, double u1, double u2, R* a0, R* a1) {
+  if (pelican) {
+    R v = R(floor(u1 * 4.0));
+    if (v > R(3)) v = R(3);
+    *a0 = v; *a1 = R(0);
+    return;
   }
-  const Share<R> share = road_share_general(dense_pose(sm, k, b), &sc.quads[r], tau);
-  near |= (share.tangent != 0) || (rabs(share.value - R(0.5)) < tau);
-  return share.value;
+  if (!buf.uni_override) {
+    double w[2];
+    draw_block(buf.seed, (uint64_t)(buf.shard + e), b, KIND_AGENT1, episode, t_ep, w);
+    u2 = w[0];
+  }
+  *a0 = R(double(k.amin) + (double(k.amax) - double(k.amin)) * u1);
+  *a1 = R(double(k.smin) + (double(k.smax) - double(k.smin)) * u2);
+}
+
+// A vote of the pair sweep fired: look at the eight (or sixteen) folded tests one by one and run the exact stage on the
+// candidates.  Out of line — a few calls per env-step — so that the sweep itself is a few hundred bytes of code.
+template <typename R>
+__device__ __noinline__ bool dense_sweep_candidates(const DenseSmem<R>& sm, const DenseTables<R>& tb, int i0, int jA, int jB, bool useA,
+                                                    float4 pA, float4 pB, R tau, bool* tangent) {
+  bool hit = false, tg = false;
+  for (int u = 0; u < 8; ++u) {
+    const int i = i0 + u;
+    const float4 pi = sm.bp[i];
+    if (useA && broad_overlap(pi, pA)) hit |= dense_pair(sm, tb, i, jA, tau, tg);
+    if (broad_overlap(pi, pB)) hit |= dense_pair(sm, tb, i, jB, tau, tg);
+  }
+  *tangent |= tg;
+  return hit;
+}
+template <typename R>
+__device__ __noinline__ bool dense_within_candidates(const DenseSmem<R>& sm, const DenseTables<R>& tb, int base, int lane, int j, float4 pj,
+                                                     R tau, bool* tangent) {
+  bool hit = false, tg = false;
+  for (int r = 1; r <= 16; ++r) {
+    const int i = base + ((lane + r) & 31);
+    if ((r < 16 || lane < 16) && broad_overlap(sm.bp[i], pj)) hit |= dense_pair(sm, tb, i < j ? i : j, i < j ? j : i, tau, tg);
+  }
+  *tangent |= tg;
+  return hit;
 }
 
 // Warp-uniform per-env scalars.
@@ -383,20 +451,8 @@ __device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const
       if (agent == CAV_AGENT_NOOP) {
         a0 = R(0); a1 = R(0);
       } else if (agent == CAV_AGENT_RANDOM) {
-        if (u[0] < body.epsilon) {
-          if (pelican) {
-            a0 = R(floor(u[1] * 4.0)); if (a0 > R(3)) a0 = R(3);
-            a1 = R(0);
-          } else {
-            if (!buf.uni_override) {
-              double w[2];
-              draw_block(buf.seed, (uint64_t)(buf.shard + e), b, KIND_AGENT1, (uint32_t)env.episode, (uint32_t)env.t_ep, w);
-              u[2] = w[0];
-            }
-            a0 = R(double(k.amin) + (double(k.amax) - double(k.amin)) * u[1]);
-            a1 = R(double(k.smin) + (double(k.smax) - double(k.smin)) * u[2]);
-          }
-        }
+        if (u[0] < body.epsilon)
+          dense_random_sample(buf, k, e, b, pelican, (uint32_t)env.episode, (uint32_t)env.t_ep, u[1], u[2], &a0, &a1);
       } else if (crossing) {
         const bool trigger = agent == CAV_AGENT_RANDOM_CONSTRAINED
                                  ? u[0] < body.epsilon
@@ -430,7 +486,7 @@ __device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const
       sm.bp[b] = broad_absent();
     } else {
       R c = sm.c[b], s = sm.s[b], snapped;
-      const bool turned = body_step(k, st, a0, a1, dt, c, s, snapped);
+      const bool turned = body_step<R, true>(k, st, a0, a1, dt, c, s, snapped);
       if (b == 0) { ego_steer = snapped; ego_v = st[2]; }
       if (ag_loaded) crossing_feedback(sc, st, ag, ag_dirty);
       sm.x[b] = st[0]; sm.y[b] = st[1];
@@ -502,14 +558,7 @@ __device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const
             any |= broad_overlap(pi, pB);
           }
           if (__any_sync(kFull, any)) {
-            if (any) {
-              for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u;
-                const float4 pi = sm.bp[i];
-                if (useA && broad_overlap(pi, pA)) hit |= dense_pair(sm, tb, i, jA, tau, tangent);
-                if (broad_overlap(pi, pB)) hit |= dense_pair(sm, tb, i, jB, tau, tangent);
-              }
-            }
+            if (any) hit |= dense_sweep_candidates(sm, tb, i0, jA, jB, useA, pA, pB, tau, &tangent);
           }
         }
       };
@@ -523,12 +572,7 @@ __device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const
           any |= broad_overlap(pi, pj) && (r < 16 || lane < 16);
         }
         if (__any_sync(kFull, any)) {
-          if (any) {
-            for (int r = 1; r <= 16; ++r) {
-              const int i = base + ((lane + r) & 31);
-              if ((r < 16 || lane < 16) && broad_overlap(sm.bp[i], pj)) hit |= dense_pair(sm, tb, i < j ? i : j, i < j ? j : i, tau, tangent);
-            }
-          }
+          if (any) hit |= dense_within_candidates(sm, tb, base, lane, j, pj, tau, &tangent);
         }
       };
       for (int it = 0; it < jt; it += 32) {                      // tiles wholly below both of this pass's tiles
