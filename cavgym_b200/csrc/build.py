@@ -25,7 +25,7 @@ def sources():
 
 
 def headers_mtime():
-    paths = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".cuh")]
+    paths = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cuh", ".inc"))]
     paths.append(os.path.join(PKG, "..", "include", "cavgym.h"))
     return max(os.path.getmtime(p) for p in paths)
 

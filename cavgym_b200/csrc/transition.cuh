@@ -132,244 +132,45 @@ struct NoSink {
 
 // `moved(env)` is called once, right after body.step: a kernel that stages state in shared memory writes the new
 // state there at that point, so x, y, v, theta need not stay in registers through the geometry.
+//
+// Two instantiations of one body (transition_body.inc):
+//   transition_unrolled   loops over bodies fully unrolled, every per-body array in registers — the homogeneous and the
+//                         two-body kernels (the tuned paths of configs C2 / C5);
+//   transition_rolled     loops over bodies kept as loops.  Heterogeneous scenarios with three or more bodies (crossroads,
+//                         bus stop, pelican crossing): unrolled, one step of the M = 5 kernel is ~3,700 straight-line
+//                         instructions — 60 KB of code per step against a 32 KB instruction cache — and ncu shows it waiting
+//                         for instruction fetch 29 cycles for every cycle it issues (profiles/r1_rollout_busstop_ncu.txt).
+//                         Rolled, the per-body code exists once; the per-body arrays are then indexed at run time and live in
+//                         L1-resident local memory instead of registers.  Same arithmetic, same order: results are bitwise
+//                         those of the unrolled form (and of the warp-per-env kernels, tests/test_gpu_dense.py).
+#ifndef CAV_ROLLED_FROM_M
+#define CAV_ROLLED_FROM_M 3
+#endif
+
+#define CAV_BODY_LOOP _Pragma("unroll")
+template <typename R, int M, bool AGENTS, bool GENERIC, typename Sink = NoSink>
+__device__ __forceinline__ void transition_unrolled(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, int64_t t_global,
+                                                    EnvRegs<R, M>& env, const R (&ext)[M][2], StepResult<R, M>& out,
+                                                    Sink moved = Sink()) {
+#include "transition_body.inc"
+}
+#undef CAV_BODY_LOOP
+
+#define CAV_BODY_LOOP _Pragma("unroll 1")
+template <typename R, int M, bool AGENTS, bool GENERIC, typename Sink = NoSink>
+__device__ __forceinline__ void transition_rolled(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, int64_t t_global,
+                                                  EnvRegs<R, M>& env, const R (&ext)[M][2], StepResult<R, M>& out,
+                                                  Sink moved = Sink()) {
+#include "transition_body.inc"
+}
+#undef CAV_BODY_LOOP
+
 template <typename R, int M, bool AGENTS, bool GENERIC, typename Sink = NoSink>
 __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, int64_t t_global,
                                            EnvRegs<R, M>& env, const R (&ext)[M][2], StepResult<R, M>& out,
                                            Sink moved = Sink()) {
-  const R tau = sc.tau, dt = sc.dt;
-  bool tangent = false;
-  R act[M][2];
-  auto is_pelican = [&](int b) { return GENERIC && sc.bodies[b].kind == CAV_BODY_PELICAN; };
-  auto is_pedestrian = [&](int b) { return !GENERIC || (sc.bodies[b].flags & CAV_FLAG_PEDESTRIAN) != 0; };
-
-  // ---- joint action from the pre-step state
-  bool valid = true;
-#pragma unroll
-  for (int b = 0; b < M; ++b) {
-    const DevBody<R>& body = sc.bodies[b];
-    const DevType<R>& k = body.k;
-    R a0 = ext[b][0], a1 = ext[b][1];
-    if (AGENTS && body.agent != CAV_AGENT_EXTERNAL) {
-      a0 = env.held[b][0]; a1 = env.held[b][1];
-      double u[CAV_DRAWS] = {0.0, 0.0, 0.0};
-      const bool draws = body.agent == CAV_AGENT_RANDOM || body.agent == CAV_AGENT_RANDOM_CONSTRAINED;
-      if (draws) {
-        if (buf.uni_override) {
-#pragma unroll
-          for (int c = 0; c < CAV_DRAWS; ++c) u[c] = buf.uni_override[((int64_t)b * CAV_DRAWS + c) * buf.n + e];
-        } else {
-          draw_block(buf.seed, (uint64_t)(buf.shard + e), b, KIND_AGENT0, (uint32_t)env.episode, (uint32_t)env.t_ep, u);
-        }
-      }
-      if (body.agent == CAV_AGENT_NOOP) {
-        a0 = R(0); a1 = R(0);
-      } else if (body.agent == CAV_AGENT_RANDOM) {  // RandomAgent.choose_action (template.py:52-56)
-        if (u[0] < body.epsilon) {
-          if (is_pelican(b)) {
-            a0 = R(floor(u[1] * 4.0)); if (a0 > R(3)) a0 = R(3);
-            a1 = R(0);
-          } else {
-            if (!buf.uni_override) {
-              double w[2];
-              draw_block(buf.seed, (uint64_t)(buf.shard + e), b, KIND_AGENT1, (uint32_t)env.episode, (uint32_t)env.t_ep, w);
-              u[2] = w[0];
-            }
-            a0 = R(double(k.amin) + (double(k.amax) - double(k.amin)) * u[1]);  // Box.sample = low + (high-low)*u
-            a1 = R(double(k.smin) + (double(k.smax) - double(k.smin)) * u[2]);
-          }
-        }
-      } else if (body.agent == CAV_AGENT_RANDOM_CONSTRAINED) {  // pedestrian.py:72-75
-        a0 = R(0);
-        bool dirty = false;
-        a1 = choose_crossing_action(sc, k, env.s[b], env.ag[b], u[0] < body.epsilon, dirty);
-        if (dirty) env.ag_dirty |= 1u << b;
-      } else if (body.agent == CAV_AGENT_PROXIMITY) {  // pedestrian.py:78-91
-        const bool trigger = point_distance(env.s[b][0], env.s[b][1], env.s[0][0], env.s[0][1]) < body.threshold;
-        a0 = R(0);
-        bool dirty = false;
-        a1 = choose_crossing_action(sc, k, env.s[b], env.ag[b], trigger, dirty);
-        if (dirty) env.ag_dirty |= 1u << b;
-      }
-    }
-    act[b][0] = a0; act[b][1] = a1;
-    if (is_pelican(b)) valid = valid && (a0 == R(0) || a0 == R(1) || a0 == R(2) || a0 == R(3));
-    else valid = valid && (a0 >= k.amin && a0 <= k.amax && a1 >= k.smin && a1 <= k.smax);
-  }
-  out.invalid = !valid;
-  out.tangent = false;
-  out.terminate = false;
-  out.winner = -1;
-  if (!valid) {  // AssertionError before any mutation (environment.py:120)
-#pragma unroll
-    for (int b = 0; b < M; ++b) out.reward[b] = R(0);
-    return;
-  }
-
-  // ---- body.step, then the half extents of every body's AABB (all later tests start from them)
-  R ex[M], ey[M];
-  R ego_steer = R(0);
-#pragma unroll
-  for (int b = 0; b < M; ++b) {
-    const DevBody<R>& body = sc.bodies[b];
-    if (AGENTS) { env.held[b][0] = act[b][0]; env.held[b][1] = act[b][1]; }
-    if (is_pelican(b)) {  // PelicanCrossing.step (bodies.py:450-461)
-      if (act[b][0] == R(1)) env.s[b][0] = R(0);
-      else if (act[b][0] == R(2)) env.s[b][0] = R(1);
-      else if (act[b][0] == R(3)) env.s[b][0] = R(2);
-      ex[b] = R(0); ey[b] = R(0);
-    } else {
-      const DevType<R>& k = body.k;
-      R snapped;
-      if (body_step(k, env.s[b], act[b][0], act[b][1], dt, env.cs[b][0], env.cs[b][1], snapped)) env.cs_dirty |= 1u << b;
-      if (b == 0) ego_steer = snapped;
-      box_extents(env.cs[b][0], env.cs[b][1], k.hl, k.hw, ex[b], ey[b]);
-    }
-  }
-  moved(env);
-
-  // ---- termination cascade (evaluated before the rewards: neither depends on the other, and the rare general
-  //      road-share call below then happens with almost nothing live)
-  const R W = sc.W;
-  bool terminate = false, win_ego = false;
-  int win_tester = -1;
-  {
-    const R margin = (env.s[0][0] - ex[0]) - W;  // all four ego corners x > viewer_width  <=>  min corner x > W
-    if (margin > -tau) {                         // only the last steps of an episode get here
-      CAV_DBG(9);
-      if (margin < tau) tangent = true;
-      if (margin > R(0)) { terminate = true; win_ego = true; }
-    }
-  }
-  if (!terminate && sc.collisions == CAV_COLLISIONS_ALL) {
-    bool hit = false;
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-      if (is_pelican(i)) continue;
-#pragma unroll
-      for (int j = i + 1; j < M; ++j) {
-        if (is_pelican(j)) continue;
-        const bool apart = rabs(env.s[i][0] - env.s[j][0]) - (ex[i] + ex[j]) > tau ||
-                           rabs(env.s[i][1] - env.s[j][1]) - (ey[i] + ey[j]) > tau;
-        if (!apart) hit |= margin_hit(box_margin(body_box<R, M>(sc, env, i), body_box<R, M>(sc, env, j)), tau, tangent);
-      }
-#pragma unroll 1
-      for (int s = 0; s < sc.n_statics; ++s) {
-        const Aabb<R> sb = sc.static_bb[s];
-        const R px = env.s[i][0], py = env.s[i][1];
-        const bool apart = (px - ex[i]) - sb.x1 > tau || sb.x0 - (px + ex[i]) > tau || (py - ey[i]) - sb.y1 > tau ||
-                           sb.y0 - (py + ey[i]) > tau;
-        if (!apart) {
-          if (sc.static_rect[s]) hit |= margin_hit(box_margin(body_box<R, M>(sc, env, i), sc.static_box[s]), tau, tangent);
-          else hit |= geo_hit(sat_pose_quad(body_pose<R, M>(sc, env, i), &sc.quads[CAV_MAX_ROADS + s], tau), tangent);
-        }
-      }
-    }
-    terminate = hit;
-  }
-  if (!terminate && sc.offroad) {
-    bool on_road = false;
-#pragma unroll 1
-    for (int r = 0; r < sc.n_roads; ++r) {
-      const Aabb<R> rd = sc.road_bb[r];
-      const R px = env.s[0][0], py = env.s[0][1];
-      const bool apart = (px - ex[0]) - rd.x1 > tau || rd.x0 - (px + ex[0]) > tau || (py - ey[0]) - rd.y1 > tau ||
-                         rd.y0 - (py + ey[0]) > tau;
-      if (!apart) {
-        if (!GENERIC || sc.road_rect[r]) on_road |= margin_hit(box_margin(body_box<R, M>(sc, env, 0), sc.road_box[r]), tau, tangent);
-        else on_road |= geo_hit(sat_pose_quad(body_pose<R, M>(sc, env, 0), &sc.quads[r], tau), tangent);
-      }
-    }
-    terminate = !on_road;
-  }
-  if (!terminate && (sc.collisions == CAV_COLLISIONS_EGO || sc.zones)) {
-    const DevType<R>& k0 = sc.bodies[0].k;
-    EgoFrame<R> f;
-    f.x = env.s[0][0]; f.y = env.s[0][1]; f.c = env.cs[0][0]; f.s = env.cs[0][1]; f.hl = k0.hl; f.hw = k0.hw;
-    const R v0 = env.s[0][2];
-    f.bd = (v0 * v0) * k0.inv_2brake;           // bodies.py:123
-    f.td = f.bd + v0 * R(0.675);                // bodies.py:124-125 (REACTION_TIME)
-    f.have = !(f.td == R(0)) && (ego_steer == R(0));
-    const bool ego_mode = sc.collisions == CAV_COLLISIONS_EGO;
-    bool hit = false;
-#pragma unroll
-    for (int b = 1; b < M; ++b) {
-      if (!is_pedestrian(b)) continue;   // environment.py:192,199
-      // Common case, decided with one predicate chain: the pedestrian is clear (by tau or more) of the strip swept by
-      // the ego box and both zones.  Only otherwise are the closed predicates and near-tangent flags evaluated.
-      const EgoMargins<R> m = ego_margins(f, env.s[b][0], env.s[b][1], env.cs[b][0], env.cs[b][1], sc.bodies[b].k.hl,
-                                          sc.bodies[b].k.hw, tau);
-      if (m.all_clear) continue;
-      CAV_DBG(8);
-      if (ego_mode) {   // environment.py:183-193: ego box, then the braking zone
-        bool h = margin_hit(m.ego, tau, tangent);
-        if (!h && f.have) h = margin_hit(m.braking, tau, tangent);
-        hit |= h;
-      }
-      // environment.py:195-206: first pedestrian in the reaction zone wins (only consulted if nothing terminated above)
-      if (sc.zones && f.have && win_tester < 0 && !hit) {
-        if (margin_hit(m.reaction, tau, tangent)) win_tester = b;
-      }
-    }
-    if (hit) { terminate = true; win_tester = -1; }
-    else terminate = win_tester >= 0;
-  }
-
-  // ---- rewards and liveness
-  const R c = sc.cost_step;
-  // Both divisors are scenario constants: multiply by the host-computed reciprocal (<= 1 ulp from the division).
-  const R ego_rel = rmax(R(0), rmin(R(1), (W - env.s[0][0]) * sc.inv_W));
-  const R voff = rabs(env.s[0][2] - sc.v_maint) * sc.inv_v_off;
-  R r0 = R(0);
-  r0 -= voff * c;
-  r0 += (R(1) - ego_rel) * c;
-  out.reward[0] = r0;
-#pragma unroll
-  for (int b = 1; b < M; ++b) {
-    R p = R(0);
-    if (is_pelican(b)) {
-      p = sc.bodies[b].static_share;  // static box vs static roads: a constant of the scenario
-    } else {
-#pragma unroll 1
-      for (int r = 0; r < sc.n_roads; ++r) {  // max over roads (environment.py:141)
-        const R q = road_share<R, M, GENERIC>(sc, env, b, r, ex[b], ey[b], tau, tangent);
-        if (r == 0 || q > p) p = q;
-      }
-    }
-    R rb = R(0);
-    rb -= p * c;
-    rb += ego_rel * c;
-    out.reward[b] = rb;
-    if (p > R(0.5)) { env.live[b] += 1; env.live_dirty |= 1u << b; }
-  }
-
-  // ---- terminal rewards and winner
-  if (terminate || t_global == sc.max_timesteps - 1) {
-    out.reward[0] += win_ego ? sc.reward_win : (win_tester >= 0 ? -sc.reward_win : sc.reward_draw);
-#pragma unroll
-    for (int b = 1; b < M; ++b)
-      out.reward[b] += win_ego ? -sc.reward_win : (win_tester < 0 ? sc.reward_draw : (win_tester == b ? sc.reward_win : sc.reward_draw));
-    if (win_ego) out.winner = 0;
-    else if (win_tester >= 0) out.winner = win_tester;
-  }
-
-  // ---- crossing agents' process_feedback on the new state
-  if (AGENTS) {
-#pragma unroll
-    for (int b = 0; b < M; ++b) {
-      if (uses_agent_state<R, M>(sc, b)) {
-        bool dirty = false;
-        crossing_feedback(sc, env.s[b], env.ag[b], dirty);
-        if (dirty) env.ag_dirty |= 1u << b;
-      }
-    }
-  }
-
-  env.t_ep += 1;
-  env.winner = out.winner;
-  if (terminate) env.done = 1;
-  else if (env.t_ep >= sc.max_timesteps) env.done = 2;  // cut off by Simulation.run (simulation.py:69-70), not `done`
-  out.terminate = terminate;
-  out.tangent = tangent;
+  if constexpr (GENERIC && M >= CAV_ROLLED_FROM_M) transition_rolled<R, M, AGENTS, GENERIC, Sink>(sc, buf, e, t_global, env, ext, out, moved);
+  else transition_unrolled<R, M, AGENTS, GENERIC, Sink>(sc, buf, e, t_global, env, ext, out, moved);
 }
 
 // reporting.analyse_episode (reporting.py:227-243) for an env whose episode just ended.
