@@ -251,13 +251,13 @@ __device__ __noinline__ void spawn_body(const DevSpawn<R>& sp, const double u[5]
 // ---------------------------------------------------------------- crossing agents
 template <typename R>
 __device__ __noinline__ R steering_towards(const DevType<R>& k, R v, R theta, R dt, R target) {
-  R so, co;
-  sincos_(target - theta, &so, &co);
-  const R tta = atan2_(so, co);
+  // atan2(sin(t - theta), cos(t - theta)) (dynamic_body.py:36) is t - theta wrapped into [-pi, pi]: one conditional +-2 pi
+  // instead of three libm calls, as in body_step; sqrt(wb^2 (1 + 4 / tan^2(limit))) only ever sees the two steering limits
+  // and comes from the host (DevType::max_turn_*).
+  const R tta = wrap_angle(target - theta);
   const R csa = tta < R(0) ? k.smin : k.smax;
   const R wb = k.wheelbase;
-  const R tn = tan_(csa);
-  const R mta = (csa < R(0) ? R(-2) : R(2)) * dt * v / rsqrt_((wb * wb) * (R(1) + R(4) / (tn * tn)));
+  const R mta = (csa < R(0) ? R(-2) : R(2)) * dt * v / (csa < R(0) ? k.max_turn_smin : k.max_turn_smax);
   const R ta = (tta / mta > R(1)) ? mta : tta;
   const R steer = atan_(R(2) * wb * rsqrt_((ta * ta) / (R(4) * (v * v) * (dt * dt) - (wb * wb) * (ta * ta))));
   return ta < R(0) ? -steer : steer;
@@ -312,9 +312,8 @@ __device__ __forceinline__ void crossing_feedback(const DevScenario<R>& sc, cons
     }
   }
   if (!isnan_(ag[3])) {
-    R sd, cd;
-    sincos_(ag[3] - st[3], &sd, &cd);
-    if (rabs(atan2_(sd, cd)) < sc.target_err) { ag[3] = nan_<R>(); dirty = true; }
+    // |atan2(sin d, cos d)| < TARGET_ERROR (pedestrian.py:44-47) with d = target - theta wrapped into [-pi, pi]
+    if (rabs(wrap_angle(ag[3] - st[3])) < sc.target_err) { ag[3] = nan_<R>(); dirty = true; }
   }
 }
 

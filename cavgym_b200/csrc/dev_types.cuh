@@ -38,6 +38,9 @@ struct DevType {
   // Full-lock turns (what a crossing agent commands for all but the last step of a turn): wheelbase / tan(limit)
   // and 1 / turn radius of the body centre, host libm values.
   double kk_smin, kk_smax, inv_r_smin, inv_r_smax;  // double in both modes (see body_step)
+  // Largest heading change per unit of travelled distance at full lock, 2 / sqrt(wb^2 (1 + 4 / tan^2(limit))), host libm
+  // values in the reference's operation order (dynamic_body.py:40-41): make_steering_action only ever asks for the two limits.
+  R max_turn_smin, max_turn_smax;
 };
 
 template <typename R>

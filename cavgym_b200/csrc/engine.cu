@@ -92,6 +92,12 @@ static DevType<R> to_type(const CavBodyType& t) {
   k.kk_smin = kk_min; k.kk_smax = kk_max;
   k.inv_r_smin = 1.0 / std::sqrt(half_wb * half_wb + kk_min * kk_min);
   k.inv_r_smax = 1.0 / std::sqrt(half_wb * half_wb + kk_max * kk_max);
+  auto turn_root = [&](double limit) {   // sqrt(wb^2 (1 + 4 / tan^2(limit))) in R, as steering_towards used to form it on the device
+    const R wb = k.wheelbase, tn = (R)std::tan((double)(R)limit);
+    return (R)std::sqrt((double)((wb * wb) * ((R)1 + (R)4 / (tn * tn))));
+  };
+  k.max_turn_smin = turn_root((double)k.smin);
+  k.max_turn_smax = turn_root((double)k.smax);
   return k;
 }
 
