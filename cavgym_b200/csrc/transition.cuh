@@ -139,12 +139,15 @@ struct NoSink {
 //   transition_rolled     loops over bodies kept as loops.  Heterogeneous scenarios with three or more bodies (crossroads,
 //                         bus stop, pelican crossing): unrolled, one step of the M = 5 kernel is ~3,700 straight-line
 //                         instructions — 60 KB of code per step against a 32 KB instruction cache — and ncu shows it waiting
-//                         for instruction fetch 29 cycles for every cycle it issues (profiles/r1_rollout_busstop_ncu.txt).
+//                         for instruction fetch 29 cycles for every cycle it issues (profiles/r1_rollout_kernels_ncu.txt).
 //                         Rolled, the per-body code exists once; the per-body arrays are then indexed at run time and live in
 //                         L1-resident local memory instead of registers.  Same arithmetic, same order: results are bitwise
 //                         those of the unrolled form (and of the warp-per-env kernels, tests/test_gpu_dense.py).
 #ifndef CAV_ROLLED_FROM_M
 #define CAV_ROLLED_FROM_M 3
+#endif
+#ifndef CAV_ROLL_AGENTS
+#define CAV_ROLL_AGENTS 0
 #endif
 
 #define CAV_BODY_LOOP _Pragma("unroll")
@@ -169,7 +172,7 @@ template <typename R, int M, bool AGENTS, bool GENERIC, typename Sink = NoSink>
 __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, int64_t t_global,
                                            EnvRegs<R, M>& env, const R (&ext)[M][2], StepResult<R, M>& out,
                                            Sink moved = Sink()) {
-  if constexpr (GENERIC && M >= CAV_ROLLED_FROM_M) transition_rolled<R, M, AGENTS, GENERIC, Sink>(sc, buf, e, t_global, env, ext, out, moved);
+  if constexpr ((GENERIC && M >= CAV_ROLLED_FROM_M) || (AGENTS && CAV_ROLL_AGENTS != 0 && M >= 2)) transition_rolled<R, M, AGENTS, GENERIC, Sink>(sc, buf, e, t_global, env, ext, out, moved);
   else transition_unrolled<R, M, AGENTS, GENERIC, Sink>(sc, buf, e, t_global, env, ext, out, moved);
 }
 
