@@ -299,6 +299,55 @@ __global__ void geometry_probe_kernel(const R* qa, const R* qb, R* out, int64_t 
   out[3 * n + i] = tangent ? R(1) : R(0);
 }
 
+// CAVEnv.info (environment.py:106-117): body_polygons and road_angles of the current state, one thread per env.
+// road angle = DynamicBody.line_anchor_relative_angle (bodies.py:206-212): direction from the body to the closest point of
+// the major road's centre line (geometry.py:412-421) minus the heading, normalised into (-pi, pi] (geometry.py:380-385);
+// NaN stands for the reference's None (the body's box intersects the major road).
+template <typename R>
+__global__ void info_kernel(const __grid_constant__ DevScenario<R> sc, const __grid_constant__ DenseTables<R> tb,
+                            const __grid_constant__ EnvBuffers<R> buf, const Quad<R>* static_quads, R* polygons, R* angles) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n = buf.n;
+  if (e >= n) return;
+  const R pi = R(3.14159265358979323846), two_pi = R(6.28318530717958647692);
+  for (int b = 0; b < sc.n_bodies; ++b) {
+    const int32_t mt = tb.bodies[b].meta;
+    const DevType<R>& k = tb.types[mt & DM_TYPE_MASK];
+    const R x = buf.state[((int64_t)b * 4 + 0) * n + e], y = buf.state[((int64_t)b * 4 + 1) * n + e];
+    const R th = buf.state[((int64_t)b * 4 + 3) * n + e];
+    Quad<R> q;
+    bool on_road;
+    if (mt & DM_PELICAN) {
+      q = static_quads[b];
+      on_road = (sat_bits(q, sc.quads[0], sc.tau) & GEO_HIT) != 0;
+    } else {
+      const R c = buf.cs[((int64_t)b * 2 + 0) * n + e], s = buf.cs[((int64_t)b * 2 + 1) * n + e];
+      make_box(k.length, k.width, th, c, s, x, y, q);
+      if (sc.road_rect[0]) on_road = !(box_margin(Box<R>{x, y, c, s, k.hl, k.hw}, sc.road_box[0]) > R(0));
+      else on_road = (sat_bits(q, sc.quads[0], sc.tau) & GEO_HIT) != 0;
+    }
+    if (polygons) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        polygons[((int64_t)b * 8 + c) * n + e] = q.x[c];
+        polygons[((int64_t)b * 8 + 4 + c) * n + e] = q.y[c];
+      }
+    }
+    if (angles) {
+      R angle = nan_<R>();
+      if (!on_road) {
+        const R dx = sc.cl[2] - sc.cl[0], dy = sc.cl[3] - sc.cl[1];
+        const R a = (dy * (y - sc.cl[1]) + dx * (x - sc.cl[0])) / ((dx * dx) + (dy * dy));
+        const R cx = sc.cl[0] + a * dx, cy = sc.cl[1] + a * dy;
+        R radians = atan2_(cy - y, cx - x) - th;
+        while (radians <= -pi) radians += two_pi;
+        while (radians > pi) radians -= two_pi;
+        angle = radians == R(0) ? radians + R(0) : radians;
+      }
+      angles[(int64_t)b * n + e] = angle;
+    }
+  }
+}
+
 }  // namespace cav
 
 using namespace cav;
@@ -315,6 +364,7 @@ struct CavEngine {
   DenseTables<double> tb64;
   DenseTables<float> tb32;
   void* d_dense_bodies = nullptr;
+  void* d_static_quads = nullptr;   // Quad<R>[m]: PelicanCrossing.static_bounding_box per body (cavgym_info)
   double tau = 1e-7;
   CavScenario host{};
   std::vector<CavBody> bodies;
@@ -515,6 +565,22 @@ int cavgym_create(const CavScenario* tables, int64_t n_envs, int dtype, int devi
     eng->d_dense_bodies = rows;
   }
   if (rc == CAV_OK) rc = rebuild_tables(eng);
+  if (rc == CAV_OK) {   // static boxes of PelicanCrossing bodies, in the engine's type
+    const size_t quad_bytes = dtype == CAV_F64 ? sizeof(Quad<double>) : sizeof(Quad<float>);
+    char* quads = nullptr;
+    rc = dev_alloc(eng, &quads, (size_t)eng->m * quad_bytes);
+    eng->d_static_quads = quads;
+    if (rc == CAV_OK) {
+      std::vector<char> host((size_t)eng->m * quad_bytes, 0);
+      for (int b = 0; b < eng->m; ++b) {
+        if (eng->bodies[(size_t)b].kind != CAV_BODY_PELICAN) continue;
+        if (dtype == CAV_F64) { const Quad<double> q = to_quad<double>(eng->bodies[(size_t)b].static_box); std::memcpy(&host[(size_t)b * quad_bytes], &q, quad_bytes); }
+        else { const Quad<float> q = to_quad<float>(eng->bodies[(size_t)b].static_box); std::memcpy(&host[(size_t)b * quad_bytes], &q, quad_bytes); }
+      }
+      cudaError_t err = cudaMemcpy(quads, host.data(), host.size(), cudaMemcpyHostToDevice);
+      if (err != cudaSuccess) rc = fail(CAV_ECUDA, std::string("static quads: ") + cudaGetErrorString(err));
+    }
+  }
   if (rc == CAV_OK) rc = dev_alloc(eng, &eng->d_scratch, 2);
   if (rc == CAV_OK) rc = do_reset(eng, nullptr, nullptr, 1, nullptr);  // constructor-time spawn (bodies.py:296)
   if (rc == CAV_OK) {
@@ -691,6 +757,20 @@ int cavgym_step_host(CavEngine* eng, const void* actions, void* state_out, void*
   for (auto& s : eng->pipe) CUDA_TRY(cudaStreamSynchronize(s));
   eng->t_global += 1;
   return CAV_OK;
+}
+
+int cavgym_info(CavEngine* eng, void* polygons_out, void* road_angle_out, cudaStream_t stream) {
+  int rc = check_engine(eng);
+  if (rc) return rc;
+  if (!polygons_out && !road_angle_out) return CAV_OK;
+  const unsigned grid = (unsigned)((eng->n + 127) / 128);
+  if (eng->dtype == CAV_F64)
+    info_kernel<double><<<grid, 128, 0, stream>>>(eng->sc64, eng->tb64, eng->buf64, (const Quad<double>*)eng->d_static_quads,
+                                                  (double*)polygons_out, (double*)road_angle_out);
+  else
+    info_kernel<float><<<grid, 128, 0, stream>>>(eng->sc32, eng->tb32, eng->buf32, (const Quad<float>*)eng->d_static_quads,
+                                                 (float*)polygons_out, (float*)road_angle_out);
+  return launch_check(eng, "info kernel");
 }
 
 int cavgym_stats(CavEngine* eng, int64_t* out10) {

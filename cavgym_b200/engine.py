@@ -147,6 +147,15 @@ class BatchedCAVEnv:
         _native.check(self._lib.cavgym_step_host(self._handle, hp(actions), hp(state_out), hp(reward_out), hp(done_out),
                                                  hp(winner_out), hp(tangent_out)))
 
+    def info(self, polygons=True, road_angles=True):
+        """CAVEnv.info() for every env: {'body_polygons': [M, 8, N] (x of the four corners, then y), 'road_angles': [M, N]
+        with NaN where the reference returns None}.  Computed on demand by one small kernel."""
+        n, m = self.num_envs, self.num_bodies
+        out = {"body_polygons": torch.empty((m, 8, n), dtype=self.dtype, device=self.device) if polygons else None,
+               "road_angles": torch.empty((m, n), dtype=self.dtype, device=self.device) if road_angles else None}
+        _native.check(self._lib.cavgym_info(self._handle, _ptr(out["body_polygons"]), _ptr(out["road_angles"]), self._stream()))
+        return out
+
     # ---- accounting and knobs ------------------------------------------------------------
     def stats(self):
         out = (C.c_int64 * _abi.CAV_N_STATS)()

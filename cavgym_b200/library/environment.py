@@ -60,17 +60,16 @@ class _LazyInfo(dict):
         self._env = env
 
     def __missing__(self, key):
-        if key == 'body_polygons':
-            value = [body.bounding_box() for body in self._env.bodies]
-        elif key == 'road_angles':
-            road = self._env.constants.road_map.major_road
-            road_polygon = road.bounding_box()
-            value = [body.line_anchor_relative_angle(road) if not polygon.intersects(road_polygon) else None
-                     for body, polygon in zip(self._env.bodies, self['body_polygons'])]
-        else:
+        if key not in ('body_polygons', 'road_angles'):
             raise KeyError(key)
-        self[key] = value
-        return value
+        # one launch of the engine's info kernel (cavgym_info) on the batch of one; reference-shaped values out
+        from .geometry import ConvexQuadrilateral
+        out = self._env._batched().info()
+        corners = out['body_polygons'][:, :, 0].double().cpu().tolist()
+        angles = out['road_angles'][:, 0].double().cpu().tolist()
+        self['body_polygons'] = [ConvexQuadrilateral(*[(row[i], row[4 + i]) for i in range(4)]) for row in corners]
+        self['road_angles'] = [None if a != a else a for a in angles]
+        return self[key]
 
     def __contains__(self, key):
         return key in ('body_polygons', 'road_angles') or super().__contains__(key)

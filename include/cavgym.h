@@ -182,6 +182,13 @@ int cavgym_replay(CavEngine* engine, int n_steps, const void* actions, void* sta
 int cavgym_step_host(CavEngine* engine, const void* actions, void* state_out, void* reward_out,
                      uint8_t* done_out, int32_t* winner_out, uint8_t* tangent_flag_out);
 
+/* CAVEnv.info (environment.py:106-117) for the current state of every env, on demand (nothing on the step path reads it):
+ * polygons_out   device real[M][8][N]: body_polygons, x of rear_left, front_left, front_right, rear_right, then y
+ *                (bodies.py:116-117; PelicanCrossing: its static box), nullable;
+ * road_angle_out device real[M][N]: road_angles — DynamicBody.line_anchor_relative_angle towards the major road's centre line
+ *                (bodies.py:206-212), NaN where the reference gives None (the body's box intersects the major road), nullable. */
+int cavgym_info(CavEngine* engine, void* polygons_out, void* road_angle_out, cudaStream_t stream);
+
 /* ---- accounting ------------------------------------------------------------------ */
 
 /* reporting.analyse_episode / analyse_run (reporting.py:227-269) sums over episodes

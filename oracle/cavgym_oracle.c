@@ -23,6 +23,9 @@
  * Philox keying is restated here so engine and oracle agree draw-for-draw; the
  * MT19937 draws of a reference run can be replayed through the override buffers.
  */
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -865,6 +868,49 @@ int32_t* cav_oracle_timestep_ptr(CavOracle* o) { return o->t_ep; }
 int32_t* cav_oracle_winner_ptr(CavOracle* o) { return o->winner; }
 uint8_t* cav_oracle_done_ptr(CavOracle* o) { return o->done; }
 uint8_t* cav_oracle_error_ptr(CavOracle* o) { return o->err; }
+
+/* CAVEnv.info (environment.py:106-117) for every env: body_polygons [M][8][N] (x of rear_left, front_left, front_right,
+ * rear_right, then y) and road_angles [M][N], NaN where the reference returns None (the body's box intersects the major
+ * road).  road angle = DynamicBody.line_anchor_relative_angle (bodies.py:206-212): orientation of the line from the body to
+ * the closest point of the major road's centre line (geometry.py:412-421), minus the heading, normalised (:380-385). */
+void cav_oracle_info(CavOracle* o, double* polygons_out, double* road_angle_out) {
+  const CavScenario* sc = &o->sc;
+  const int m = sc->n_bodies;
+  const int64_t n = o->n;
+  const double* cl = sc->centre_line;
+  for (int64_t e = 0; e < n; ++e) {
+    for (int b = 0; b < m; ++b) {
+      const CavBody* body = &o->bodies[b];
+      CavQuad box;
+      if (body->kind == CAV_BODY_PELICAN) box = body->static_box;
+      else {
+        const CavBodyType* k = &sc->types[body->type_id];
+        make_box(k->length, k->width, 0.5, ST(o, b, 3, e), ST(o, b, 0, e), ST(o, b, 1, e), &box);
+      }
+      if (polygons_out)
+        for (int c = 0; c < 4; ++c) {
+          polygons_out[((int64_t)b * 8 + c) * n + e] = box.x[c];
+          polygons_out[((int64_t)b * 8 + 4 + c) * n + e] = box.y[c];
+        }
+      if (road_angle_out) {
+        int unused = 0;
+        double angle = NAN;
+        if (!quad_intersects(&box, &sc->roads[0], o->tau, &unused)) {
+          const double px = ST(o, b, 0, e), py = ST(o, b, 1, e);
+          const double dx = cl[2] - cl[0], dy = cl[3] - cl[1];
+          const double denominator = (dx * dx) + (dy * dy);
+          const double a = (dy * (py - cl[1]) + dx * (px - cl[0])) / denominator;
+          const double cx = cl[0] + a * dx, cy = cl[1] + a * dy;
+          double radians = atan2(cy - py, cx - px) - ST(o, b, 3, e);
+          while (radians <= -M_PI) radians += 2 * M_PI;
+          while (radians > M_PI) radians -= 2 * M_PI;
+          angle = radians == 0 ? radians + 0.0 : radians;
+        }
+        road_angle_out[(int64_t)b * n + e] = angle;
+      }
+    }
+  }
+}
 
 /* ---- single-shot helpers for unit parity tests (geometry known-answer vectors) */
 

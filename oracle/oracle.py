@@ -47,6 +47,7 @@ def lib():
         L.cav_oracle_rollout.argtypes = [vp, C.c_int, C.c_int]
         L.cav_oracle_replay.argtypes = [vp, C.c_int, f64p, f64p, f64p, vp, vp, vp]
         L.cav_oracle_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.cav_oracle_info.argtypes = [vp, f64p, f64p]
         for name in ("state", "action", "agent_state", "liveness", "timestep", "winner", "done", "error"):
             fn = getattr(L, f"cav_oracle_{name}_ptr")
             fn.restype, fn.argtypes = vp, [vp]
@@ -188,6 +189,12 @@ class Oracle:
                np.empty((t, n), np.uint8))
         lib().cav_oracle_replay(self._h, t, _ptr(actions), *[_ptr(a) for a in out])
         return out
+
+    def info(self):
+        """CAVEnv.info for the current state: (body_polygons [M, 8, N], road_angles [M, N], NaN = None)."""
+        polygons, angles = np.empty((self.m, 8, self.n)), np.empty((self.m, self.n))
+        lib().cav_oracle_info(self._h, _ptr(polygons), _ptr(angles))
+        return polygons, angles
 
     def stats(self):
         out = (C.c_int64 * _abi.CAV_N_STATS)()

@@ -8,7 +8,7 @@ import numpy as np
 from cavgym_b200.scenario import AgentSpec, compile_scenario
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f != "geometry_kat.npz")
+GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f != "geometry_kat.npz" and not f.startswith("info_"))
 
 
 def load_golden(name):
@@ -19,6 +19,15 @@ def load_golden(name):
         prefix = f"ep{e}_"
         episodes.append({k[len(prefix):]: data[k] for k in data.files if k.startswith(prefix)})
     return meta, episodes
+
+
+INFO_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("info_") and f.endswith(".npz"))
+
+
+def load_info_golden(name):
+    """(meta, state [T, M, 4], body_polygons [T, M, 8], road_angles [T, M]) recorded from the reference's env.info()."""
+    data = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
+    return json.loads(bytes(data["meta"]).decode()), data["state"], data["body_polygons"], data["road_angles"]
 
 
 def env_config_from(cfg):

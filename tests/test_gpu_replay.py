@@ -326,3 +326,30 @@ def test_sharded_engines_match_one_engine(dtype):
         got = part.stats()
         total = got if total is None else {k: total[k] + got[k] for k in got}
     assert total == want and want["episodes"] > n
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", __import__("helpers").INFO_CASES)
+def test_info_matches_reference(name, dtype):
+    """cavgym_info against env.info() recorded from the unmodified reference (environment.py:106-117): body polygons and road
+    angles within the state tolerance, None (NaN) for exactly the same bodies — one env per recorded step."""
+    from helpers import load_info_golden
+    meta, state, polygons, angles = load_info_golden(name)
+    t_len = state.shape[0]
+    env = make_env(meta, t_len, dtype)
+    env.reset(init_state=np.ascontiguousarray(np.transpose(state, (1, 2, 0))))
+    out = env.info()
+    got_polygons = np.transpose(out["body_polygons"].double().cpu().numpy(), (2, 0, 1))
+    got_angles = out["road_angles"].double().cpu().numpy().T
+    tol = REL[dtype]
+    assert np.max(np.abs(got_polygons - polygons) / np.maximum(1.0, np.abs(polygons))) < tol
+    # a body whose box edge lies within the tolerance of the road edge may be classified either way in fp32
+    defined = np.isfinite(got_angles) & np.isfinite(angles)
+    disagree = np.isfinite(got_angles) != np.isfinite(angles)
+    assert disagree.sum() <= (0 if dtype == "float64" else max(2, angles.size // 200))
+    d = got_angles[defined] - angles[defined]
+    assert np.max(np.abs(np.arctan2(np.sin(d), np.cos(d)))) < (1e-9 if dtype == "float64" else 1e-4)
+    assert defined.sum() > 100
+    # polygons only / angles only
+    only = env.info(road_angles=False)
+    assert only["road_angles"] is None and only["body_polygons"].shape == (meta["n_bodies"], 8, t_len)

@@ -57,3 +57,30 @@ def test_batched_simulation_matches_oracle_counters():
         for key in ("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2", "env_steps"):
             assert got[key] == want[key], key
     assert "interesting test(s)" in summary.console_message()
+
+
+def test_compat_view_info_matches_reference():
+    """env.info() of the single-environment compat view (one cavgym_info launch) against the reference's own info()
+    along the recorded run: polygons as ConvexQuadrilateral objects, road angles as float / None."""
+    from helpers import load_info_golden
+    from cavgym_b200.config import make_config
+    meta, state, polygons, angles = load_info_golden("info_pedestrians2_rc_seed12")
+    config = make_config(copy.deepcopy(meta["config"]))
+    _, env, agents, _ = config.setup()
+    observation = env.reset()
+    info = env.info()
+    for agent in agents:
+        agent.reset()
+    for t in range(60):
+        assert state_err(np.array(observation), state[t]) < 1e-9
+        got = np.array([[x for x, _ in polygon] + [y for _, y in polygon] for polygon in info["body_polygons"]])
+        assert np.max(np.abs(got - polygons[t])) < 1e-8
+        for mine, theirs in zip(info["road_angles"], angles[t]):
+            assert (mine is None) == bool(np.isnan(theirs))
+            if mine is not None:
+                assert abs(mine - theirs) < 1e-9
+        joint_action = [agent.choose_action(observation, space, info) for agent, space in zip(agents, env.action_space)]
+        previous = observation
+        observation, reward, done, info = env.step(joint_action)
+        for agent, action, r in zip(agents, joint_action, reward):
+            agent.process_feedback(previous, action, observation, r)

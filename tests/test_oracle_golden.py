@@ -61,3 +61,19 @@ def test_philox_known_answers():
     assert o.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert o.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+@pytest.mark.parametrize("name", __import__("helpers").INFO_CASES)
+def test_oracle_info_matches_reference(name):
+    """CAVEnv.info() (environment.py:106-117) recorded from the unmodified reference: body polygons bit-equal, road angles
+    bit-equal where defined, None (NaN) for exactly the same bodies."""
+    from helpers import load_info_golden
+    meta, state, polygons, angles = load_info_golden(name)
+    t_len, m = state.shape[0], meta["n_bodies"]
+    oracle = Oracle(compile_from_meta(meta), t_len)           # one env per recorded step
+    oracle.reset(init_state=np.ascontiguousarray(np.transpose(state, (1, 2, 0))))
+    got_polygons, got_angles = oracle.info()
+    assert np.array_equal(np.transpose(got_polygons, (2, 0, 1)), polygons)
+    assert np.array_equal(np.isnan(got_angles.T), np.isnan(angles))
+    assert np.array_equal(got_angles.T, angles, equal_nan=True)
+    assert np.isfinite(angles).any() and np.isnan(angles).any()
