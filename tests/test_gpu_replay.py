@@ -353,3 +353,49 @@ def test_info_matches_reference(name, dtype):
     # polygons only / angles only
     only = env.info(road_angles=False)
     assert only["road_angles"] is None and only["body_polygons"].shape == (meta["n_bodies"], 8, t_len)
+
+
+@pytest.mark.parametrize("name", ["pedestrians_rc_seed0", "pedestrians_rc_eps05_seed1", "pedestrians3_rc_seed2", "pedestrians_proximity_seed3",
+                                  "pedestrians_random_all_seed4", "pelican_random_all_seed10", "crossroads_random_all_seed6"])
+def test_device_agents_follow_reference_with_replayed_draws(name):
+    """The ON-DEVICE agents (crossing state machine, steering inverse, RandomAgent; agents.cuh) fed with the MT19937 draws the
+    reference consumed (cavgym_set_uniform_override): the actions they choose, the agents' internal state, the body state and
+    the events must follow the reference's own run — one env per recorded episode, no replayed actions anywhere."""
+    import torch
+    meta, episodes = load_golden(name)
+    n, m = len(episodes), meta["n_bodies"]
+    t_max = max(ep["actions"].shape[0] for ep in episodes)
+    env = make_env(meta, n, "float64", mode="device")
+    env.set_action_logging(True)
+    env.reset(init_state=soa(np.stack([ep["init_state"] for ep in episodes])))
+    starts = {int(ep["t_global_start"]) for ep in episodes}
+    env.set_global_timestep(starts.pop() if len(starts) == 1 else -10 ** 9)
+    draws = np.full((t_max, m, 3, n), 0.5)
+    for e, ep in enumerate(episodes):
+        draws[:ep["draws"].shape[0], :, :, e] = np.nan_to_num(ep["draws"], nan=0.5)
+    override = torch.zeros((m, 3, n), dtype=torch.float64, device=env.device)
+    env.set_uniform_override(override)
+    draws_t = torch.tensor(draws, device=env.device)
+    flagged = 0
+    for t in range(t_max):
+        override.copy_(draws_t[t])
+        state, reward, done, winner, tangent = env.step(None)
+        state_h, taken, agent_h = state.cpu().numpy(), env.actions_taken.cpu().numpy(), env.agent_state.cpu().numpy()
+        done_h, winner_h, tangent_h = done.cpu().numpy(), winner.cpu().numpy(), tangent.cpu().numpy()
+        for e, ep in enumerate(episodes):
+            if t >= ep["actions"].shape[0]:
+                continue
+            flagged += int(tangent_h[e])
+            assert rel_err(taken[:, :, e], ep["actions"][t]) < 1e-9, (name, e, t)
+            assert state_err(state_h[:, :, e], ep["state"][t]) < 1e-9, (name, e, t)
+            if not tangent_h[e]:
+                assert bool(done_h[e]) == bool(ep["done"][t]) and int(winner_h[e]) == int(ep["winner"][t]), (name, e, t)
+            want = ep["agent_state"][t]
+            crossing = ~np.isnan(want).all(axis=1)
+            got = agent_h[:, :, e]
+            assert np.array_equal(np.isnan(got[crossing]), np.isnan(want[crossing])), (name, e, t)
+            g, w = np.nan_to_num(got[crossing]), np.nan_to_num(want[crossing])
+            assert rel_err(g[:, :3], w[:, :3]) < 1e-9, (name, e, t)          # initial distance, waypoint x, y
+            d = g[:, 3:] - w[:, 3:]                                            # target / prior orientation: angles, +pi == -pi
+            assert np.max(np.abs(np.arctan2(np.sin(d), np.cos(d))), initial=0.0) < 1e-9, (name, e, t)
+    assert flagged < 0.02 * sum(ep["actions"].shape[0] for ep in episodes)
