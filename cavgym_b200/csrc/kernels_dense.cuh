@@ -11,16 +11,21 @@
 // any near-tangent decision, lowest-index pedestrian in the reaction zone (environment.py:198-200), action validity —
 // are warp votes (__any_sync / __all_sync / __reduce_min_sync).  There is no block-wide barrier after the prologue.
 //
-// Shared memory (per env = per warp): the stepped bodies in centre-extent form, x, y, cos, sin, theta in the engine's
-// type R (what the exact separating-axis test and the road share read) and a float4 {x, y, ex, ey} per body for the
-// BROAD PHASE: the axis-aligned extent test of every pair runs in fp32 on outward-rounded extents (a strict superset of
-// the pairs the R-precision test passes — see `broad_entry`), one broadcast LDS.128 + 8 fp32 instructions per 32 pairs.
-// Survivors (a few per env-step) take exactly the test sequence of the thread-per-env path (transition.cuh): R-precision
-// AABB gap, then the four-axis margin, so results — including near-tangent flags — are bitwise those of the small-M
-// kernels on the same scenario (tests/test_gpu_dense.py).  Per-body metadata (type, class flags, agent kind) is staged
-// once per CTA and shared by its envs.
+// Shared memory (per env = per warp), resident for the whole launch: x, y, v, theta, cos, sin of every body in the
+// engine's type R — staged once (dense_stage_env), stepped in place for every fused step, written back once
+// (dense_writeback_env) — plus one float4 per body for the BROAD PHASE of the all-pairs test: the body's axis-aligned
+// bounds {x lo, x hi, y lo, y hi} in fp32, rounded outward (broad_entry), so that a pair test is four fp32 compares and no
+// arithmetic (broad_overlap) and passes a strict superset of the pairs the R-precision test passes.  Two levels: the union
+// box of every 32-body tile (four REDUX each) lets whole tiles be skipped; inside, a lane meets the bodies below its own
+// through broadcast LDS.128 reads, and the pairs within a tile by rotation.  Survivors (a few per env-step) take exactly
+// the test sequence of the thread-per-env path (transition.cuh): R-precision AABB gap, then the four-axis margin, so
+// results — including near-tangent flags — are bitwise those of the small-M kernels on the same scenario
+// (tests/test_gpu_dense.py).  Per-body metadata (type, class flags, agent kind) is staged once per CTA and shared by its
+// envs; which crossing agents are mid-crossing is a bit per body in a register (DenseEnv::busy).
 //
-// Bound: ALU (fp32 pair tests), not HBM: an env-step moves 88 B per body but tests M(M-1)/2 pairs.  DESIGN.md §4.4.
+// Bound: instruction fetch and fixed-latency dependencies at 8 warps per SM, not HBM and not a pipe: an env-step moves
+// 88 B per body but runs ~11 k warp-instructions of branchy fp64 code.  Rare paths are therefore
+// out of line (body_turn_outlined, dense_road_share_edge, dense_random_sample, dense_*_candidates, dense_pair).
 #pragma once
 #include "transition.cuh"
 
