@@ -272,7 +272,7 @@ def run_ours(args):
             out["hbm_config"] = hbm_config(torch, device, dtype, peak_gbs)
         if not args.skip_configs:   # the other BASELINE configs on this one GPU: reported beside the headline, not as it
             out["scenario_configs"] = scenario_configs(torch, device, dtype)
-            out["dense_config"] = dense_config(torch, device, dtype)
+            out["dense_config"] = dense_config(torch, device, dtype, skip_cpu=args.skip_cpu)
             out["sweep_config"] = sweep_config(torch, device, dtype)
         if not args.skip_cpu:
             out["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_seconds)
@@ -352,7 +352,7 @@ def scenario_configs(torch, device, dtype, n=131072, steps=1000, chunk=100):
                         f"cavgym_rollout {chunk} steps/launch, {steps} steps", "scenarios": out}
 
 
-def dense_config(torch, device, dtype, n=100000, steps=40, chunk=10):
+def dense_config(torch, device, dtype, n=100000, steps=40, chunk=10, skip_cpu=False):
     """BASELINE config C4: 64 cars + 256 spawned pedestrians per env (51,040 box pairs per env-step), 100,000 envs,
     terminate_collisions = all; warp-per-env kernels (kernels_dense.cuh), on-device agents, auto-reset."""
     from types import SimpleNamespace
@@ -379,12 +379,25 @@ def dense_config(torch, device, dtype, n=100000, steps=40, chunk=10):
     env.close()
     rate = live / (ms * 1e-3)
     real = 8 if dtype == "float64" else 4
+    cpu = None
+    if not skip_cpu:   # the oracle port on the same scenario, all host threads, a bounded sample (cpu_baseline leg)
+        from oracle.oracle import Oracle
+        threads = os.cpu_count() or 1
+        sim = Oracle(compile_scenario(bodies, constants, cfg, specs), 4 * threads, seed=1, threads=threads)
+        sim.reset()
+        sim.rollout(5, auto_reset=True)
+        t0 = time.perf_counter()
+        sim.rollout(40, auto_reset=True)
+        cpu = {"env_steps_per_sec": 4 * threads * 40 / (time.perf_counter() - t0), "cores": threads, "kind": "port",
+               "sample": f"{4 * threads} envs x 40 steps, oracle/cavgym_oracle.c"}
+        sim.close()
     return {"workload": f"C4: 64 cars + 256 spawned pedestrians x {n} envs, terminate_collisions=all, on-device agents "
                         f"(noop cars, random-constrained pedestrians eps=2e-4), auto-reset, {chunk} steps/launch",
             "kernel": f"dense_kernel<{'double' if dtype == 'float64' else 'float'},true>", "envs": n, "bodies": m,
             "env_steps_per_sec": rate, "body_steps_per_sec": rate * m, "pair_tests_per_sec": rate * (m * (m - 1) // 2),
             "ms_per_batch_step": ms / steps, "episodes": after["episodes"] - before["episodes"], "tangent": after["tangent"] - before["tangent"],
-            "algorithmic_gbs": rate * m * 11 * real / 1e9, "bound": "latency / ALU (see DESIGN.md 4.4), not HBM"}
+            "algorithmic_gbs": rate * m * 11 * real / 1e9, "bound": "instruction fetch / latency (DESIGN.md 4.4, 4.5), not HBM",
+            "cpu_baseline": cpu}
 
 
 def sweep_config(torch, device, dtype, n=1048576, steps=1000, chunk=100):

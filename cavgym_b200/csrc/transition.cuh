@@ -149,6 +149,9 @@ struct NoSink {
 #ifndef CAV_ROLL_AGENTS
 #define CAV_ROLL_AGENTS 0
 #endif
+#ifndef CAV_ROLLED_HOMOGENEOUS_FROM_M   // homogeneous (Pedestrians-v0 family) kernels: rolled from this many bodies on
+#define CAV_ROLLED_HOMOGENEOUS_FROM_M 99
+#endif
 
 #define CAV_BODY_LOOP _Pragma("unroll")
 template <typename R, int M, bool AGENTS, bool GENERIC, typename Sink = NoSink>
@@ -172,7 +175,8 @@ template <typename R, int M, bool AGENTS, bool GENERIC, typename Sink = NoSink>
 __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, int64_t t_global,
                                            EnvRegs<R, M>& env, const R (&ext)[M][2], StepResult<R, M>& out,
                                            Sink moved = Sink()) {
-  if constexpr ((GENERIC && M >= CAV_ROLLED_FROM_M) || (AGENTS && CAV_ROLL_AGENTS != 0 && M >= 2)) transition_rolled<R, M, AGENTS, GENERIC, Sink>(sc, buf, e, t_global, env, ext, out, moved);
+  if constexpr ((GENERIC && M >= CAV_ROLLED_FROM_M) || (!GENERIC && M >= CAV_ROLLED_HOMOGENEOUS_FROM_M) ||
+                (AGENTS && CAV_ROLL_AGENTS != 0 && M >= 2)) transition_rolled<R, M, AGENTS, GENERIC, Sink>(sc, buf, e, t_global, env, ext, out, moved);
   else transition_unrolled<R, M, AGENTS, GENERIC, Sink>(sc, buf, e, t_global, env, ext, out, moved);
 }
 

@@ -10,10 +10,12 @@ GOLDEN = {"pedestrians": "pedestrians_rc_seed0", "crossroads": "crossroads_rando
           "pelican-crossing": "pelican_random_all_seed10"}
 ap = argparse.ArgumentParser()
 ap.add_argument("--scenario", default="bus-stop"); ap.add_argument("--envs", type=int, default=131072)
-ap.add_argument("--chunk", type=int, default=100); ap.add_argument("--launches", type=int, default=4); ap.add_argument("--dtype", default="float64")
+ap.add_argument("--chunk", type=int, default=100); ap.add_argument("--launches", type=int, default=4); ap.add_argument("--dtype", default="float64"); ap.add_argument("--pedestrians", type=int, default=0)
 args = ap.parse_args()
 meta, _ = load_golden(GOLDEN[args.scenario])
 meta["config"]["tester_config"]["epsilon"] = 0.01
+if args.pedestrians:
+    meta["config"]["scenario_config"]["num_pedestrians"] = args.pedestrians
 env = BatchedCAVEnv(None, None, None, num_envs=args.envs, dtype=args.dtype, compiled=compile_from_meta(meta, mode="device"), device="cuda:0", seed=0)
 env.reset()
 times = []

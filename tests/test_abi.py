@@ -40,3 +40,5 @@ def test_bad_arguments_return_codes_without_a_gpu():
     assert b"NULL" in lib.cavgym_last_error()
     assert lib.cavgym_destroy(None) == 0
     assert lib.cavgym_set_global_timestep(None, 0) == -22
+    assert lib.cavgym_info(None, None, None, None) == -22 and lib.cavgym_step(None, None, None, None, None, None, None, None) == -22
+    assert lib.cavgym_set_dense_path(None, 1) == -22 and lib.cavgym_rollout(None, 1, 1, None) == -22
