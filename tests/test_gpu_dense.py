@@ -301,3 +301,30 @@ def test_more_than_maximum_bodies_is_rejected():
     from cavgym_b200 import _native
     with pytest.raises((ValueError, _native.CavgymError)):
         make(dense_scenario("external", num_cars=130, num_pedestrians=384), 2, "float64")
+
+
+def test_dense_step_host_equals_device_step():
+    """cavgym_step_host on a 320-body scenario: pinned buffers (zero copy), pageable buffers (staged copies) and the device
+    step give identical bits."""
+    import torch
+    n, steps = 6, 25
+    comp = dense_scenario("external")
+    m = comp.n_bodies
+    actions = torch.tensor(random_actions(np.random.RandomState(2), steps, n, comp.is_car))
+    envs = [make(dense_scenario("external"), n, "float64", seed=4) for _ in range(3)]
+    def buffers(pin):
+        shapes = {"actions": ((m, 2, n), torch.float64), "state": ((m, 4, n), torch.float64), "reward": ((m, n), torch.float64),
+                  "done": ((n,), torch.uint8), "winner": ((n,), torch.int32), "tangent": ((n,), torch.uint8)}
+        return {k: (torch.empty(s, dtype=d).pin_memory() if pin else torch.empty(s, dtype=d)) for k, (s, d) in shapes.items()}
+    host = [buffers(True), buffers(False)]
+    for env in envs:
+        env.reset()
+    for t in range(steps):
+        for env, h in zip(envs[:2], host):
+            h["actions"].copy_(actions[t])
+            env.step_host(h["actions"], h["state"], h["reward"], h["done"], h["winner"], h["tangent"])
+        out = envs[2].step(actions[t].to(envs[2].device))
+        for key, dev in zip(("state", "reward", "done", "winner", "tangent"), out):
+            assert torch.equal(host[0][key], dev.cpu()), (t, key)
+            assert torch.equal(host[1][key], dev.cpu()), (t, key)
+    assert envs[0].stats() == envs[1].stats() == envs[2].stats()
