@@ -23,6 +23,15 @@ constexpr int kThreads = 128;
 #define CAV_LOOP_THREADS 224
 #endif
 constexpr int kLoopThreads = CAV_LOOP_THREADS;
+// The rollout kernel (on-device agents, auto-reset) usually runs over many more envs than one wave: 128-thread blocks,
+// four per SM (pedestrians rollout at 1M envs: 7.2 -> 6.8 ms per 100 steps against 224 x 2).
+#ifndef CAV_ROLLOUT_THREADS
+#define CAV_ROLLOUT_THREADS 128
+#endif
+#ifndef CAV_MIN_BLOCKS_ROLLOUT
+#define CAV_MIN_BLOCKS_ROLLOUT 4
+#endif
+constexpr int kRolloutThreads = CAV_ROLLOUT_THREADS;
 #ifndef CAV_MIN_BLOCKS_STEP
 #define CAV_MIN_BLOCKS_STEP 4
 #endif
@@ -195,10 +204,10 @@ __global__ void __launch_bounds__(kLoopThreads, CAV_MIN_BLOCKS_LOOP) replay_kern
 }
 
 template <typename R, int M, bool GENERIC>
-__global__ void __launch_bounds__(kLoopThreads, CAV_MIN_BLOCKS_LOOP) rollout_kernel(const __grid_constant__ DevScenario<R> sc,
+__global__ void __launch_bounds__(kRolloutThreads, CAV_MIN_BLOCKS_ROLLOUT) rollout_kernel(const __grid_constant__ DevScenario<R> sc,
                                                            const __grid_constant__ EnvBuffers<R> buf, int64_t t_global,
                                                            int n_steps, int auto_reset) {
-  const int64_t e = buf.lo + (int64_t)blockIdx.x * kLoopThreads + threadIdx.x;
+  const int64_t e = buf.lo + (int64_t)blockIdx.x * kRolloutThreads + threadIdx.x;
   if (e < buf.hi) {
     EnvRegs<R, M> env;
     load_env<R, M, true>(sc, buf, e, env);
@@ -276,8 +285,8 @@ void launch_replay(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const Ste
 template <typename R, int M>
 void launch_rollout(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t t_global, int n_steps, int auto_reset,
                     cudaStream_t stream) {
-  if (sc.homogeneous) rollout_kernel<R, M, false><<<grid_for(buf, kLoopThreads), kLoopThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
-  else rollout_kernel<R, M, true><<<grid_for(buf, kLoopThreads), kLoopThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
+  if (sc.homogeneous) rollout_kernel<R, M, false><<<grid_for(buf, kRolloutThreads), kRolloutThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
+  else rollout_kernel<R, M, true><<<grid_for(buf, kRolloutThreads), kRolloutThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
 }
 template <typename R, int M>
 void launch_reset(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const uint8_t* mask, const R* init, int first_time,
