@@ -48,6 +48,7 @@ namespace cav {
 #define CAV_TMA_STAGES 3
 #endif
 constexpr int kTmaStages = CAV_TMA_STAGES;
+constexpr int kMaxSmemPerBlock = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
 constexpr int kStepWarps = CAV_TMA_STEP_WARPS, kStepTile = 32 * kStepWarps;
 constexpr int kReplayWarps = CAV_TMA_REPLAY_WARPS, kReplayTile = 32 * kReplayWarps;
 
@@ -501,6 +502,7 @@ bool launch_step_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const S
                      int64_t* envs_done) {
   using L = StepLayout<R, M>;
   *envs_done = 0;
+  if (L::kSmemBytes > kMaxSmemPerBlock) return true;   // the staging buffers of this body count do not fit: plain kernel
   const int64_t span = tma_span(buf, io, kStepTile, false);
   if (span == 0) return true;
   const int64_t tiles = (span + kStepTile - 1) / kStepTile;
@@ -508,11 +510,13 @@ bool launch_step_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const S
   static int sms = 0;
   auto kernel = sc.homogeneous ? step_tma_kernel<R, M, false> : step_tma_kernel<R, M, true>;
   int& res = resident[sc.homogeneous ? 0 : 1];
+  if (res < 0) return true;   // found unusable before (shared memory): plain kernel
   if (res == 0) {
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes) != cudaSuccess) return false;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, kernel, kStepTile + 32, L::kSmemBytes) != cudaSuccess || res < 1) {
-      res = 0;
-      return false;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, kernel, kStepTile + 32, L::kSmemBytes) != cudaSuccess || res < 1) {
+      cudaGetLastError();     // not an error of the caller's: this body count's staging does not fit, the plain kernel runs
+      res = -1;
+      return true;
     }
     int dev = 0;
     cudaGetDevice(&dev);
@@ -531,14 +535,22 @@ bool launch_replay_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const
                        cudaStream_t stream, int64_t* envs_done) {
   using L = ReplayLayout<R, M>;
   *envs_done = 0;
+  if (L::kSmemBytes > kMaxSmemPerBlock) return true;   // (fp64, six or more bodies): plain kernel
   const int64_t span = tma_span(buf, io, kReplayTile, io.done_out != nullptr || io.tangent_out != nullptr);
   if (span == 0) return true;
-  static bool ready[2] = {false, false};
+  static int ready[2] = {0, 0};   // 0 unknown, 1 usable, -1 does not fit shared memory
   auto kernel = sc.homogeneous ? replay_tma_kernel<R, M, false> : replay_tma_kernel<R, M, true>;
-  bool& ok = ready[sc.homogeneous ? 0 : 1];
-  if (!ok) {
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes) != cudaSuccess) return false;
-    ok = true;
+  int& ok = ready[sc.homogeneous ? 0 : 1];
+  if (ok < 0) return true;
+  if (ok == 0) {
+    int blocks = 0;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kReplayTile + 32, L::kSmemBytes) != cudaSuccess || blocks < 1) {
+      cudaGetLastError();
+      ok = -1;
+      return true;          // plain replay kernel for this body count
+    }
+    ok = 1;
   }
   EnvBuffers<R> range = buf;
   range.hi = buf.lo + span;

@@ -152,6 +152,9 @@ struct NoSink {
 // Homogeneous (Pedestrians-v0 family) kernels WITH on-device agents are rolled from this many bodies on (rollout at M = 4:
 // 14.2 -> 8.8 ms per 100 steps of 262,144 envs, at M = 8: 78 -> 26 ms); on replayed actions they stay unrolled (the fused
 // replay kernel keeps the state in registers across steps: 0.85 ms unrolled vs 1.42 ms rolled at M = 4).
+#ifndef CAV_ROLLED_HOMOGENEOUS_REPLAY_FROM_M   // the same family on replayed actions (measured below)
+#define CAV_ROLLED_HOMOGENEOUS_REPLAY_FROM_M 99
+#endif
 #ifndef CAV_ROLLED_HOMOGENEOUS_FROM_M
 #define CAV_ROLLED_HOMOGENEOUS_FROM_M 4
 #endif
@@ -179,6 +182,7 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
                                            EnvRegs<R, M>& env, const R (&ext)[M][2], StepResult<R, M>& out,
                                            Sink moved = Sink()) {
   if constexpr ((GENERIC && M >= CAV_ROLLED_FROM_M) || (!GENERIC && AGENTS && M >= CAV_ROLLED_HOMOGENEOUS_FROM_M) ||
+                (!GENERIC && !AGENTS && M >= CAV_ROLLED_HOMOGENEOUS_REPLAY_FROM_M) ||
                 (AGENTS && CAV_ROLL_AGENTS != 0 && M >= 2)) transition_rolled<R, M, AGENTS, GENERIC, Sink>(sc, buf, e, t_global, env, ext, out, moved);
   else transition_unrolled<R, M, AGENTS, GENERIC, Sink>(sc, buf, e, t_global, env, ext, out, moved);
 }

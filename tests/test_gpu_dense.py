@@ -328,3 +328,45 @@ def test_dense_step_host_equals_device_step():
             assert torch.equal(host[0][key], dev.cpu()), (t, key)
             assert torch.equal(host[1][key], dev.cpu()), (t, key)
     assert envs[0].stats() == envs[1].stats() == envs[2].stats()
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("pedestrians", [5, 7])
+def test_six_and_eight_body_scenarios_replay_and_step(pedestrians, dtype):
+    """Pedestrians-v0 with 5 / 7 pedestrians (M = 6 / 8, the largest thread-per-env body counts; the TMA staging of the fp64
+    replay kernel no longer fits shared memory there and the plain kernel takes over): a joint-action trace logged from the
+    on-device agents, replayed through cavgym_replay and cavgym_step on both paths — bitwise equal — and against the oracle."""
+    import torch
+    from oracle.oracle import Oracle
+    meta, _ = load_golden("pedestrians_rc_eps05_seed1")
+    meta["config"]["scenario_config"]["num_pedestrians"] = pedestrians
+    n, steps = 576, 120          # whole 16-env groups: the TMA kernels are eligible wherever their staging fits
+    gen = make(compile_from_meta(meta, mode="device"), n, "float64", seed=6)
+    gen.set_action_logging(True)
+    gen.reset()
+    init = gen.state.cpu().numpy().copy()
+    actions = np.empty((steps, pedestrians + 1, 2, n))
+    for t in range(steps):
+        gen.step(None)
+        actions[t] = gen.actions_taken.cpu().numpy()
+    outs = []
+    for dense in (False, True):
+        env = make(compile_from_meta(meta), n, dtype)
+        env.set_dense_path(dense)
+        env.reset(init_state=init)
+        fused = numpy_traj(env.replay(actions[:steps // 2]))
+        act_t = torch.tensor(actions[steps // 2:], dtype=env.dtype, device=env.device)
+        last = None
+        for t in range(act_t.shape[0]):
+            last = [v.cpu().numpy().copy() for v in env.step(act_t[t])]
+        outs.append((fused, last, env.stats()))
+    for key in ("state", "reward", "done", "winner", "tangent"):
+        assert np.array_equal(outs[0][0][key], outs[1][0][key], equal_nan=True), key
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert outs[0][2] == outs[1][2]
+    if dtype == "float64":
+        oracle = Oracle(compile_from_meta(meta), n, threads=8)
+        oracle.reset(init_state=init)
+        want = oracle.replay(actions[:steps // 2])
+        check_against_oracle({k: v for k, v in outs[0][0].items()}, want, dtype)
