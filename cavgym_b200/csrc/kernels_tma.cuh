@@ -49,6 +49,13 @@ namespace cav {
 #endif
 constexpr int kTmaStages = CAV_TMA_STAGES;
 constexpr int kMaxSmemPerBlock = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
+// The TMA-staged kernels pay off while three CTAs (step) / two 256-thread CTAs (replay) fit an SM, i.e. for one or two
+// bodies.  From three bodies on the staging buffers crowd the SM and the plain kernels are faster — measured at 1M envs,
+// fp64, step: M=3 0.135 vs 0.111 ms, M=4 0.353 vs 0.170, M=5 0.616 vs 0.243, bus stop 0.97 vs 0.47; replay of 50 steps at
+// 65,536 envs: bus stop 2.76 vs 1.74 ms (scripts/profile_replay.py) — so the launchers hand those scenarios to them.
+#ifndef CAV_TMA_MAX_BODIES
+#define CAV_TMA_MAX_BODIES 2
+#endif
 constexpr int kStepWarps = CAV_TMA_STEP_WARPS, kStepTile = 32 * kStepWarps;
 constexpr int kReplayWarps = CAV_TMA_REPLAY_WARPS, kReplayTile = 32 * kReplayWarps;
 
@@ -502,7 +509,9 @@ bool launch_step_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const S
                      int64_t* envs_done) {
   using L = StepLayout<R, M>;
   *envs_done = 0;
-  if (L::kSmemBytes > kMaxSmemPerBlock) return true;   // the staging buffers of this body count do not fit: plain kernel
+  if constexpr (M > CAV_TMA_MAX_BODIES || L::kSmemBytes > kMaxSmemPerBlock) {
+    return true;   // plain kernel (see CAV_TMA_MAX_BODIES); the TMA kernel is not even instantiated for this body count
+  } else {
   const int64_t span = tma_span(buf, io, kStepTile, false);
   if (span == 0) return true;
   const int64_t tiles = (span + kStepTile - 1) / kStepTile;
@@ -528,6 +537,7 @@ bool launch_step_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const S
   kernel<<<(unsigned)grid, kStepTile + 32, L::kSmemBytes, stream>>>(sc, range, io, t_global, tiles);
   *envs_done = span;
   return true;
+  }
 }
 
 template <typename R, int M>
@@ -535,7 +545,9 @@ bool launch_replay_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const
                        cudaStream_t stream, int64_t* envs_done) {
   using L = ReplayLayout<R, M>;
   *envs_done = 0;
-  if (L::kSmemBytes > kMaxSmemPerBlock) return true;   // (fp64, six or more bodies): plain kernel
+  if constexpr (M > CAV_TMA_MAX_BODIES || L::kSmemBytes > kMaxSmemPerBlock) {
+    return true;   // plain kernel (see CAV_TMA_MAX_BODIES)
+  } else {
   const int64_t span = tma_span(buf, io, kReplayTile, io.done_out != nullptr || io.tangent_out != nullptr);
   if (span == 0) return true;
   static int ready[2] = {0, 0};   // 0 unknown, 1 usable, -1 does not fit shared memory
@@ -558,6 +570,7 @@ bool launch_replay_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const
   kernel<<<(unsigned)tiles, kReplayTile + 32, L::kSmemBytes, stream>>>(sc, range, io, t_global, n_steps);
   *envs_done = span;
   return true;
+  }
 }
 
 template <typename R, int M>

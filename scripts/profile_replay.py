@@ -37,4 +37,8 @@ def reset_only():
 ms_replay = timed(replay, 5) - timed(reset_only, 5)
 env.reset(init_state=init)
 ms_step = timed(lambda: env.step(actions[0]), 20)
+env.set_step_path(use_tma=False)
+ms_plain = timed(lambda: env.step(actions[0]), 20)
+ms_replay_plain = timed(replay, 5) - timed(reset_only, 5)
+print(f"plain step {ms_plain:.4f} ms, plain replay {ms_replay_plain:.3f} ms;", end=" ")
 print(f"{args.scenario} bodies {env.num_bodies} envs {args.envs}: replay {args.steps} steps {ms_replay:.3f} ms ({args.envs * args.steps / ms_replay / 1e6:.1f} G env-steps/s... x1e-3), step {ms_step:.4f} ms")

@@ -187,7 +187,7 @@ def test_tma_step_kernel_is_bitwise_equal_to_plain_kernel(name, dtype, n):
     for attr in ("episode_liveness", "timestep", "done_latch", "winner_latch"):
         assert torch.equal(getattr(envs[0], attr), getattr(envs[1], attr)), attr
     assert envs[0].stats() == envs[1].stats()
-    if n % 16:
+    if n % 16 and m <= 2:   # the TMA-staged kernels serve scenarios of one or two bodies (CAV_TMA_MAX_BODIES)
         assert envs[0].launch_count() > envs[1].launch_count()  # two launches per step (tiles + tail) vs one
     else:
         assert envs[0].launch_count() == envs[1].launch_count()
