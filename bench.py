@@ -28,7 +28,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N_ENVS = 65536          # per GPU (weak scaling)
 SEGMENT = 500           # steps replayed from a fresh reset before resetting again (ego finishes at step 901)
-CHUNK = 50              # steps fused per cavgym_replay launch
+CHUNK = 250             # steps fused per cavgym_replay launch (50: 16.0, 100: 17.9, 250: 20.3, 500: 20.8 G env-steps/s)
 HBM_ENVS = 4 * 1024 * 1024
 HBM_ADVANCE = 300        # unrecorded steps before the HBM-config trace: envs are mid-episode, pedestrians mid-crossing
 EPSILON = 0.01
@@ -121,6 +121,8 @@ def make_trace(torch, device, n_envs, n_steps, dtype, env_offset, advance=0):
 
 
 def run_ours(args):
+    global CHUNK
+    CHUNK = max(1, min(int(args.chunk), SEGMENT))
     import torch
     import torch.distributed as dist
     from cavgym_b200 import BatchedCAVEnv
@@ -215,7 +217,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": kernel_name,
                 "achieved": round(achieved, 1), "peak": peak_gbs, "peak_source": peak_src, "unit": "GB/s",
                 "frac": round(achieved / peak_gbs, 4), "traffic": measured_traffic(kernel_name),
-                "traffic_note": "DRAM bytes per 50-step launch (ncu); below the algorithmic figure because the fused kernel keeps "
+                "traffic_note": "DRAM bytes per launch of CHUNK fused steps (ncu); below the algorithmic figure because the fused kernel keeps "
                                 "the state in registers between steps: only actions in and trajectories out touch HBM",
                 "algorithmic_bytes_per_launch": int(bytes_per_launch),
                 "algorithmic_bytes_per_env_step": bytes_env_step, "launches": replay_launches,
@@ -227,9 +229,9 @@ def run_ours(args):
            "vs_baseline": None, "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic",
            "body_steps_per_sec": value * m,
            "config": {"workload": "C2: pedestrians scenario (Car + SpawnPedestrian) x 65,536 envs per GPU, replayed joint "
-                                  "actions (on-device RandomConstrained eps=0.01 trace), cavgym_replay 50 steps/launch, "
+                                  f"actions (on-device RandomConstrained eps=0.01 trace), cavgym_replay {CHUNK} steps/launch, "
                                   "trajectories recorded", "envs_per_gpu": n, "bodies": m, "segment": SEGMENT,
-                      "l2": "trajectory slabs (262 MB) and action trace (1 GB) exceed L2; state is L2/register resident",
+                      "l2": f"trajectory slabs ({CHUNK * 5.24e6 / 1e9:.2f} GB) and action trace (1 GB) exceed L2; state is L2/register resident",
                       "live_fraction": round(live_fraction, 4)},
            "roofline": roofline, "gpu_launches": int(gpu_launches), "clocks": clocks}
 
@@ -519,6 +521,7 @@ def main():
     parser.add_argument("--dtype", default="float64", choices=["float64", "float32"])
     parser.add_argument("--e2e-steps", type=int, default=200)
     parser.add_argument("--cpu-seconds", type=float, default=15.0)
+    parser.add_argument("--chunk", type=int, default=CHUNK, help="steps fused per cavgym_replay launch")
     parser.add_argument("--skip-hbm", action="store_true")
     parser.add_argument("--skip-cpu", action="store_true")
     parser.add_argument("--skip-configs", action="store_true", help="skip the C3 / C4 / C5 side measurements")

@@ -38,16 +38,17 @@ def main():
         env.close()
     if args.mode in ("replay", "all"):
         n = 65536
-        init, actions = bench.make_trace(torch, device, n, 100, args.dtype, 0)
+        steps = bench.CHUNK
+        init, actions = bench.make_trace(torch, device, n, steps, args.dtype, 0)
         env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=args.dtype, compiled=bench.scenario("external"), device=device)
         env.reset(init_state=init)
         times = []
         for t in range(args.launches):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); env.replay(actions[:50]); b.record()
+            a.record(); env.replay(actions[:steps]); b.record()
             times.append((a, b))
         torch.cuda.synchronize()
-        print("replay_kernel (50 steps) ms:", [round(a.elapsed_time(b), 4) for a, b in times])
+        print(f"replay_kernel ({steps} steps) ms:", [round(a.elapsed_time(b), 4) for a, b in times])
         env.close()
     if args.mode in ("rollout", "all"):
         env = BatchedCAVEnv(None, None, None, num_envs=args.envs, dtype=args.dtype, compiled=bench.scenario("device"), device=device)
