@@ -354,7 +354,7 @@ def scenario_configs(torch, device, dtype, n=131072, steps=1000, chunk=100):
                         f"cavgym_rollout {chunk} steps/launch, {steps} steps", "scenarios": out}
 
 
-def dense_config(torch, device, dtype, n=100000, steps=40, chunk=10, skip_cpu=False):
+def dense_config(torch, device, dtype, n=100000, steps=100, chunk=50, skip_cpu=False):
     """BASELINE config C4: 64 cars + 256 spawned pedestrians per env (51,040 box pairs per env-step), 100,000 envs,
     terminate_collisions = all; warp-per-env kernels (kernels_dense.cuh), on-device agents, auto-reset."""
     from types import SimpleNamespace
@@ -371,7 +371,7 @@ def dense_config(torch, device, dtype, n=100000, steps=40, chunk=10, skip_cpu=Fa
     m = len(bodies)
     env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=compile_scenario(bodies, constants, cfg, specs), device=device, seed=1)
     env.reset()
-    for _ in range(6):
+    for _ in range(2):
         env.rollout(chunk, auto_reset=True)
     torch.cuda.synchronize(device)
     before = env.stats()
