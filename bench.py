@@ -28,6 +28,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N_ENVS = 65536          # per GPU (weak scaling)
 SEGMENT = 500           # steps replayed from a fresh reset before resetting again (ego finishes at step 901)
+REGION_REPEATS = 50     # the --steps-long timed region is repeated this many times back to back (all launches pre-enqueued)
 CHUNK = 250             # steps fused per cavgym_replay launch (50: 16.0, 100: 17.9, 250: 20.3, 500: 20.8 G env-steps/s)
 HBM_ENVS = 4 * 1024 * 1024
 HBM_ADVANCE = 300        # unrecorded steps before the HBM-config trace: envs are mid-episode, pedestrians mid-crossing
@@ -44,14 +45,26 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+def measured_traffic(kernel, steps_per_launch=None):
+    """(DRAM bytes per launch, note) of `kernel` from the committed ncu captures (profiles/traffic.json).  Entries are
+    keyed by launch shape; a shape that was not captured is scaled per fused step from the nearest one, and says so."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as fh:
-            return json.load(fh).get(kernel, {}).get("dram_bytes_per_launch")
+            entry = json.load(fh).get(kernel, {})
     except (OSError, ValueError):
-        return None
+        return None, "no ncu capture found"
+    if steps_per_launch is None:
+        return entry.get("dram_bytes_per_launch"), entry.get("launch", "")
+    shapes = {int(k): v for k, v in entry.get("per_steps_per_launch", {}).items()}
+    if not shapes:
+        return None, "no ncu capture found"
+    if steps_per_launch in shapes:
+        return shapes[int(steps_per_launch)], (f"dram__bytes_read.sum + dram__bytes_write.sum of one {int(steps_per_launch)}-step launch "
+                                                f"(ncu --set full, {entry.get('source', 'profiles/')})")
+    nearest = min(shapes, key=lambda k: abs(k - steps_per_launch))
+    return int(shapes[nearest] * steps_per_launch / nearest), (f"scaled per fused step from the ncu capture of a {nearest}-step launch "
+                                                               f"({entry.get('source', 'profiles/')}); this shape was not captured")
 
 
 class ClockSampler(threading.Thread):
@@ -121,8 +134,7 @@ def make_trace(torch, device, n_envs, n_steps, dtype, env_offset, advance=0):
 
 
 def run_ours(args):
-    global CHUNK
-    CHUNK = max(1, min(int(args.chunk), SEGMENT))
+    chunk = max(1, min(int(args.chunk), SEGMENT, args.steps))   # steps fused per cavgym_replay launch
     import torch
     import torch.distributed as dist
     from cavgym_b200 import BatchedCAVEnv
@@ -140,11 +152,15 @@ def run_ours(args):
     init, actions = make_trace(torch, device, n, SEGMENT, dtype, env_offset=sharding.shard_offset(rank, n))
     env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=scenario("external"), device=device,
                         env_offset=sharding.shard_offset(rank, n))
-    slab = {"state": torch.empty((CHUNK, m, 4, n), dtype=env.dtype, device=device),
-            "reward": torch.empty((CHUNK, m, n), dtype=env.dtype, device=device),
-            "done": torch.empty((CHUNK, n), dtype=torch.uint8, device=device),
-            "winner": torch.empty((CHUNK, n), dtype=torch.int32, device=device),
-            "tangent": torch.empty((CHUNK, n), dtype=torch.uint8, device=device)}
+    # Trajectory slabs: 5.24 MB per step.  Launches rotate over `slots` slabs so that >= 315 MB (2.5 x the 126 MB L2) are
+    # written before a slab is written again: the trajectory stores of the timed region reach HBM, not a warm L2 line.
+    slots = max(1, -(-60 // chunk))
+    slab_steps = slots * chunk
+    slab = {"state": torch.empty((slab_steps, m, 4, n), dtype=env.dtype, device=device),
+            "reward": torch.empty((slab_steps, m, n), dtype=env.dtype, device=device),
+            "done": torch.empty((slab_steps, n), dtype=torch.uint8, device=device),
+            "winner": torch.empty((slab_steps, n), dtype=torch.int32, device=device),
+            "tangent": torch.empty((slab_steps, n), dtype=torch.uint8, device=device)}
     lib, handle, stream = env._lib, env._handle, env._stream()
     from cavgym_b200._native import check
     import ctypes as C
@@ -152,7 +168,7 @@ def run_ours(args):
     def ptr(t):
         return C.c_void_p(t.data_ptr())
 
-    kernel_events = []
+    launch_events, region_events, launch_no = [], [], [0]
 
     def advance(n_steps, cursor, timed):
         """Replay n_steps starting at trace position `cursor` (resetting every SEGMENT steps); returns new cursor."""
@@ -160,15 +176,17 @@ def run_ours(args):
         while done < n_steps:
             if cursor == 0:
                 env.reset(init_state=init)
-            take = min(CHUNK, n_steps - done, SEGMENT - cursor)
+            take = min(chunk, n_steps - done, SEGMENT - cursor)
             if timed:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-            check(lib.cavgym_replay(handle, take, ptr(actions[cursor]), ptr(slab["state"]), ptr(slab["reward"]),
-                                    ptr(slab["done"]), ptr(slab["winner"]), ptr(slab["tangent"]), stream))
+            at = (launch_no[0] % slots) * chunk
+            launch_no[0] += 1
+            check(lib.cavgym_replay(handle, take, ptr(actions[cursor]), ptr(slab["state"][at]), ptr(slab["reward"][at]),
+                                    ptr(slab["done"][at]), ptr(slab["winner"][at]), ptr(slab["tangent"][at]), stream))
             if timed:
                 b.record()
-                kernel_events.append((a, b, take))
+                launch_events.append((a, b, take))
             done += take
             cursor = (cursor + take) % SEGMENT
         return cursor
@@ -180,58 +198,77 @@ def run_ours(args):
         torch.cuda.synchronize(device)
 
     # ---- device-resident throughput (value) -------------------------------------------------
-    cursor = advance(args.warmup, 0, False)
+    # The timed region is `--steps` steps (resets included), repeated REGION_REPEATS times back to back.  Every launch of
+    # every repetition is enqueued while a gate kernel keeps the stream busy, so no host launch latency sits between
+    # the events: they time the GPU, not the Python loop (at --steps 20 one region is a single ~70 us launch).
+    advance(args.warmup, 0, False)
+    cursor = 0   # the first timed region starts from a fresh reset: regions tile the SEGMENT-step trace whenever --steps divides it
     barrier()
     before, launches_before = env.stats(), env.launch_count()
     sampler = ClockSampler(local)
     sampler.start()
     sampler.ready.wait(timeout=10)    # NVML initialised before the timed region starts
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    repeats = max(1, args.repeats)
+    launches_per_region = -(-args.steps // chunk) + args.steps // SEGMENT + 2
     barrier()
     if args.profile_region:      # ncu --profile-from-start off: capture exactly the timed region
         torch.cuda.profiler.start()
-    start.record()
-    cursor = advance(args.steps, cursor, True)
-    stop.record()
+    else:                        # (under ncu every launch is serialised anyway, and the gate would be profiled)
+        torch.cuda._sleep(int((4e-3 + 4e-5 * repeats * launches_per_region) * 1.9e9))
+    for _ in range(repeats):   # a region starts at its first launch's start event and ends at its last launch's stop event
+        first = len(launch_events)
+        cursor = advance(args.steps, cursor, True)
+        region_events.append((launch_events[first][0], launch_events[-1][1]))
+    queued_ahead = not region_events[0][0].query()   # the GPU had not reached the first event when the host finished enqueuing
     barrier()
     if args.profile_region:
         torch.cuda.profiler.stop()
     clocks = sampler.stop()
-    elapsed_ms = start.elapsed_time(stop)
+    elapsed_ms = region_events[0][0].elapsed_time(region_events[-1][1])
+    region_ms = sorted(a.elapsed_time(b) for a, b in region_events)
     after, launches_after = env.stats(), env.launch_count()
     live_env_steps = after["env_steps"] - before["env_steps"]
     # stats() itself launches one reduction kernel per call: not part of the timed region
     gpu_launches = launches_after - launches_before - 1
-    kernel_ms = sum(a.elapsed_time(b) for a, b, _ in kernel_events)
-    kernel_steps = sum(k for _, _, k in kernel_events)
-    replay_launches = len(kernel_events)
+    kernel_ms = sum(a.elapsed_time(b) for a, b, _ in launch_events)
+    kernel_steps = sum(k for _, _, k in launch_events)
+    replay_launches = len(launch_events)
+    steps_per_launch = kernel_steps / replay_launches
 
     elapsed_ms, total_env_steps = sharding.reduce_timing(elapsed_ms, live_env_steps, device)   # MAX time, SUM units
     value = total_env_steps / (elapsed_ms * 1e-3)
 
-    # roofline of the dominant kernel (replay_kernel): algorithmic bytes per launch / mean launch duration
-    live_fraction = live_env_steps / float(n * args.steps)
-    bytes_per_launch = bytes_env_step * n * (kernel_steps / replay_launches) * live_fraction
+    # roofline of the dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events around each launch)
+    live_fraction = live_env_steps / float(n * args.steps * repeats)
+    bytes_per_launch = bytes_env_step * n * steps_per_launch * live_fraction
     achieved = bytes_per_launch / (kernel_ms / replay_launches * 1e-3) / 1e9
     kernel_name = f"replay_tma_kernel<{'double' if dtype == 'float64' else 'float'},2,false>"
+    traffic, traffic_note = measured_traffic(kernel_name, steps_per_launch)
     roofline = {"bound": "hbm", "kernel": kernel_name,
                 "achieved": round(achieved, 1), "peak": peak_gbs, "peak_source": peak_src, "unit": "GB/s",
-                "frac": round(achieved / peak_gbs, 4), "traffic": measured_traffic(kernel_name),
-                "traffic_note": "DRAM bytes per launch of CHUNK fused steps (ncu); below the algorithmic figure because the fused kernel keeps "
-                                "the state in registers between steps: only actions in and trajectories out touch HBM",
+                "frac": round(achieved / peak_gbs, 4), "traffic": traffic, "traffic_note": traffic_note,
                 "algorithmic_bytes_per_launch": int(bytes_per_launch),
                 "algorithmic_bytes_per_env_step": bytes_env_step, "launches": replay_launches,
-                "avg_launch_ms": round(kernel_ms / replay_launches, 4),
-                "note": "65,536 envs: state (4 MiB) stays in L2/registers, only actions and trajectories stream"}
+                "steps_per_launch": steps_per_launch, "avg_launch_ms": round(kernel_ms / replay_launches, 5),
+                "note": "65,536 envs: the state (4 MiB) stays in registers for the whole launch; actions stream in and "
+                        "trajectories stream out through HBM (slabs larger than L2)"}
 
+    median_region = region_ms[len(region_ms) // 2]
     out = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": elapsed_ms / (args.steps * repeats), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic",
            "body_steps_per_sec": value * m,
+           "timed_region": {"steps": args.steps, "repeats": repeats, "total_ms": elapsed_ms,
+                            "region_ms_median": median_region, "region_ms_min": region_ms[0], "region_ms_max": region_ms[-1],
+                            "value_at_median_region": world * live_env_steps / repeats / (median_region * 1e-3),
+                            "launches_queued_before_first_event": bool(queued_ahead),
+                            "note": "value = live env-steps of all repeats / device time from the first region's start event to the "
+                                    "last region's stop event (max over ranks); every launch was enqueued behind a gate kernel"},
            "config": {"workload": "C2: pedestrians scenario (Car + SpawnPedestrian) x 65,536 envs per GPU, replayed joint "
-                                  f"actions (on-device RandomConstrained eps=0.01 trace), cavgym_replay {CHUNK} steps/launch, "
-                                  "trajectories recorded", "envs_per_gpu": n, "bodies": m, "segment": SEGMENT,
-                      "l2": f"trajectory slabs ({CHUNK * 5.24e6 / 1e9:.2f} GB) and action trace (1 GB) exceed L2; state is L2/register resident",
+                                  f"actions (on-device RandomConstrained eps=0.01 trace), cavgym_replay {steps_per_launch:g} steps/launch, "
+                                  f"trajectories recorded, region of {args.steps} steps repeated {repeats}x",
+                      "envs_per_gpu": n, "bodies": m, "segment": SEGMENT,
+                      "l2": f"{slots} rotating trajectory slabs ({slab_steps * 5.24e6 / 1e9:.2f} GB) and the action trace (1 GB) exceed L2; state is register resident",
                       "live_fraction": round(live_fraction, 4)},
            "roofline": roofline, "gpu_launches": int(gpu_launches), "clocks": clocks}
 
@@ -521,7 +558,8 @@ def main():
     parser.add_argument("--dtype", default="float64", choices=["float64", "float32"])
     parser.add_argument("--e2e-steps", type=int, default=200)
     parser.add_argument("--cpu-seconds", type=float, default=15.0)
-    parser.add_argument("--chunk", type=int, default=CHUNK, help="steps fused per cavgym_replay launch")
+    parser.add_argument("--chunk", type=int, default=CHUNK, help="steps fused per cavgym_replay launch (at most --steps)")
+    parser.add_argument("--repeats", type=int, default=REGION_REPEATS, help="back-to-back repetitions of the --steps-long timed region")
     parser.add_argument("--skip-hbm", action="store_true")
     parser.add_argument("--skip-cpu", action="store_true")
     parser.add_argument("--skip-configs", action="store_true", help="skip the C3 / C4 / C5 side measurements")

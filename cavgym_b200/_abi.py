@@ -14,7 +14,7 @@ CAV_SMALL_M = 8
 CAV_MAX_BODIES = 512
 CAV_AGENT_WORDS = 5
 CAV_DRAWS = 3
-CAV_N_STATS = 10
+CAV_N_STATS = 12
 
 CAV_F64, CAV_F32 = 0, 1
 CAV_BODY_DYNAMIC, CAV_BODY_PELICAN = 0, 1
@@ -22,7 +22,7 @@ CAV_FLAG_PEDESTRIAN, CAV_FLAG_SPAWN = 1, 2
 CAV_AGENT_EXTERNAL, CAV_AGENT_NOOP, CAV_AGENT_RANDOM, CAV_AGENT_RANDOM_CONSTRAINED, CAV_AGENT_PROXIMITY = range(5)
 CAV_COLLISIONS_NONE, CAV_COLLISIONS_EGO, CAV_COLLISIONS_ALL = range(3)
 STAT_NAMES = ("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2", "env_steps", "body_steps",
-              "tangent", "errors")
+              "tangent", "errors", "sum_t_interesting", "sum_t2_interesting")
 
 
 class CavQuad(C.Structure):
@@ -93,6 +93,7 @@ PROTOTYPES = {
     "cavgym_set_tangent_tolerance": (C.c_int, [c_engine_p, C.c_double]),
     "cavgym_bodies_step": (C.c_int, [C.POINTER(CavBodyType), C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, c_stream]),
     "cavgym_geometry_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_stream]),
+    "cavgym_zones_probe": (C.c_int, [C.POINTER(CavBodyType), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_stream]),
     "cavgym_last_error": (C.c_char_p, []),
     "cavgym_version": (C.c_char_p, []),
 }

@@ -261,6 +261,38 @@ __global__ void bodies_step_kernel(const __grid_constant__ DevType<R> k, R* stat
   for (int j = 0; j < 4; ++j) state[j * n + i] = st[j];
 }
 
+// DynamicBody.stopping_zones (bodies.py:122-135) written out from the EgoFrame the step kernels use (geometry.cuh): the
+// braking rectangle spans [hl, hl + bd] and the reaction rectangle [hl + bd, hl + td] along the heading, the body's width across.
+template <typename R>
+__global__ void zones_probe_kernel(const __grid_constant__ DevType<R> k, const R* state, const R* steering, R* zones, uint8_t* have,
+                                   int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const R x = state[i], y = state[n + i], v = state[2 * n + i], th = state[3 * n + i];
+  R steer = steering[i];
+  if (rabs(steer) < R(0.0000000000001)) steer = R(0);
+  R c = R(1), s = th;
+  if (!(th == R(0))) sincos_(th, &s, &c);
+  EgoFrame<R> f;
+  f.x = x; f.y = y; f.c = c; f.s = s; f.hl = k.hl; f.hw = k.hw;
+  f.bd = (v * v) * k.inv_2brake;
+  f.td = f.bd + v * R(0.675);
+  f.have = !(f.td == R(0)) && (steer == R(0));
+  have[i] = f.have ? 1 : 0;
+  const R hb = f.bd * R(0.5), hr = (f.td - f.bd) * R(0.5);
+  const R centre[2] = {f.hl + hb, f.hl + f.bd + hr}, half[2] = {hb, hr};
+#pragma unroll
+  for (int z = 0; z < 2; ++z) {
+    const R along[4] = {centre[z] - half[z], centre[z] + half[z], centre[z] + half[z], centre[z] - half[z]};
+    const R across[4] = {f.hw, f.hw, -f.hw, -f.hw};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      zones[(z * 8 + q) * n + i] = f.have ? x + (along[q] * c - across[q] * s) : nan_<R>();
+      zones[(z * 8 + 4 + q) * n + i] = f.have ? y + (along[q] * s + across[q] * c) : nan_<R>();
+    }
+  }
+}
+
 // Shape.intersects / contains / percentage_intersects on n quad pairs (geometry.py:74-87).
 template <typename R>
 __global__ void geometry_probe_kernel(const R* qa, const R* qb, R* out, int64_t n, R tau) {
@@ -773,7 +805,7 @@ int cavgym_info(CavEngine* eng, void* polygons_out, void* road_angle_out, cudaSt
   return launch_check(eng, "info kernel");
 }
 
-int cavgym_stats(CavEngine* eng, int64_t* out10) {
+int cavgym_stats(CavEngine* eng, int64_t* out10 /* [CAV_N_STATS] */) {
   int rc = check_engine(eng);
   if (rc) return rc;
   if (!out10) return fail(CAV_EINVAL, "out10 is NULL");
@@ -883,6 +915,19 @@ int cavgym_bodies_step(const CavBodyType* type, void* state, const void* actions
   else return fail(CAV_EINVAL, "dtype must be CAV_F64 or CAV_F32");
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(CAV_ECUDA, std::string("bodies_step kernel: ") + cudaGetErrorString(err));
+  return CAV_OK;
+}
+
+int cavgym_zones_probe(const CavBodyType* type, const void* state, const void* steering, void* zones_out, uint8_t* have_out,
+                       int64_t n, int dtype, cudaStream_t stream) {
+  if (!type || !state || !steering || !zones_out || !have_out || n < 0) return fail(CAV_EINVAL, "bad argument");
+  if (n == 0) return CAV_OK;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (dtype == CAV_F64) zones_probe_kernel<double><<<grid, 128, 0, stream>>>(to_type<double>(*type), (const double*)state, (const double*)steering, (double*)zones_out, have_out, n);
+  else if (dtype == CAV_F32) zones_probe_kernel<float><<<grid, 128, 0, stream>>>(to_type<float>(*type), (const float*)state, (const float*)steering, (float*)zones_out, have_out, n);
+  else return fail(CAV_EINVAL, "dtype must be CAV_F64 or CAV_F32");
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(CAV_ECUDA, std::string("zones_probe kernel: ") + cudaGetErrorString(err));
   return CAV_OK;
 }
 

@@ -22,9 +22,17 @@
 
 namespace cav {
 
-#ifdef CAV_DEBUG_TIMES
-__device__ unsigned long long g_dbg[16];
-#define CAV_DBG(i) atomicAdd(&g_dbg[i], 1ull)
+#ifdef CAV_DEBUG_COUNTERS
+// per CTA: [i] warp-level executions of path i, [16 + i] lanes that took it
+__device__ unsigned long long g_dbg[512][32];
+#define CAV_DBG(i)                                                                   \
+  do {                                                                               \
+    const unsigned m_ = __activemask();                                              \
+    if ((threadIdx.x & 31) == __ffs(m_) - 1) {                                       \
+      atomicAdd(&g_dbg[blockIdx.x & 511][i], 1ull);                                  \
+      atomicAdd(&g_dbg[blockIdx.x & 511][16 + i], (unsigned long long)__popc(m_));   \
+    }                                                                                \
+  } while (0)
 #else
 #define CAV_DBG(i)
 #endif
@@ -345,6 +353,7 @@ __device__ __noinline__ int sat_pose_quad(Pose<R> a, const Quad<R>* other, R tau
 // the reference returns too (intersects() false -> 0).
 template <typename R>
 __device__ __noinline__ R corner_share(Pose<R> a, R sx, R bx, R sy, R by) {
+  CAV_DBG(10);
   Quad<R> q;
   make_box(a.length, a.width, a.theta, a.c, a.s, a.x, a.y, q);
   R acc = R(0), fx2 = R(0), fy2 = R(0), px2 = R(0), py2 = R(0);
@@ -386,6 +395,41 @@ __device__ __noinline__ R corner_share(Pose<R> a, R sx, R bx, R sy, R by) {
   }
   if (have2) acc += px2 * fy2 - fx2 * py2;
   return fast_div(rabs(acc) * R(0.5), a.length * a.width);
+}
+
+// The same share without clipping whenever possible.  With Hx, Hy the half-planes of the two crossed edges and Q the open
+// quadrant outside both,  area(box ∩ Hx ∩ Hy) = area(box ∩ Hx) + area(box ∩ Hy) − area(box) + area(box ∩ Q)
+// (inclusion-exclusion).  The first two terms are kerb shares (closed form); box ∩ Q is empty when a box axis separates the
+// box from Q and a rectangle when the box is axis-aligned (a pedestrian that has turned onto ±pi/2, the case that actually
+// occurs: it stays on a road corner for the ~65 steps of its kerb crossing, and the ~500 dependent instructions of the
+// streaming clipper made its warp — and with it the whole CTA of a fused replay launch — run at half speed).  Only a
+// rotated box that really reaches into Q still goes to corner_share.
+//   tx, ty   signed distance of the box centre from the crossed x-edge / y-edge, positive inside the road
+//   sx, sy   outward direction (+-1) of those edges; bx, by as for corner_share
+template <typename R>
+__device__ __noinline__ R corner_share_closed(Pose<R> a, R tx, R ty, R sx, R bx, R sy, R by, R tau) {
+  const R hl = a.length * R(0.5), hw = a.width * R(0.5);
+  const R ac = rabs(a.c), as = rabs(a.s);
+  const R ex = ac * hl + as * hw, ey = as * hl + ac * hw;
+  const R ox = ex - tx, oy = ey - ty;   // how far the box's bounding box reaches beyond each of the two edges
+  R outside = R(0);                     // area(box ∩ Q)
+  if (ox > R(0) && oy > R(0)) {
+    if (rmin(ac, as) < (sizeof(R) == 8 ? R(1e-9) : R(1e-5))) {
+      outside = rmin(ox, ex + ex) * rmin(oy, ey + ey);
+    } else {
+      // in the frame where Q is the first quadrant seen from the road corner: corner - centre = (tx, ty), box axes u, v
+      const R ux = sx * a.c, uy = sy * a.s, vx = -(sx * a.s), vy = sy * a.c;
+      const R pu = ux * tx + uy * ty, pv = vx * tx + vy * ty;
+      bool apart = false;   // an axis pointing into Q along which the whole box lies before the corner
+      if (ux >= R(0) && uy >= R(0)) apart |= pu >= hl + tau;
+      if (ux <= R(0) && uy <= R(0)) apart |= -pu >= hl + tau;
+      if (vx >= R(0) && vy >= R(0)) apart |= pv >= hw + tau;
+      if (vx <= R(0) && vy <= R(0)) apart |= -pv >= hw + tau;
+      if (!apart) return corner_share(a, sx, bx, sy, by);
+    }
+  }
+  const R p = ((kerb_share(tx, ac * hl, as * hw) + kerb_share(ty, as * hl, ac * hw)) - R(1)) + fast_div(outside, a.length * a.width);
+  return rmax(R(0), rmin(R(1), p));
 }
 
 // Share of a body box lying on a road by the general predicates: rotated roads, road corners, near-tangent

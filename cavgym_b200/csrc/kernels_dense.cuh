@@ -133,8 +133,8 @@ __device__ __noinline__ R dense_road_share_edge(const DevScenario<R>& sc, const 
       result = p; settled = true;
     } else if (mx < tau && my < tau && rmax(m0, m1) >= tau && rmax(m2, m3) >= tau) {
       const bool low_x = m0 < m1, low_y = m2 < m3;
-      const R p = corner_share(dense_pose(sm, k, b), low_x ? R(-1) : R(1), low_x ? -rd.x0 : rd.x1, low_y ? R(-1) : R(1),
-                               low_y ? -rd.y0 : rd.y1);
+      const R p = corner_share_closed(dense_pose(sm, k, b), mx + ex, my + ey, low_x ? R(-1) : R(1), low_x ? -rd.x0 : rd.x1,
+                                      low_y ? R(-1) : R(1), low_y ? -rd.y0 : rd.y1, tau);
       if (rabs(p - R(0.5)) < tau) near = true;
       result = p; settled = true;
     }

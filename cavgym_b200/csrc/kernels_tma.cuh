@@ -420,20 +420,22 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
   const bool active = (uint32_t)tid < cnt;
   const int64_t e = tile_lo + (active ? tid : 0);
 #ifdef CAV_DEBUG_TIMES
-  unsigned long long t_start;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+  // per CTA: [0] entry, [1] after load_env, [2 + w] end of warp w's first step, [10 + w] end of warp w's last step, [18] exit
+  double* probe = buf.uni_override ? const_cast<double*>(buf.uni_override) + (int64_t)blockIdx.x * 20 : nullptr;
+  auto stamp = [&](int slot) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (probe && lane == 0) probe[slot] = (double)now;
+  };
+  if (warp == 0) stamp(0);
 #endif
   EnvRegs<R, M> env;
   load_env<R, M, false>(sc, buf, e, env);
   const bool was_live = env.done == 0;
-  for (int t = 0; t < n_steps; ++t) {
 #ifdef CAV_DEBUG_TIMES
-    if (buf.uni_override && lane == 0 && blockIdx.x < 4 && t < 60) {
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      const_cast<double*>(buf.uni_override)[4096 + ((blockIdx.x * 8 + warp) * 60 + t)] = (double)(now - t_start);
-    }
+  if (warp == 0) stamp(1);
 #endif
+  for (int t = 0; t < n_steps; ++t) {
     const int s = t % kTmaStages;
     const uint32_t parity = (uint32_t)(t / kTmaStages) & 1u;
     unsigned char* st = smem + s * L::kStageBytes;
@@ -475,15 +477,18 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
     fence_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(&done[s]);
+#ifdef CAV_DEBUG_TIMES
+    if (t == 0) stamp(2 + warp);
+    if (t == n_steps - 1) stamp(10 + warp);
+#endif
   }
   if (active && was_live) store_env<R, M, false>(sc, buf, e, env, false);
 #ifdef CAV_DEBUG_TIMES
-  if (buf.uni_override && tid == 0) {
-    unsigned long long now;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-    const_cast<double*>(buf.uni_override)[blockIdx.x * 2] = (double)t_start;
-    const_cast<double*>(buf.uni_override)[blockIdx.x * 2 + 1] = (double)now;
-    if (blockIdx.x == 0) for (int i = 0; i < 16; ++i) const_cast<double*>(buf.uni_override)[2048 + i] = (double)g_dbg[i];
+  if (warp == 0) stamp(18);
+  if (probe && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    probe[19] = (double)smid;
   }
 #endif
 }

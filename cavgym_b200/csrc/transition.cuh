@@ -16,6 +16,9 @@
 // Boxes never become corner lists here: each body is (x, y, cos, sin, half length, half width) and every test is
 // written on that form (geometry.cuh).  What stays out of line: general quads, road corners, libm.
 #pragma once
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+
 #include "agents.cuh"
 
 namespace cav {
@@ -103,8 +106,8 @@ __device__ __forceinline__ R road_share(const DevScenario<R>& sc, const EnvRegs<
     // a corner of the road: one x-edge and one y-edge crossed (or touched), the opposite edges clearly inside
     if (mx < tau && my < tau && rmax(m0, m1) >= tau && rmax(m2, m3) >= tau) {
       const bool low_x = m0 < m1, low_y = m2 < m3;
-      const R p = corner_share(body_pose<R, M>(sc, env, b), low_x ? R(-1) : R(1), low_x ? -rd.x0 : rd.x1, low_y ? R(-1) : R(1),
-                               low_y ? -rd.y0 : rd.y1);
+      const R p = corner_share_closed(body_pose<R, M>(sc, env, b), mx + ex, my + ey, low_x ? R(-1) : R(1), low_x ? -rd.x0 : rd.x1,
+                                      low_y ? R(-1) : R(1), low_y ? -rd.y0 : rd.y1, tau);
       if (rabs(p - R(0.5)) < tau) near = true;
       return p;
     }
@@ -187,18 +190,38 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
   else transition_unrolled<R, M, AGENTS, GENERIC, Sink>(sc, buf, e, t_global, env, ext, out, moved);
 }
 
-// reporting.analyse_episode (reporting.py:227-243) for an env whose episode just ended.
+// reporting.analyse_episode (reporting.py:227-243) for an env whose episode just ended.  The lanes of a warp that end their
+// episodes in the same step (with a Noop ego EVERY env reaches the finish line at step 901 at once) first add up their
+// contributions, so the ten global counters see one atomic per warp and counter instead of one per env.
 template <typename R, int M>
 __device__ __noinline__ void score_episode(unsigned long long* stats, int32_t t_ep, int32_t winner, long long liveness_sum) {
+  namespace cg = cooperative_groups;
+  const cg::coalesced_group lanes = cg::coalesced_threads();
   const unsigned long long t = (unsigned long long)t_ep;
-  atomicAdd(&stats[CAV_STAT_EPISODES], 1ull);
-  atomicAdd(&stats[CAV_STAT_SUM_T], t);
-  atomicAdd(&stats[CAV_STAT_SUM_T2], t * t);
-  if (winner > 0) {
-    const long long score = -liveness_sum;
-    atomicAdd(&stats[CAV_STAT_INTERESTING], 1ull);
-    atomicAdd(&stats[CAV_STAT_SUM_SCORE], (unsigned long long)score);  // two's complement: wraps to the signed sum
-    atomicAdd(&stats[CAV_STAT_SUM_SCORE2], (unsigned long long)(score * score));
+  const bool interesting = winner > 0;
+  const long long score = interesting ? -liveness_sum : 0;
+  const cg::plus<unsigned long long> add;
+  const unsigned long long n_eps = lanes.size();
+  const unsigned long long sum_t = cg::reduce(lanes, t, add), sum_t2 = cg::reduce(lanes, t * t, add);
+  const unsigned long long n_int = cg::reduce(lanes, (unsigned long long)(interesting ? 1 : 0), add);
+  unsigned long long sum_s = 0, sum_s2 = 0, sum_it = 0, sum_it2 = 0;
+  if (n_int) {   // two's complement: the unsigned sums wrap to the signed ones
+    sum_s = cg::reduce(lanes, (unsigned long long)score, add);
+    sum_s2 = cg::reduce(lanes, (unsigned long long)(score * score), add);
+    sum_it = cg::reduce(lanes, interesting ? t : 0ull, add);
+    sum_it2 = cg::reduce(lanes, interesting ? t * t : 0ull, add);
+  }
+  if (lanes.thread_rank() == 0) {
+    atomicAdd(&stats[CAV_STAT_EPISODES], n_eps);
+    atomicAdd(&stats[CAV_STAT_SUM_T], sum_t);
+    atomicAdd(&stats[CAV_STAT_SUM_T2], sum_t2);
+    if (n_int) {
+      atomicAdd(&stats[CAV_STAT_INTERESTING], n_int);
+      atomicAdd(&stats[CAV_STAT_SUM_SCORE], sum_s);
+      atomicAdd(&stats[CAV_STAT_SUM_SCORE2], sum_s2);
+      atomicAdd(&stats[CAV_STAT_SUM_T_INTERESTING], sum_it);
+      atomicAdd(&stats[CAV_STAT_SUM_T2_INTERESTING], sum_it2);
+    }
   }
 }
 

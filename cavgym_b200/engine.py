@@ -234,6 +234,28 @@ def bodies_step(constants, states, actions, time_resolution, dtype="float64", de
     return state_t.t().cpu().tolist()
 
 
+def zones_probe(constants, states, steering, dtype="float64", device=None):
+    """DynamicBody.stopping_zones (reference library/bodies.py:122-135) for n independent bodies of one type, as the step
+    kernels represent the zones.  states [n][4], steering [n] -> (zones [n][2][4][2] = braking / reaction corner lists in the
+    reference's order, have [n] bool; rows without zones are NaN)."""
+    lib = _native.load()
+    device = _require_cuda(device)
+    code, tdtype = _DTYPES[dtype]
+    state_t = torch.tensor(np.asarray(states, dtype=np.float64), dtype=tdtype, device=device).t().contiguous()
+    steer_t = torch.tensor(np.asarray(steering, dtype=np.float64), dtype=tdtype, device=device).contiguous()
+    n = state_t.shape[1]
+    zones = torch.empty((16, n), dtype=tdtype, device=device)
+    have = torch.empty(n, dtype=torch.uint8, device=device)
+    k = _abi.CavBodyType(*[float(v) for v in (constants.length, constants.width, constants.wheelbase, constants.min_velocity,
+                                               constants.max_velocity, constants.min_throttle, constants.max_throttle,
+                                               constants.min_steering_angle, constants.max_steering_angle)])
+    with torch.cuda.device(device):
+        _native.check(lib.cavgym_zones_probe(C.byref(k), _ptr(state_t), _ptr(steer_t), _ptr(zones), _ptr(have), n, code,
+                                             C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+    z = zones.double().cpu().numpy().reshape(2, 2, 4, n)           # [zone][x|y][corner][n]
+    return np.transpose(z, (3, 0, 2, 1)), have.cpu().numpy().astype(bool)
+
+
 def geometry_probe(quads_a, quads_b, dtype="float64", device=None):
     """Shape.intersects / contains / percentage_intersects (reference library/geometry.py:74-87) on n quad pairs,
     run by the CUDA geometry code.  quads [n][4][2] -> array [n][4]: intersects, b.contains(a), share, tangent."""

@@ -134,6 +134,9 @@ def analyse_episode(index, start_time, end_time, timesteps, env_info, run_config
 
 @dataclass(frozen=True)
 class RunSummary:
+    """analyse_run (reporting.py:246-269) and RunResults' two messages (reporting.py:219-224).  The three intervals are over
+    the INTERESTING episodes only, as in the reference; the per-episode runtime has no meaning for a batch of concurrent
+    environments, so that interval is NaN there (its two run_log columns are kept: the line has the reference's 10 fields)."""
     episodes: int
     timesteps: int
     runtime_ms: float
@@ -141,31 +144,34 @@ class RunSummary:
     interesting: int
     confidence_timesteps: Interval
     confidence_score: Interval
+    confidence_runtime: Interval = Interval(float("nan"), float("nan"))
 
     @classmethod
     def from_episodes(cls, episode_data, start_time, end_time, resolution):
         hits = [row for row in episode_data if row.interesting]
         return cls(len(episode_data), sum(row.time.timesteps for row in episode_data), (end_time - start_time) * 1000, resolution,
-                   len(hits), confidence_interval([row.time.timesteps for row in hits]), confidence_interval([row.score for row in hits]))
+                   len(hits), confidence_interval([row.time.timesteps for row in hits]), confidence_interval([row.score for row in hits]),
+                   confidence_interval([row.time.runtime() for row in hits]))
 
     @classmethod
-    def from_stats(cls, stats, runtime_ms, resolution, interesting_t=None):
-        """`stats` is the dict of cavgym_stats (summed over GPUs).  The device keeps sum/sum^2 of timesteps over ALL
-        episodes and of the score over interesting ones; the timestep interval is therefore over all episodes
-        unless the caller supplies per-episode data."""
+    def from_stats(cls, stats, runtime_ms, resolution):
+        """`stats` is the dict of cavgym_stats (summed over GPUs): the device keeps count, sum and sum of squares of the
+        timesteps and of the score over the interesting episodes (score_episode, transition.cuh)."""
         return cls(stats["episodes"], stats["env_steps"], runtime_ms, resolution, stats["interesting"],
-                   interval_from_sums(stats["episodes"], stats["sum_t"], stats["sum_t2"]),
+                   interval_from_sums(stats["interesting"], stats["sum_t_interesting"], stats["sum_t2_interesting"]),
                    interval_from_sums(stats["interesting"], stats["sum_score"], stats["sum_score2"]))
 
     def simulation_speed(self):
         return (self.timesteps * self.resolution * 1000) / self.runtime_ms
 
     def console_message(self):
-        tests = (f"{self.interesting} interesting test(s) with {self.confidence_timesteps.pretty(decimal_places=0)} timestep(s) and "
+        tests = (f"{self.interesting} interesting test(s) with {self.confidence_timesteps.pretty(decimal_places=0)} timestep(s), "
+                 f"{self.confidence_runtime.pretty(decimal_places=0)} ms runtime, and "
                  f"{self.confidence_score.pretty(decimal_places=0)} score") if self.interesting > 0 else "no interesting test(s)"
         return (f"run completed after {self.episodes} episode(s) and {self.timesteps} timestep(s) in "
                 f"{pretty_float(self.runtime_ms, decimal_places=0)} ms (*{pretty_float(self.simulation_speed())} real-time), {tests}")
 
     def file_message(self):
         return (f"{self.episodes},{self.timesteps},{self.runtime_ms},{self.interesting},{self.confidence_timesteps.value},"
-                f"{self.confidence_timesteps.error},{self.confidence_score.value},{self.confidence_score.error}")
+                f"{self.confidence_timesteps.error},{self.confidence_runtime.value},{self.confidence_runtime.error},"
+                f"{self.confidence_score.value},{self.confidence_score.error}")

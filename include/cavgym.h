@@ -125,10 +125,13 @@ typedef struct CavScenario {
 
 typedef struct CavEngine CavEngine;
 
-/* Indices of cavgym_stats' ten int64 counters (reporting.py:227-269 definitions). */
+/* Indices of cavgym_stats' twelve int64 counters (reporting.py:227-269 definitions).  SUM_T / SUM_T2 run over every
+ * finished episode; SUM_T_INTERESTING / SUM_T2_INTERESTING only over episodes with winner > 0, which is what the reference's
+ * run summary reports as the timesteps of its "interesting" tests (reporting.py:246-255). */
 enum { CAV_STAT_EPISODES = 0, CAV_STAT_INTERESTING = 1, CAV_STAT_SUM_T = 2, CAV_STAT_SUM_T2 = 3,
        CAV_STAT_SUM_SCORE = 4, CAV_STAT_SUM_SCORE2 = 5, CAV_STAT_ENV_STEPS = 6, CAV_STAT_BODY_STEPS = 7,
-       CAV_STAT_TANGENT = 8, CAV_STAT_ERRORS = 9, CAV_N_STATS = 10 };
+       CAV_STAT_TANGENT = 8, CAV_STAT_ERRORS = 9, CAV_STAT_SUM_T_INTERESTING = 10, CAV_STAT_SUM_T2_INTERESTING = 11,
+       CAV_N_STATS = 12 };
 
 /* ---- lifecycle ------------------------------------------------------------------- */
 
@@ -192,8 +195,8 @@ int cavgym_info(CavEngine* engine, void* polygons_out, void* road_angle_out, cud
 /* ---- accounting ------------------------------------------------------------------ */
 
 /* reporting.analyse_episode / analyse_run (reporting.py:227-269) sums over episodes
- * scored so far; out10 is a HOST int64[CAV_N_STATS].  Synchronises. */
-int cavgym_stats(CavEngine* engine, int64_t* out10);
+ * scored so far; out is a HOST int64[CAV_N_STATS].  Synchronises. */
+int cavgym_stats(CavEngine* engine, int64_t* out);
 int cavgym_error_count(CavEngine* engine, int64_t* out);   /* envs with the invalid-action flag set */
 int cavgym_launch_count(CavEngine* engine, int64_t* out);  /* kernels launched by this engine so far */
 
@@ -256,6 +259,14 @@ int cavgym_bodies_step(const CavBodyType* type, void* state, const void* actions
  * quads_a, quads_b real[8][n] (x0..x3, y0..y3); out real[4][n] = a.intersects(b), b.contains(a),
  * a.percentage_intersects(b), near-tangent flag. */
 int cavgym_geometry_probe(const void* quads_a, const void* quads_b, void* out, int64_t n, int dtype, cudaStream_t stream);
+
+/* DynamicBody.stopping_zones (bodies.py:122-135, geometry.py:176-191) for n independent bodies of one type, from the
+ * representation the step kernels test against (braking and reaction rectangles laid end to end in the body's frame):
+ * state real[4][n], steering real[n] (the body's current steering angle) -> zones real[16][n] = braking x0..x3, y0..y3,
+ * reaction x0..x3, y0..y3 in the reference's corner order (rear left, front left, front right, rear right), and
+ * have u8[n] = 0 where the reference returns (None, None): total distance 0 or steering != 0. */
+int cavgym_zones_probe(const CavBodyType* type, const void* state, const void* steering, void* zones_out, uint8_t* have_out,
+                       int64_t n, int dtype, cudaStream_t stream);
 
 const char* cavgym_last_error(void);
 const char* cavgym_version(void);

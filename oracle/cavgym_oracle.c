@@ -464,6 +464,8 @@ static void score_episode(CavOracle* o, int64_t e, int64_t* stats) { /* reportin
     stats[CAV_STAT_INTERESTING] += 1;
     stats[CAV_STAT_SUM_SCORE] += score;
     stats[CAV_STAT_SUM_SCORE2] += score * score;
+    stats[CAV_STAT_SUM_T_INTERESTING] += t;
+    stats[CAV_STAT_SUM_T2_INTERESTING] += t * t;
   }
 }
 

@@ -187,7 +187,7 @@ def test_dense_traffic_device_agents_match_oracle():
     oracle.rollout(steps, auto_reset=True)
     got, want = env.stats(), oracle.stats()
     if got["tangent"] == 0 and want["tangent"] == 0:
-        for key in ("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2", "env_steps"):
+        for key in ("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2", "env_steps", "sum_t_interesting", "sum_t2_interesting"):
             assert got[key] == want[key], key
         assert state_err(np.moveaxis(env.state.cpu().numpy(), 1, -1), np.moveaxis(oracle.state, 1, -1)) < 1e-9
     else:   # a flagged near-tangent decision may legitimately differ: episode counts stay close
@@ -291,7 +291,7 @@ def test_maximum_body_count_matches_oracle():
     oracle.rollout(steps, auto_reset=True)
     got, want = env.stats(), oracle.stats()
     if got["tangent"] == 0 and want["tangent"] == 0:
-        for key in ("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2", "env_steps"):
+        for key in ("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2", "env_steps", "sum_t_interesting", "sum_t2_interesting"):
             assert got[key] == want[key], key
         assert state_err(np.moveaxis(env.state.cpu().numpy(), 1, -1), np.moveaxis(oracle.state, 1, -1)) < 1e-9
     assert want["episodes"] >= 2

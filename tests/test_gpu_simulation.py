@@ -54,7 +54,7 @@ def test_batched_simulation_matches_oracle_counters():
     oracle.rollout(sim.steps_run, auto_reset=True)
     want = oracle.stats()
     if got["tangent"] == 0 and want["tangent"] == 0:
-        for key in ("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2", "env_steps"):
+        for key in ("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2", "env_steps", "sum_t_interesting", "sum_t2_interesting"):
             assert got[key] == want[key], key
     assert "interesting test(s)" in summary.console_message()
 
