@@ -53,7 +53,6 @@ __device__ __forceinline__ void sin_cosm1_poly(double x, double& sn, double& cm1
 }
 
 static __device__ __noinline__ void sin_cosm1_wide(double x, double* sn, double* cm1) {  // |x| > pi/4: never in practice
-  CAV_DBG(2);
   double h, unused;
   sincos(x, sn, &unused);
   h = sin(0.5 * x);
@@ -81,7 +80,6 @@ __device__ __forceinline__ void steer_geometry(double wheelbase, double half_wb,
     sn = k * (1.0 + cr1);   // sin(k pi/2 + r) = k cos r
     cs = -k * sr;           // cos(k pi/2 + r) = -k sin r
   } else {
-    CAV_DBG(4);
     sn = sin_(steer);
     cs = cos_(steer);
   }
@@ -94,7 +92,6 @@ template <typename R>
 __device__ __forceinline__ R wrap_angle(R a) {
   const R pi = R(3.14159265358979323846), two_pi = R(6.28318530717958647692);
   if (rabs(a) > R(3) * pi) {  // bodies created with headings beyond +-2 pi: general formula
-    CAV_DBG(3);
     R sa, ca;
     sincos_(a, &sa, &ca);
     return atan2_(sa, ca);
@@ -138,8 +135,7 @@ __device__ __forceinline__ void body_turn(const DevType<R>& k, R st[4], R steer,
   double kk, inv_r;
   if (steer == k.smax) { kk = k.kk_smax; inv_r = k.inv_r_smax; }
   else if (steer == k.smin) { kk = k.kk_smin; inv_r = k.inv_r_smin; }
-  else { CAV_DBG(5); steer_geometry((double)k.wheelbase, (double)k.half_wb, (double)steer, kk, inv_r); }
-  CAV_DBG(6);
+  else { steer_geometry((double)k.wheelbase, (double)k.half_wb, (double)steer, kk, inv_r); }
   const double q = (double)d * inv_r;
   const double phi = steer < R(0) ? -q : q;
   double sn_, cm1_;

@@ -22,21 +22,6 @@
 
 namespace cav {
 
-#ifdef CAV_DEBUG_COUNTERS
-// per CTA: [i] warp-level executions of path i, [16 + i] lanes that took it
-__device__ unsigned long long g_dbg[512][32];
-#define CAV_DBG(i)                                                                   \
-  do {                                                                               \
-    const unsigned m_ = __activemask();                                              \
-    if ((threadIdx.x & 31) == __ffs(m_) - 1) {                                       \
-      atomicAdd(&g_dbg[blockIdx.x & 511][i], 1ull);                                  \
-      atomicAdd(&g_dbg[blockIdx.x & 511][16 + i], (unsigned long long)__popc(m_));   \
-    }                                                                                \
-  } while (0)
-#else
-#define CAV_DBG(i)
-#endif
-
 // a / b to ~2 ulp with a float reciprocal seed and two Newton steps (10 instructions instead of the ~60 of the
 // IEEE division subroutine).  Used only where |b| is a normal float (pixel distances, sines of steering angles).
 __device__ __forceinline__ double fast_div(double a, double b) {
@@ -337,7 +322,6 @@ struct Pose {  // what is needed to rebuild a body's corners: make_rectangle(len
 // body box vs a quad of the scenario tables that is not a rectangle
 template <typename R>
 __device__ __noinline__ int sat_pose_quad(Pose<R> a, const Quad<R>* other, R tau) {
-  CAV_DBG(0);
   Quad<R> qa;
   const Quad<R> qb = *other;
   make_box(a.length, a.width, a.theta, a.c, a.s, a.x, a.y, qa);
@@ -353,7 +337,6 @@ __device__ __noinline__ int sat_pose_quad(Pose<R> a, const Quad<R>* other, R tau
 // the reference returns too (intersects() false -> 0).
 template <typename R>
 __device__ __noinline__ R corner_share(Pose<R> a, R sx, R bx, R sy, R by) {
-  CAV_DBG(10);
   Quad<R> q;
   make_box(a.length, a.width, a.theta, a.c, a.s, a.x, a.y, q);
   R acc = R(0), fx2 = R(0), fy2 = R(0), px2 = R(0), py2 = R(0);
@@ -436,7 +419,6 @@ __device__ __noinline__ R corner_share_closed(Pose<R> a, R tx, R ty, R sx, R bx,
 // configurations.
 template <typename R>
 __device__ __noinline__ Share<R> road_share_general(Pose<R> a, const Quad<R>* road, R tau) {
-  CAV_DBG(1);
   Quad<R> box;
   make_box(a.length, a.width, a.theta, a.c, a.s, a.x, a.y, box);
   const Quad<R> other = *road;

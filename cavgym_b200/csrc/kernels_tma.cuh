@@ -3,7 +3,7 @@
 //
 //   step_tma_kernel     cavgym_step    one CAVEnv.step (environment.py:119-223) over N envs; persistent CTAs walk
 //                                      128-env tiles; the pipeline runs over TILES
-//   replay_tma_kernel   cavgym_replay  T fused steps with the state in registers; one CTA per 160-env tile; the
+//   replay_tma_kernel   cavgym_replay  T fused steps with the state in registers; one CTA per 224-env tile; the
 //                                      pipeline runs over TIME STEPS (actions in, trajectory rows out)
 //
 // Why: a step moves ~200 B per env through HBM and keeps ~20 values per env live while it computes.  In the plain
@@ -25,6 +25,8 @@
 // With n % 16 == 0 a ragged last tile is handled here too (shorter bulk copies); with only n % 4 == 0 the step kernel
 // takes the whole tiles and leaves the tail to the plain kernel.
 #pragma once
+#include <atomic>
+
 #include "kernels_small.cuh"
 
 namespace cav {
@@ -49,6 +51,7 @@ namespace cav {
 #endif
 constexpr int kTmaStages = CAV_TMA_STAGES;
 constexpr int kMaxSmemPerBlock = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
+constexpr int kMaxDevices = 64;                // per-device caches of the launchers below
 // The TMA-staged kernels pay off while three CTAs (step) / two 256-thread CTAs (replay) fit an SM, i.e. for one or two
 // bodies.  From three bodies on the staging buffers crowd the SM and the plain kernels are faster — measured at 1M envs,
 // fp64, step: M=3 0.135 vs 0.111 ms, M=4 0.353 vs 0.170, M=5 0.616 vs 0.243, bus stop 0.97 vs 0.47; replay of 50 steps at
@@ -419,22 +422,9 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
   // ================= consumer warps
   const bool active = (uint32_t)tid < cnt;
   const int64_t e = tile_lo + (active ? tid : 0);
-#ifdef CAV_DEBUG_TIMES
-  // per CTA: [0] entry, [1] after load_env, [2 + w] end of warp w's first step, [10 + w] end of warp w's last step, [18] exit
-  double* probe = buf.uni_override ? const_cast<double*>(buf.uni_override) + (int64_t)blockIdx.x * 20 : nullptr;
-  auto stamp = [&](int slot) {
-    unsigned long long now;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-    if (probe && lane == 0) probe[slot] = (double)now;
-  };
-  if (warp == 0) stamp(0);
-#endif
   EnvRegs<R, M> env;
   load_env<R, M, false>(sc, buf, e, env);
   const bool was_live = env.done == 0;
-#ifdef CAV_DEBUG_TIMES
-  if (warp == 0) stamp(1);
-#endif
   for (int t = 0; t < n_steps; ++t) {
     const int s = t % kTmaStages;
     const uint32_t parity = (uint32_t)(t / kTmaStages) & 1u;
@@ -477,20 +467,8 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
     fence_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(&done[s]);
-#ifdef CAV_DEBUG_TIMES
-    if (t == 0) stamp(2 + warp);
-    if (t == n_steps - 1) stamp(10 + warp);
-#endif
   }
   if (active && was_live) store_env<R, M, false>(sc, buf, e, env, false);
-#ifdef CAV_DEBUG_TIMES
-  if (warp == 0) stamp(18);
-  if (probe && tid == 0) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    probe[19] = (double)smid;
-  }
-#endif
 }
 
 // ================================================================ host side
@@ -520,22 +498,29 @@ bool launch_step_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const S
   const int64_t span = tma_span(buf, io, kStepTile, false);
   if (span == 0) return true;
   const int64_t tiles = (span + kStepTile - 1) / kStepTile;
-  static int resident[2] = {0, 0};  // [generic]: CTAs per SM, queried once per instantiation
-  static int sms = 0;
+  // per DEVICE and instantiation: the shared-memory opt-in is a per-device function attribute (a second engine on another
+  // GPU of the same process needs its own), so the cache is keyed by the current device; 0 unknown, -1 unusable
+  static std::atomic<int> resident[kMaxDevices][2];
+  static std::atomic<int> sm_count[kMaxDevices];
   auto kernel = sc.homogeneous ? step_tma_kernel<R, M, false> : step_tma_kernel<R, M, true>;
-  int& res = resident[sc.homogeneous ? 0 : 1];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return true;
+  std::atomic<int>& slot = resident[dev][sc.homogeneous ? 0 : 1];
+  int res = slot.load(std::memory_order_acquire);
   if (res < 0) return true;   // found unusable before (shared memory): plain kernel
   if (res == 0) {
+    int sms = 0;
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, kernel, kStepTile + 32, L::kSmemBytes) != cudaSuccess || res < 1) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, kernel, kStepTile + 32, L::kSmemBytes) != cudaSuccess || res < 1 ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
       cudaGetLastError();     // not an error of the caller's: this body count's staging does not fit, the plain kernel runs
-      res = -1;
+      slot.store(-1, std::memory_order_release);
       return true;
     }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sm_count[dev].store(sms, std::memory_order_relaxed);
+    slot.store(res, std::memory_order_release);   // idempotent: two threads racing here store the same values
   }
+  const int sms = sm_count[dev].load(std::memory_order_relaxed);
   EnvBuffers<R> range = buf;
   range.hi = buf.lo + span;
   const int64_t grid = tiles < (int64_t)sms * res ? tiles : (int64_t)sms * res;
@@ -555,19 +540,22 @@ bool launch_replay_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const
   } else {
   const int64_t span = tma_span(buf, io, kReplayTile, io.done_out != nullptr || io.tangent_out != nullptr);
   if (span == 0) return true;
-  static int ready[2] = {0, 0};   // 0 unknown, 1 usable, -1 does not fit shared memory
+  static std::atomic<int> ready[kMaxDevices][2];   // per device (see launch_step_tma): 0 unknown, 1 usable, -1 does not fit
   auto kernel = sc.homogeneous ? replay_tma_kernel<R, M, false> : replay_tma_kernel<R, M, true>;
-  int& ok = ready[sc.homogeneous ? 0 : 1];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return true;
+  std::atomic<int>& slot = ready[dev][sc.homogeneous ? 0 : 1];
+  const int ok = slot.load(std::memory_order_acquire);
   if (ok < 0) return true;
   if (ok == 0) {
     int blocks = 0;
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kReplayTile + 32, L::kSmemBytes) != cudaSuccess || blocks < 1) {
       cudaGetLastError();
-      ok = -1;
+      slot.store(-1, std::memory_order_release);
       return true;          // plain replay kernel for this body count
     }
-    ok = 1;
+    slot.store(1, std::memory_order_release);
   }
   EnvBuffers<R> range = buf;
   range.hi = buf.lo + span;

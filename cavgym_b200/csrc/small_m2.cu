@@ -13,13 +13,3 @@ const SmallLaunchers<double> kSmallF64M2 = make_launchers<double, 2>();
 const SmallLaunchers<float> kSmallF32M2 = make_launchers<float, 2>();
 #endif
 }  // namespace cav
-
-#if defined(CAV_DEBUG_COUNTERS) && !defined(CAV_STUB)
-// development builds only: per-CTA path counters of THIS translation unit (geometry.cuh CAV_DBG), read and cleared
-extern "C" int cavgym_debug_counters(unsigned long long* out /* [512][32] */) {
-  cudaDeviceSynchronize();
-  if (cudaMemcpyFromSymbol(out, cav::g_dbg, sizeof(cav::g_dbg)) != cudaSuccess) return -1;
-  static unsigned long long zeros[512][32];
-  return cudaMemcpyToSymbol(cav::g_dbg, zeros, sizeof(zeros)) == cudaSuccess ? 0 : -1;
-}
-#endif

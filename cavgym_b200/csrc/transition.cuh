@@ -98,7 +98,6 @@ __device__ __forceinline__ R road_share(const DevScenario<R>& sc, const EnvRegs<
     if (lo <= -tau && hi >= tau && opposite >= tau) {
       const R ac = rabs(env.cs[b][0]), as = rabs(env.cs[b][1]);
       const R hl = sc.bodies[b].k.hl, hw = sc.bodies[b].k.hw;
-      CAV_DBG(7);
       const R p = kerb_share(lo + (x_edge ? ex : ey), (x_edge ? ac : as) * hl, (x_edge ? as : ac) * hw);
       if (rabs(p - R(0.5)) < tau) near = true;
       return p;

@@ -1,2 +1,14 @@
-"""`library.actions` of the reference (actions.py:4-13) — the names live in `_vocabulary`."""
-from ._vocabulary import TRAFFIC_LIGHT_ACTIONS, Action, TrafficLightAction  # noqa: F401
+"""Discrete action vocabulary (reference library/actions.py:4-13)."""
+from enum import Enum
+
+
+class Action(Enum):
+    def __repr__(self):
+        return self.name
+
+
+class TrafficLightAction(Action):
+    NOOP = 0
+    TURN_RED = 1
+    TURN_AMBER = 2
+    TURN_GREEN = 3
