@@ -11,9 +11,13 @@ Sections are described by one table (OPTIONS) instead of a class per option; the
 (PedestriansConfig, RandomConstrainedConfig, HeadlessConfig ...) are kept as constructors because callers in the style
 of experiments.py:95-119 build configs with them.
 
-Not provided: the keyboard ego, the Q-learning ego / tester and the election tester (interactive or sequential host-side
-learners) and render mode (pyglet).  Their options still parse, validate and round-trip; building them
-raises NotImplementedError, as the reference does for combinations it does not support (config.py:343, 396).
+The Q-learning ego (examples/agents/ego.py) and the election tester (examples/agents/pedestrian.py, examples/election.py)
+run host-side on the single-environment view like in the reference; at batch scale the Q-learning ego has a tensor-API
+form (BatchedQLearningEgoAgent, driven by BatchedSimulation).  Not provided: the keyboard ego (interactive) and the
+Q-learning TESTER (the reference's own raises TypeError at its first update, pedestrian.py:128, 247).  Render mode has no
+viewer here (pyglet is not part of the engine): a render config runs headless and says so once.  Every option still
+parses, validates and round-trips; building an unavailable one raises NotImplementedError, as the reference does for
+combinations it does not support (config.py:343, 396).
 """
 import json
 import pathlib
@@ -148,8 +152,11 @@ OPTIONS = {
 ENV_IDS = {Scenario.PELICAN_CROSSING: "PelicanCrossing-v0", Scenario.BUS_STOP: "BusStop-v0", Scenario.CROSSROADS: "Crossroads-v0",
            Scenario.PEDESTRIANS: "Pedestrians-v0"}
 _HOST_ONLY = {AgentType.KEYBOARD: "the keyboard agent is interactive (render mode)",
-              AgentType.Q_LEARNING: "Q-learning agents update weights sequentially on the host",
-              AgentType.ELECTION: "the election tester is a host-side coordinator"}
+              AgentType.Q_LEARNING: "Q-learning agents update their weights on the host (ego: BatchedQLearningEgoAgent on the tensor API)",
+              AgentType.ELECTION: "the election tester is arbitrated on the host (examples/election.py)"}
+_UNAVAILABLE = {"ego": {AgentType.KEYBOARD: _HOST_ONLY[AgentType.KEYBOARD]},
+                "tester": {AgentType.Q_LEARNING: "the reference's Q-learning tester fails at its first process_feedback "
+                                                 "(pedestrian.py:128, 247: LinSpace * float), there is no behaviour to reproduce"}}
 
 
 @dataclass(frozen=True)
@@ -198,7 +205,7 @@ class Config:
 
     # ---- agents -------------------------------------------------------------------------------
     def _unsupported(self, agent_type):
-        raise NotImplementedError(f"agent option {agent_type.value!r} is not provided by cavgym_b200: {_HOST_ONLY[agent_type]}")
+        raise NotImplementedError(f"agent option {agent_type.value!r} has no on-device form in cavgym_b200: {_HOST_ONLY[agent_type]}")
 
     def agent_specs(self, bodies):
         """AgentSpec (on-device agent) per body, under the reference's compatibility rules (config.py:343-410):
@@ -206,9 +213,12 @@ class Config:
         from .library import bodies as body_lib
         from .scenario import AgentSpec
         ego, tester = self.ego_config, self.tester_config
-        if ego.agent in _HOST_ONLY:
+        if ego.agent is AgentType.Q_LEARNING:
+            specs = [AgentSpec("external")]   # the learner chooses the ego's action on the tensor API, every step
+        elif ego.agent in _HOST_ONLY:
             self._unsupported(ego.agent)
-        specs = [AgentSpec("noop") if ego.agent is AgentType.NOOP else AgentSpec("random", epsilon=ego.epsilon)]
+        else:
+            specs = [AgentSpec("noop") if ego.agent is AgentType.NOOP else AgentSpec("random", epsilon=ego.epsilon)]
         for body in bodies[1:]:
             if tester.agent in _HOST_ONLY:
                 self._unsupported(tester.agent)
@@ -228,7 +238,8 @@ class Config:
         """(np_seed, env, agents, keyboard_agent) like the reference: one RandomState seeds the env, the spawners and
         every tester agent, in agent-index order (config.py:275-415)."""
         from . import seeding
-        from .examples.agents.pedestrian import ProximityAgent, RandomConstrainedAgent
+        from .examples.agents.ego import QLearningEgoAgent
+        from .examples.agents.pedestrian import ElectionAgent, ProximityAgent, RandomConstrainedAgent
         from .examples.agents.template import NoopAgent, RandomAgent
         from .library import bodies as body_lib
         from .library.actions import TrafficLightAction
@@ -236,20 +247,24 @@ class Config:
         np_random, np_seed = seeding.np_random(self.seed)
         console.info(f"seed={np_seed}")
         if self.mode_config.mode is Mode.RENDER:
-            raise NotImplementedError("render mode (pyglet) is outside the batched stepping engine; use mode_config headless")
+            console.warning("render mode: cavgym_b200 has no viewer (pyglet is not part of the engine), running headless")
         env = self.make_env(np_random)
         console.info(f"bodies={pretty_str_list(body.__class__.__name__ for body in env.bodies)}")
         ego, tester = self.ego_config, self.tester_config
-        if ego.agent in _HOST_ONLY:
+        if ego.agent in _UNAVAILABLE["ego"]:
             self._unsupported(ego.agent)
         if ego.agent is AgentType.NOOP:
             agents = [NoopAgent(index=0, noop_action=env.bodies[0].noop_action)]
+        elif ego.agent is AgentType.Q_LEARNING:   # config.py:311-322: shares the env's RandomState, five throttle actions
+            agents = [QLearningEgoAgent(index=0, np_random=np_random, q_learning_config=ego, body=env.bodies[0],
+                                        time_resolution=env.time_resolution, width=env.constants.viewer_width,
+                                        height=env.constants.viewer_height, num_actions=5, num_opponents=len(env.bodies) - 1)]
         else:   # the reference builds the ego's RandomAgent WITHOUT the shared np_random (config.py:305-310)
             agents = [RandomAgent(index=0, noop_action=env.bodies[0].noop_action, epsilon=ego.epsilon)]
         road_centre = env.constants.road_map.major_road.bounding_box().longitudinal_line()
         for i, body in enumerate(env.bodies[1:], start=1):
-            if tester.agent in _HOST_ONLY:
-                self._unsupported(tester.agent)
+            if tester.agent in _UNAVAILABLE["tester"]:
+                raise NotImplementedError(f"tester option {tester.agent.value!r}: {_UNAVAILABLE['tester'][tester.agent]}")
             if isinstance(body, body_lib.DynamicBody):
                 pedestrian = isinstance(body, body_lib.Pedestrian)
                 if tester.agent is AgentType.NOOP:
@@ -262,6 +277,9 @@ class Config:
                 elif tester.agent is AgentType.PROXIMITY and pedestrian:
                     agent = ProximityAgent(index=i, body=body, time_resolution=env.time_resolution, road_centre=road_centre,
                                            distance_threshold=tester.threshold)
+                elif tester.agent is AgentType.ELECTION and pedestrian:
+                    agent = ElectionAgent(index=i, body=body, time_resolution=env.time_resolution, road_centre=road_centre,
+                                          distance_threshold=tester.threshold)
                 else:
                     raise NotImplementedError
             else:   # PelicanCrossing: with any other tester the reference re-appends the previous loop's agent (:397-410)

@@ -1,7 +1,9 @@
 """Pedestrian testers (reference examples/agents/pedestrian.py:14-116): the road-crossing state machine and its
 random / proximity triggers.  Host classes for the single-environment compat view; csrc/agents.cuh
-(choose_crossing_action, crossing_feedback) runs the same machine on the device.  ElectionAgent and the
-Q-learning tester are host-side learning/arbitration agents outside the batched hot path."""
+(choose_crossing_action, crossing_feedback) runs the same machine on the device.  ElectionAgent (arbitrated by
+examples/election.py) is host-side; the reference's Q-learning tester (pedestrian.py:119-251) cannot run — its first
+process_feedback multiplies the config's LinSpace object by a float (pedestrian.py:128, 247: TypeError; reproduced by
+oracle/gen_learning_golden.py) — so it is not mirrored and Config.setup says so."""
 import math
 
 from ...library.geometry import Point
@@ -71,3 +73,31 @@ class ProximityAgent(CrossingAgent):
 
     def device_spec(self):
         return AgentSpec("proximity", threshold=self.distance_threshold)
+
+
+class ElectionAgent(ProximityAgent):
+    """A ProximityAgent that only ASKS to cross (reference pedestrian.py:94-116): `voting` is raised on the step it would
+    start a crossing, `crossing` from then until the crossing state machine is idle again.  Election (examples/election.py)
+    lets one voter at a time carry its crossing out and resets the others."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.voting = self.crossing = False
+
+    def reset(self):
+        super().reset()
+        self.voting = self.crossing = False
+
+    def choose_action(self, state, action_space, info=None):
+        action, self.voting = self.choose_crossing_action(state, self.proximity_trigger(state))
+        self.crossing = self.crossing or self.voting
+        return action
+
+    def process_feedback(self, previous_state, action, state, reward):
+        super().process_feedback(previous_state, action, state, reward)
+        if self.idle():
+            self.crossing = False
+
+    def device_spec(self):
+        return None   # arbitration across agents happens on the host (examples/election.py)
+

@@ -12,11 +12,17 @@ from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
 from . import _abi
-from .library import bodies as body_lib
 
 AGENT_CODES = {"external": _abi.CAV_AGENT_EXTERNAL, "noop": _abi.CAV_AGENT_NOOP, "random": _abi.CAV_AGENT_RANDOM,
                "random-constrained": _abi.CAV_AGENT_RANDOM_CONSTRAINED, "proximity": _abi.CAV_AGENT_PROXIMITY}
 COLLISION_CODES = {"none": _abi.CAV_COLLISIONS_NONE, "ego": _abi.CAV_COLLISIONS_EGO, "all": _abi.CAV_COLLISIONS_ALL}
+
+
+def is_a(obj, *class_names):
+    """isinstance by CLASS NAME along the MRO: the compiler reads reference-style objects by the protocol the reference
+    defines (library/bodies.py class names and attributes), so bodies built from an unmodified copy of the reference's own
+    `library.bodies` compile exactly like the mirrors in cavgym_b200.library.bodies."""
+    return any(cls.__name__ in class_names for cls in type(obj).__mro__)
 
 
 @dataclass
@@ -62,7 +68,7 @@ def compile_scenario(bodies: Sequence, constants, env_config, agents: Optional[S
     if len(agents) != m:
         raise AssertionError("each body must be assigned an agent and vice versa")  # simulation.py:11
     ego = bodies[0]
-    if not isinstance(ego, body_lib.DynamicBody):
+    if not is_a(ego, "DynamicBody"):
         raise ValueError("the ego (bodies[0]) must be a DynamicBody")
 
     sc = _abi.CavScenario()
@@ -78,7 +84,7 @@ def compile_scenario(bodies: Sequence, constants, env_config, agents: Optional[S
 
     statics = []
     for body in bodies:  # environment.py:94-101
-        if isinstance(body, body_lib.PelicanCrossing):
+        if is_a(body, "PelicanCrossing"):
             statics += [body.outbound_traffic_light.bounding_box(), body.inbound_traffic_light.bounding_box()]
     if road_map.obstacle is not None:
         statics.append(road_map.obstacle.bounding_box())
@@ -99,13 +105,13 @@ def compile_scenario(bodies: Sequence, constants, env_config, agents: Optional[S
         row.agent = AGENT_CODES[agent.kind]
         row.agent_epsilon, row.agent_threshold = float(agent.epsilon), float(agent.threshold)
         row.spawn_id = -1
-        if isinstance(body, body_lib.PelicanCrossing):
+        if is_a(body, "PelicanCrossing"):
             row.kind = _abi.CAV_BODY_PELICAN
             row.init_state[:] = [float(body.init_state.value), 0.0, 0.0, 0.0]
             row.static_box = _quad(body.bounding_box())
             if agent.kind in ("random-constrained", "proximity"):
                 raise NotImplementedError("crossing agents need a Pedestrian body")  # config.py:358-396
-        elif isinstance(body, body_lib.DynamicBody):
+        elif is_a(body, "DynamicBody"):
             row.kind = _abi.CAV_BODY_DYNAMIC
             k = body.constants
             key = (k.length, k.width, k.wheelbase, k.min_velocity, k.max_velocity, k.min_throttle, k.max_throttle,
@@ -113,12 +119,12 @@ def compile_scenario(bodies: Sequence, constants, env_config, agents: Optional[S
             if key not in type_rows:
                 type_rows.append(key)
             row.type_id = type_rows.index(key)
-            if isinstance(body, body_lib.Pedestrian):
+            if is_a(body, "Pedestrian"):
                 row.flags |= _abi.CAV_FLAG_PEDESTRIAN
             elif agent.kind in ("random-constrained", "proximity"):
                 raise NotImplementedError("crossing agents need a Pedestrian body")  # config.py:358-396
             row.init_state[:] = [float(v) for v in body.init_state]
-            if isinstance(body, body_lib.SpawnPedestrian):
+            if is_a(body, "SpawnPedestrian"):
                 row.flags |= _abi.CAV_FLAG_SPAWN
                 sp = body.spawn_init_state
                 if not 1 <= len(sp.position_boxes) <= _abi.CAV_MAX_SPAWN_BOXES or not 1 <= len(sp.orientations) <= _abi.CAV_MAX_SPAWN_ORIENT:

@@ -15,11 +15,13 @@ from .config import AgentType, Mode
 class Simulation:
     def __init__(self, env, agents, config, keyboard_agent=None):
         assert len(env.bodies) == len(agents), "each body must be assigned an agent and vice versa"
-        if keyboard_agent is not None or config.mode_config.mode is Mode.RENDER:
-            raise NotImplementedError("render mode / keyboard agents are outside the batched stepping engine")
-        if config.tester_config.agent is AgentType.ELECTION:
-            raise NotImplementedError("the election tester is not provided by cavgym_b200")
+        if keyboard_agent is not None:
+            raise NotImplementedError("keyboard agents need the reference's pyglet viewer")
         self.env, self.agents, self.config = env, agents, config
+        self.election = None
+        if config.tester_config.agent is AgentType.ELECTION:   # simulation.py:20-23
+            from .examples.election import Election
+            self.election = Election(env, agents)
         self.console = reporting.get_console(config.verbosity)
         self.episode_file = reporting.get_episode_file_logger(config.episode_log) if config.episode_log is not None else None
         self.run_file = reporting.get_run_file_logger(config.run_log) if config.run_log is not None else None
@@ -39,6 +41,8 @@ class Simulation:
             final_timestep = config.max_timesteps
             for timestep in range(1, config.max_timesteps + 1):
                 joint_action = [agent.choose_action(state, space, info) for agent, space in zip(agents, env.action_space)]
+                if self.election:
+                    joint_action = self.election.result(state, joint_action)
                 previous_state = state
                 state, joint_reward, done, info = env.step(joint_action)
                 self.console.debug(f"timestep={timestep}")
@@ -71,6 +75,34 @@ class BatchedSimulation:
         self.console = reporting.get_console(config.verbosity)
         self.run_file = reporting.get_run_file_logger(config.run_log) if config.run_log is not None else None
 
+    def _learner(self):
+        """The Q-learning ego on the tensor API (config.json's stock ego option), or None when every agent is on the device."""
+        if self.config.ego_config.agent is not AgentType.Q_LEARNING:
+            return None
+        from .examples.agents.ego import BatchedQLearningEgoAgent
+        env = self.env
+        self.learner = BatchedQLearningEgoAgent(self.config.ego_config, env.bodies[0].constants, env.time_resolution, env.num_bodies - 1,
+                                                env.constants.viewer_width, env.constants.viewer_height, env.num_envs, env.device,
+                                                dtype=env.dtype, seed=self.config.seed or 0)
+        return self.learner
+
+    def _learning_steps(self, learner, n_steps):
+        """Simulation.run's timestep loop (simulation.py:69-93) with the ego's action chosen by the learner: choose on the
+        pre-step state, one cavgym_step (testers act on the device), TD update on the transition, reset of the envs that
+        finished (their episode was scored by the step kernel)."""
+        import torch
+        env = self.env
+        if not hasattr(self, "_joint"):
+            self._joint = torch.zeros((env.num_bodies, 2, env.num_envs), dtype=env.dtype, device=env.device)
+            self._previous = torch.empty_like(env.state)
+        for _ in range(n_steps):
+            self._previous.copy_(env.state)
+            index, rows = learner.choose_action(self._previous)
+            self._joint[0] = rows
+            state, reward, _, _, _ = env.step(self._joint)
+            learner.process_feedback(self._previous, index, state, reward[0])
+            env.reset(mask=env.done_latch != 0)
+
     def run(self, episodes=None, reduce=True):
         """Rolls every env forward (auto-reset) until at least `episodes` (default: config.episodes) episodes have finished
         on this rank; returns the RunSummary of everything finished so far (summed over ranks when a process group is up)."""
@@ -81,8 +113,12 @@ class BatchedSimulation:
         env.reset()
         self.steps_run = 0
         start = timeit.default_timer()
+        learner = self._learner()
         while True:
-            env.rollout(self.chunk, auto_reset=True)
+            if learner is None:
+                env.rollout(self.chunk, auto_reset=True)
+            else:
+                self._learning_steps(learner, self.chunk)
             self.steps_run += self.chunk
             stats = env.stats()          # synchronises
             if stats["episodes"] >= target:

@@ -106,8 +106,10 @@ def _state_row(body_state):
     return row + [0.0] * (4 - len(row))  # PelicanCrossing state = [TrafficLightState]
 
 
-def record(config_dict, max_draws=3):
-    """Run the reference on `config_dict`; return (meta, [episode dicts of numpy arrays])."""
+def record(config_dict, max_draws=3, extra=None):
+    """Run the reference on `config_dict`; return (meta, [episode dicts of numpy arrays]).
+    `extra(env, agents, simulation)` (optional) returns a flat list of floats sampled after the LAST agent's
+    process_feedback of every step (learning weights, election flags ...): stored as `extra` [T, K]."""
     mods = refload.load()
     from gym.utils import seeding
 
@@ -136,11 +138,12 @@ def record(config_dict, max_draws=3):
     n_bodies = len(env.bodies)
     episodes = []
     current = {}
+    holder = {}
 
     def begin_episode(state, spawn_draws, t_global):
         current.clear()
         current.update(init_state=[_state_row(s) for s in state], spawn_draws=spawn_draws, t_global_start=t_global,
-                       actions=[], state=[], reward=[], done=[], winner=[], liveness=[], draws=[], agent_state=[])
+                       actions=[], state=[], reward=[], done=[], winner=[], liveness=[], draws=[], agent_state=[], extra=[])
 
     pending_draws = [[NAN] * max_draws for _ in range(n_bodies)]
 
@@ -162,6 +165,8 @@ def record(config_dict, max_draws=3):
         def process_feedback(previous_state, action, state, reward):
             feedback(previous_state, action, state, reward)
             current["agent_state"][-1][index] = _agent_state(agent)
+            if extra is not None and index == n_bodies - 1:
+                current["extra"].append([float(v) for v in extra(env, agents, holder["simulation"])])
 
         agent.choose_action = choose_action
         agent.process_feedback = process_feedback
@@ -192,7 +197,8 @@ def record(config_dict, max_draws=3):
         return state, joint_reward, done, info
 
     env.reset, env.step = reset, step
-    mods["simulation"].Simulation(env, agents, config=cfg, keyboard_agent=keyboard_agent).run()
+    holder["simulation"] = mods["simulation"].Simulation(env, agents, config=cfg, keyboard_agent=keyboard_agent)
+    holder["simulation"].run()
     episodes.append({k: v for k, v in current.items()})
 
     bodies_mod = mods["bodies"]
@@ -218,6 +224,8 @@ def record(config_dict, max_draws=3):
             "draws": np.asarray(ep["draws"], dtype=np.float64),
             "agent_state": np.asarray(ep["agent_state"], dtype=np.float64),
         }
+        if extra is not None:
+            arrays["extra"] = np.asarray(ep["extra"], dtype=np.float64)
         out.append(arrays)
     return meta, out
 

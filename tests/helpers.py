@@ -8,7 +8,8 @@ import numpy as np
 from cavgym_b200.scenario import AgentSpec, compile_scenario
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f != "geometry_kat.npz" and not f.startswith("info_"))
+GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f != "geometry_kat.npz" and not f.startswith(("info_", "learn_")))
+LEARN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("learn_") and f.endswith(".npz"))   # oracle/gen_learning_golden.py
 
 
 def load_golden(name):

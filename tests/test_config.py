@@ -81,10 +81,12 @@ def test_agent_specs_follow_the_reference_compatibility_rules():
         cfg.make_config(stock(scenario_config={"option": "bus-stop"})).agent_specs(bus_stop.make_bodies())
     specs = cfg.make_config(stock(scenario_config={"option": "pelican-crossing"}, tester_config={"option": "random", "epsilon": 0.1})).agent_specs(pelican_crossing.make_bodies())
     assert all(s.kind == "random" for s in specs[1:])
-    for option in (Q_LEARNING, {"option": "keyboard"}):
-        with pytest.raises(NotImplementedError, match="not provided"):
-            cfg.make_config(stock(ego_config=option, mode_config={"option": "render", "episode_condition": 1, "video_dir": None})).agent_specs(peds)
-    with pytest.raises(NotImplementedError, match="not provided"):
+    render = {"option": "render", "episode_condition": 1, "video_dir": None}
+    specs = cfg.make_config(stock(ego_config=Q_LEARNING, mode_config=render)).agent_specs(peds)
+    assert specs[0].kind == "external"       # the tensor-API learner supplies the ego's action; testers stay on the device
+    with pytest.raises(NotImplementedError, match="no on-device form"):
+        cfg.make_config(stock(ego_config={"option": "keyboard"}, mode_config=render)).agent_specs(peds)
+    with pytest.raises(NotImplementedError, match="no on-device form"):   # arbitrated on the host (examples/election.py)
         cfg.make_config(stock(tester_config={"option": "election", "threshold": 5.0})).agent_specs(peds)
 
 
