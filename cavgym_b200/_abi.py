@@ -46,6 +46,11 @@ class CavBody(C.Structure):
                 ("agent_threshold", C.c_double), ("init_state", C.c_double * 4), ("static_box", CavQuad)]
 
 
+class CavEpisodeRow(C.Structure):
+    _fields_ = [("env", C.c_int64), ("episode", C.c_int32), ("timesteps", C.c_int32), ("winner", C.c_int32),
+                ("liveness_sum", C.c_int32)]
+
+
 class CavScenario(C.Structure):
     _fields_ = [("n_bodies", C.c_int32), ("n_types", C.c_int32), ("n_roads", C.c_int32), ("n_statics", C.c_int32),
                 ("n_spawns", C.c_int32), ("terminate_collisions", C.c_int32), ("terminate_ego_zones", C.c_int32),
@@ -71,8 +76,11 @@ PROTOTYPES = {
     "cavgym_rollout": (C.c_int, [c_engine_p, C.c_int, C.c_int, c_stream]),
     "cavgym_replay": (C.c_int, [c_engine_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_stream]),
     "cavgym_step_host": (C.c_int, [c_engine_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cavgym_reset_host": (C.c_int, [c_engine_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cavgym_info": (C.c_int, [c_engine_p, C.c_void_p, C.c_void_p, c_stream]),
     "cavgym_stats": (C.c_int, [c_engine_p, C.POINTER(C.c_int64)]),
+    "cavgym_set_episode_log": (C.c_int, [c_engine_p, C.c_int64]),
+    "cavgym_drain_episodes": (C.c_int, [c_engine_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cavgym_error_count": (C.c_int, [c_engine_p, C.POINTER(C.c_int64)]),
     "cavgym_launch_count": (C.c_int, [c_engine_p, C.POINTER(C.c_int64)]),
     "cavgym_state_ptr": (C.c_void_p, [c_engine_p]),

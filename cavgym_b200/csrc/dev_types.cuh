@@ -115,6 +115,10 @@ struct EnvBuffers {
   const double* uni_override;    // [M][3][N] or null
   const double* spawn_override;  // [M][5][N] or null
   int32_t log_actions;           // store every on-device agent's action in `action` (default: RandomAgent only)
+  // per-episode rows (reporting.py:157-158 episode.log), appended by score_episode when enabled (cavgym_set_episode_log)
+  CavEpisodeRow* ep_log;              // [ep_log_capacity] or null
+  unsigned long long* ep_log_count;   // rows appended since the last drain (may exceed the capacity: the excess was dropped)
+  int64_t ep_log_capacity;
 };
 
 template <typename R>

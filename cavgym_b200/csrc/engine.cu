@@ -409,6 +409,12 @@ struct CavEngine {
   // host-buffer pipeline (cavgym_step_host)
   static constexpr int kPipe = 3;
   cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr};
+  bool host_ready = false;        // streams and staging buffers of the host-buffer entry points all exist
+  bool caller_work_pending = true;   // a call queued work on a caller stream since the last host-buffer call synchronised
+  const void* host_seen[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // caller buffers of the last zero-copy call ...
+  void* host_mapped[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};       // ... and their device addresses
+  void* d_init = nullptr;         // staging for cavgym_reset_host's init_state / mask
+  uint8_t* d_mask = nullptr;
   void *d_actions = nullptr, *d_reward = nullptr;
   uint8_t *d_done = nullptr, *d_tangent = nullptr;
   int32_t* d_winner = nullptr;
@@ -491,6 +497,7 @@ static int launch_check(CavEngine* eng, const char* what, int n_launches = 1) {
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(CAV_ECUDA, std::string(what) + ": " + cudaGetErrorString(err));
   eng->launches += n_launches;
+  eng->caller_work_pending = true;
   return CAV_OK;
 }
 
@@ -564,6 +571,14 @@ int cavgym_create(const CavScenario* tables, int64_t n_envs, int dtype, int devi
   if (tables->n_roads < 1 || tables->n_roads > CAV_MAX_ROADS || tables->n_statics < 0 || tables->n_statics > CAV_MAX_STATICS ||
       tables->n_types < 0 || tables->n_types > CAV_MAX_TYPES)
     return fail(CAV_EINVAL, "road/static/type counts out of range");
+  if (tables->n_spawns < 0 || (tables->n_spawns > 0 && !tables->spawns)) return fail(CAV_EINVAL, "n_spawns < 0 or spawns is NULL");
+  for (int k = 0; k < tables->n_spawns; ++k) {   // spawn_body indexes fixed arrays with these counts
+    const CavSpawn& sp = tables->spawns[k];
+    if (sp.n_boxes < 1 || sp.n_boxes > CAV_MAX_SPAWN_BOXES || sp.n_orientations < 1 || sp.n_orientations > CAV_MAX_SPAWN_ORIENT)
+      return fail(CAV_EINVAL, "spawn n_boxes / n_orientations out of range");
+  }
+  if (!(tables->time_resolution > 0) || !(tables->viewer_width > 0)) return fail(CAV_EINVAL, "time_resolution and viewer_width must be > 0");
+  if (tables->max_timesteps < 1) return fail(CAV_EINVAL, "max_timesteps must be >= 1");
   if (tables->bodies[0].kind != CAV_BODY_DYNAMIC) return fail(CAV_EINVAL, "the ego (body 0) must be a dynamic body");
   for (int b = 0; b < tables->n_bodies; ++b) {
     const CavBody& body = tables->bodies[b];
@@ -720,6 +735,28 @@ int cavgym_replay(CavEngine* eng, int n_steps, const void* actions, void* state_
   return CAV_OK;
 }
 
+// Streams and staging buffers of the host-buffer entry points, created on first use.  `host_ready` is only set once every
+// allocation has succeeded; a failure part-way leaves the pieces on eng->allocations (freed by cavgym_destroy) and the
+// next call starts over instead of running with null staging pointers.
+static int host_setup(CavEngine* eng) {
+  if (eng->host_ready) return CAV_OK;
+  int rc = CAV_OK;
+  const int64_t n = eng->n, m = eng->m;
+  const size_t rs = eng->real_size();
+  for (auto& s : eng->pipe)
+    if (!s) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, (size_t)m * 2 * n * rs)); eng->allocations.push_back(p); eng->d_actions = p;
+  CUDA_TRY(cudaMalloc(&p, (size_t)m * n * rs)); eng->allocations.push_back(p); eng->d_reward = p;
+  CUDA_TRY(cudaMalloc(&p, (size_t)m * 4 * n * rs)); eng->allocations.push_back(p); eng->d_init = p;
+  if ((rc = dev_alloc(eng, &eng->d_done, (size_t)n))) return rc;
+  if ((rc = dev_alloc(eng, &eng->d_tangent, (size_t)n))) return rc;
+  if ((rc = dev_alloc(eng, &eng->d_winner, (size_t)n))) return rc;
+  if ((rc = dev_alloc(eng, &eng->d_mask, (size_t)n))) return rc;
+  eng->host_ready = true;
+  return CAV_OK;
+}
+
 // Host buffers: env range split into chunks, each chunk's H2D copy -> kernel -> D2H copies queued on one of
 // kPipe streams so that copies of one chunk overlap the kernel and copies of the others (PCIe is full duplex).
 int cavgym_step_host(CavEngine* eng, const void* actions, void* state_out, void* reward_out, uint8_t* done_out,
@@ -729,16 +766,10 @@ int cavgym_step_host(CavEngine* eng, const void* actions, void* state_out, void*
   if (!actions && eng->has_external) return fail(CAV_EINVAL, "actions is NULL but a body has CAV_AGENT_EXTERNAL");
   const int64_t n = eng->n, m = eng->m;
   const size_t rs = eng->real_size();
-  if (!eng->pipe[0]) {
-    for (auto& s : eng->pipe) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    void* p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, (size_t)m * 2 * n * rs)); eng->allocations.push_back(p); eng->d_actions = p;
-    CUDA_TRY(cudaMalloc(&p, (size_t)m * n * rs)); eng->allocations.push_back(p); eng->d_reward = p;
-    if ((rc = dev_alloc(eng, &eng->d_done, (size_t)n))) return rc;
-    if ((rc = dev_alloc(eng, &eng->d_tangent, (size_t)n))) return rc;
-    if ((rc = dev_alloc(eng, &eng->d_winner, (size_t)n))) return rc;
-  }
-  CUDA_TRY(cudaDeviceSynchronize());  // order after whatever the caller queued on other streams
+  if ((rc = host_setup(eng))) return rc;
+  // Order after whatever the caller queued on its own streams (a reset on torch's stream, say) — only when some call has
+  // queued such work since this entry point last synchronised: back-to-back host steps pay no device-wide synchronise.
+  if (eng->caller_work_pending) CUDA_TRY(cudaDeviceSynchronize());
 
   // Zero-copy path: when every caller buffer is pinned (page-locked, mapped) host memory, the step kernel reads the
   // actions and writes the results over PCIe itself — the TMA producer warp's bulk copies take host addresses just as
@@ -746,20 +777,27 @@ int cavgym_step_host(CavEngine* eng, const void* actions, void* state_out, void*
   // instead of a chain of chunked cudaMemcpyAsync calls whose launch overheads dominate at this batch size.
   if (eng->zero_copy_host) {
     const void* host[6] = {actions, state_out, reward_out, done_out, winner_out, tangent_flag_out};
-    void* dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool all_mapped = true;
-    for (int i = 0; i < 6 && all_mapped; ++i) {
-      if (!host[i]) continue;
-      cudaPointerAttributes attr;
-      if (cudaPointerGetAttributes(&attr, host[i]) != cudaSuccess) { cudaGetLastError(); all_mapped = false; break; }
-      if (attr.type == cudaMemoryTypeHost && attr.devicePointer) dev[i] = attr.devicePointer;
-      else all_mapped = false;
+    if (memcmp(host, eng->host_seen, sizeof(host)) != 0) {   // new buffers: ask the driver once, remember the answer
+      for (int i = 0; i < 6; ++i) eng->host_seen[i] = nullptr;
+      void* dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+      for (int i = 0; i < 6 && all_mapped; ++i) {
+        if (!host[i]) continue;
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, host[i]) != cudaSuccess) { cudaGetLastError(); all_mapped = false; break; }
+        if (attr.type == cudaMemoryTypeHost && attr.devicePointer) dev[i] = attr.devicePointer;
+        else all_mapped = false;
+      }
+      if (all_mapped)
+        for (int i = 0; i < 6; ++i) { eng->host_seen[i] = host[i]; eng->host_mapped[i] = dev[i]; }
     }
     if (all_mapped) {
+      void** dev = eng->host_mapped;
       cudaStream_t s = eng->pipe[0];
       rc = step_range(eng, 0, n, dev[0], dev[1], dev[2], (uint8_t*)dev[3], (int32_t*)dev[4], (uint8_t*)dev[5], s);
       if (rc) return rc;
       CUDA_TRY(cudaStreamSynchronize(s));
+      eng->caller_work_pending = false;
       eng->t_global += 1;
       return CAV_OK;
     }
@@ -787,7 +825,30 @@ int cavgym_step_host(CavEngine* eng, const void* actions, void* state_out, void*
     if (tangent_flag_out) CUDA_TRY(cudaMemcpyAsync(tangent_flag_out + lo, eng->d_tangent + lo, w, cudaMemcpyDeviceToHost, s));
   }
   for (auto& s : eng->pipe) CUDA_TRY(cudaStreamSynchronize(s));
+  eng->caller_work_pending = false;
   eng->t_global += 1;
+  return CAV_OK;
+}
+
+// CAVEnv.reset with HOST buffers (the host-buffer twin of cavgym_reset, for callers that hold no device memory):
+// mask u8[N] and init_state real[M][4][N] are copied in (each nullable), the post-reset state is copied out (nullable).
+int cavgym_reset_host(CavEngine* eng, const uint8_t* mask, const void* init_state, void* state_out) {
+  int rc = check_engine(eng);
+  if (rc) return rc;
+  if ((rc = host_setup(eng))) return rc;
+  if (eng->caller_work_pending) CUDA_TRY(cudaDeviceSynchronize());
+  const size_t state_bytes = (size_t)eng->m * 4 * eng->n * eng->real_size();
+  cudaStream_t s = eng->pipe[0];
+  if (mask) CUDA_TRY(cudaMemcpyAsync(eng->d_mask, mask, (size_t)eng->n, cudaMemcpyHostToDevice, s));
+  if (init_state) CUDA_TRY(cudaMemcpyAsync(eng->d_init, init_state, state_bytes, cudaMemcpyHostToDevice, s));
+  rc = do_reset(eng, mask ? eng->d_mask : nullptr, init_state ? eng->d_init : nullptr, 0, s);
+  if (rc) return rc;
+  if (state_out) {
+    const void* d_state = eng->dtype == CAV_F64 ? (const void*)eng->buf64.state : (const void*)eng->buf32.state;
+    CUDA_TRY(cudaMemcpyAsync(state_out, d_state, state_bytes, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  eng->caller_work_pending = false;
   return CAV_OK;
 }
 
@@ -826,6 +887,49 @@ int cavgym_stats(CavEngine* eng, int64_t* out10 /* [CAV_N_STATS] */) {
   out10[CAV_STAT_ENV_STEPS] = (int64_t)(raw[CAV_STAT_SUM_T] + raw[CAV_STAT_ENV_STEPS] + extra[0]);
   out10[CAV_STAT_BODY_STEPS] = out10[CAV_STAT_ENV_STEPS] * eng->m;
   out10[CAV_STAT_ERRORS] = (int64_t)extra[1];
+  return CAV_OK;
+}
+
+int cavgym_set_episode_log(CavEngine* eng, int64_t capacity) {
+  int rc = check_engine(eng);
+  if (rc) return rc;
+  if (capacity < 0) return fail(CAV_EINVAL, "capacity must be >= 0");
+  CUDA_TRY(cudaDeviceSynchronize());   // kernels in flight carry the old ring in their parameters
+  CavEpisodeRow* rows = nullptr;
+  unsigned long long* count = eng->dtype == CAV_F64 ? eng->buf64.ep_log_count : eng->buf32.ep_log_count;
+  if (capacity > 0) {
+    if ((rc = dev_alloc(eng, &rows, (size_t)capacity, false))) return rc;
+    if (!count && (rc = dev_alloc(eng, &count, 1))) return rc;
+    CUDA_TRY(cudaMemset(count, 0, sizeof(*count)));
+  }
+  for (int k = 0; k < 2; ++k) {   // both typed views of the buffers carry the ring
+    CavEpisodeRow*& r = k ? eng->buf32.ep_log : eng->buf64.ep_log;
+    (k ? eng->buf32.ep_log_count : eng->buf64.ep_log_count) = count;
+    (k ? eng->buf32.ep_log_capacity : eng->buf64.ep_log_capacity) = capacity;
+    r = rows;
+  }
+  return CAV_OK;
+}
+
+int cavgym_drain_episodes(CavEngine* eng, CavEpisodeRow* out, int64_t max_rows, int64_t* n_rows, int64_t* dropped) {
+  int rc = check_engine(eng);
+  if (rc) return rc;
+  if (!n_rows || max_rows < 0 || (max_rows > 0 && !out)) return fail(CAV_EINVAL, "bad argument");
+  *n_rows = 0;
+  if (dropped) *dropped = 0;
+  const CavEpisodeRow* rows = eng->dtype == CAV_F64 ? eng->buf64.ep_log : eng->buf32.ep_log;
+  unsigned long long* count = eng->dtype == CAV_F64 ? eng->buf64.ep_log_count : eng->buf32.ep_log_count;
+  const int64_t capacity = eng->dtype == CAV_F64 ? eng->buf64.ep_log_capacity : eng->buf32.ep_log_capacity;
+  if (!rows) return fail(CAV_ESTATE, "the episode log is off (cavgym_set_episode_log)");
+  CUDA_TRY(cudaDeviceSynchronize());
+  unsigned long long appended = 0;
+  CUDA_TRY(cudaMemcpy(&appended, count, sizeof(appended), cudaMemcpyDeviceToHost));
+  const int64_t held = (int64_t)appended < capacity ? (int64_t)appended : capacity;
+  const int64_t take = held < max_rows ? held : max_rows;
+  if (take > 0) CUDA_TRY(cudaMemcpy(out, rows, (size_t)take * sizeof(CavEpisodeRow), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemset(count, 0, sizeof(*count)));
+  *n_rows = take;
+  if (dropped) *dropped = (int64_t)appended - take;
   return CAV_OK;
 }
 
@@ -899,8 +1003,10 @@ int cavgym_set_global_timestep(CavEngine* eng, int64_t t) {
 }
 
 int cavgym_set_tangent_tolerance(CavEngine* eng, double tau) {
-  if (!eng) return fail(CAV_EINVAL, "engine is NULL");
+  int rc = check_engine(eng);
+  if (rc) return rc;
   if (!(tau >= 0)) return fail(CAV_EINVAL, "tau must be >= 0");
+  CUDA_TRY(cudaDeviceSynchronize());   // the device tables are rewritten: no kernel of this engine may still be reading them
   eng->tau = tau;
   return rebuild_tables(eng);
 }

@@ -714,7 +714,11 @@ __device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const
     long long sum = 0;
     for (int b = lane; b < M; b += 32) if (b > 0) sum += buf.liveness[(int64_t)b * n + e];
     sum = (long long)warp_sum((unsigned long long)sum);
-    if (lane == 0) score_episode<R, 1>(buf.stats, env.t_ep, env.winner, sum);
+    if (lane == 0) {
+      EpisodeLog log{buf.ep_log, buf.ep_log_count, buf.ep_log_capacity, buf.shard + e, env.episode};
+      if (buf.ep_log && !AGENTS) log.episode = buf.episode[e];
+      score_episode<R, 1>(buf.stats, env.t_ep, env.winner, sum, log);
+    }
   }
 }
 

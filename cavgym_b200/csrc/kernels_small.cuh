@@ -139,7 +139,7 @@ __device__ __forceinline__ bool advance(const DevScenario<R>& sc, const EnvBuffe
     if (res.invalid) buf.err[e] = 1;
     if (res.tangent) count_tangent(buf.stats);
     if (env.done) {
-      score_episode<R, M>(buf, env);
+      score_episode<R, M>(buf, env, e, AGENTS ? env.episode : -1);
       ended = true;
     }
   }

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kStepTile + 32, CAV_MIN_BLOCKS_TMA) step_tma_k
         if (res.invalid) buf.err[e] = 1;
         if (res.tangent) count_tangent(buf.stats);
         if (env.done) {
-          score_episode<R, M>(buf, env);
+          score_episode<R, M>(buf, env, e);
           buf.done[e] = env.done;
           buf.winner[e] = env.winner;
         }
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
         transition<R, M, false, GENERIC>(sc, buf, e, t_global + t, env, ext, res);
         if (res.invalid) buf.err[e] = 1;
         if (res.tangent) count_tangent(buf.stats);
-        if (env.done) score_episode<R, M>(buf, env);
+        if (env.done) score_episode<R, M>(buf, env, e);
       }
     }
     // the stage's output rows are free once the stores of the step that used it last have read them

@@ -192,8 +192,16 @@ __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBu
 // reporting.analyse_episode (reporting.py:227-243) for an env whose episode just ended.  The lanes of a warp that end their
 // episodes in the same step (with a Noop ego EVERY env reaches the finish line at step 901 at once) first add up their
 // contributions, so the ten global counters see one atomic per warp and counter instead of one per env.
+struct EpisodeLog {
+  CavEpisodeRow* rows;
+  unsigned long long* count;
+  int64_t capacity, env;   // env = global id of the env that finished
+  int32_t episode;         // its per-env episode number (1 = the first episode after cavgym_create)
+};
+
 template <typename R, int M>
-__device__ __noinline__ void score_episode(unsigned long long* stats, int32_t t_ep, int32_t winner, long long liveness_sum) {
+__device__ __noinline__ void score_episode(unsigned long long* stats, int32_t t_ep, int32_t winner, long long liveness_sum,
+                                           const EpisodeLog log) {
   namespace cg = cooperative_groups;
   const cg::coalesced_group lanes = cg::coalesced_threads();
   const unsigned long long t = (unsigned long long)t_ep;
@@ -210,6 +218,7 @@ __device__ __noinline__ void score_episode(unsigned long long* stats, int32_t t_
     sum_it = cg::reduce(lanes, interesting ? t : 0ull, add);
     sum_it2 = cg::reduce(lanes, interesting ? t * t : 0ull, add);
   }
+  unsigned long long slot = 0;
   if (lanes.thread_rank() == 0) {
     atomicAdd(&stats[CAV_STAT_EPISODES], n_eps);
     atomicAdd(&stats[CAV_STAT_SUM_T], sum_t);
@@ -221,15 +230,23 @@ __device__ __noinline__ void score_episode(unsigned long long* stats, int32_t t_
       atomicAdd(&stats[CAV_STAT_SUM_T_INTERESTING], sum_it);
       atomicAdd(&stats[CAV_STAT_SUM_T2_INTERESTING], sum_it2);
     }
+    if (log.rows) slot = atomicAdd(log.count, n_eps);   // one reservation for all the rows of this warp
+  }
+  if (log.rows) {   // the reporting.EpisodeResults of this episode, one 24-byte row (file_message, reporting.py:157-158)
+    slot = lanes.shfl(slot, 0) + lanes.thread_rank();
+    if (slot < (unsigned long long)log.capacity) log.rows[slot] = {log.env, log.episode, t_ep, winner, (int32_t)liveness_sum};
   }
 }
 
+// `episode` = the env's episode number if the kernel carries it in registers (on-device agents), else -1: read it back.
 template <typename R, int M>
-__device__ __forceinline__ void score_episode(const EnvBuffers<R>& buf, const EnvRegs<R, M>& env) {
+__device__ __forceinline__ void score_episode(const EnvBuffers<R>& buf, const EnvRegs<R, M>& env, int64_t e, int32_t episode = -1) {
   long long sum = 0;
 #pragma unroll
   for (int b = 1; b < M; ++b) sum += env.live[b];
-  score_episode<R, M>(buf.stats, env.t_ep, env.winner, sum);
+  EpisodeLog log{buf.ep_log, buf.ep_log_count, buf.ep_log_capacity, buf.shard + e, episode};
+  if (buf.ep_log && episode < 0) log.episode = buf.episode[e];
+  score_episode<R, M>(buf.stats, env.t_ep, env.winner, sum, log);
 }
 
 // CAVEnv.reset for one env (environment.py:225-229): bodies back to init_state (SpawnPedestrians re-drawn),

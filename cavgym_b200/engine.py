@@ -114,6 +114,10 @@ class BatchedCAVEnv:
         engine's own buffer (zero copy) unless `copy_state` is a [M,4,N] tensor to receive a snapshot."""
         n, m = self.num_envs, self.num_bodies
         actions_t = self._as_real(actions, (m, 2, n), "actions")
+        if copy_state is not None:   # written by the kernel through a raw pointer: it must be exactly the engine's layout
+            if not (isinstance(copy_state, torch.Tensor) and copy_state.device == self.device and copy_state.dtype == self.dtype
+                    and tuple(copy_state.shape) == (m, 4, n) and copy_state.is_contiguous()):
+                raise ValueError(f"copy_state must be a contiguous {self.dtype} tensor of shape {(m, 4, n)} on {self.device}")
         _native.check(self._lib.cavgym_step(self._handle, _ptr(actions_t), _ptr(copy_state), _ptr(self.reward), _ptr(self.done),
                                             _ptr(self.winner), _ptr(self.tangent), self._stream()))
         return (self.state if copy_state is None else copy_state), self.reward, self.done, self.winner, self.tangent
@@ -140,12 +144,30 @@ class BatchedCAVEnv:
                                               _ptr(out["done"]), _ptr(out["winner"]), _ptr(out["tangent"]), self._stream()))
         return out
 
+    def _host_buffer(self, array, shape, dtype, name):
+        """Raw host pointer of a numpy array / CPU tensor after checking it is what the kernel will read or write."""
+        if array is None:
+            return None
+        if isinstance(array, torch.Tensor):
+            ok = array.device.type == "cpu" and array.dtype == dtype and tuple(array.shape) == tuple(shape) and array.is_contiguous()
+            address = array.data_ptr()
+        else:
+            want = np.dtype({torch.float64: "f8", torch.float32: "f4", torch.uint8: "u1", torch.int32: "i4"}[dtype])
+            ok = isinstance(array, np.ndarray) and array.dtype == want and array.shape == tuple(shape) and array.flags.c_contiguous
+            address = array.ctypes.data if ok else 0
+        if not ok:
+            raise ValueError(f"{name} must be a contiguous host array of shape {tuple(shape)} and dtype {dtype}")
+        return C.c_void_p(address)
+
     def step_host(self, actions, state_out=None, reward_out=None, done_out=None, winner_out=None, tangent_out=None):
-        """cavgym_step_host: numpy (ideally pinned) host buffers in and out, copies pipelined with the kernel."""
-        def hp(a):
-            return None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
-        _native.check(self._lib.cavgym_step_host(self._handle, hp(actions), hp(state_out), hp(reward_out), hp(done_out),
-                                                 hp(winner_out), hp(tangent_out)))
+        """cavgym_step_host: host buffers in and out (numpy arrays or CPU tensors in the engine's layout).  Pinned buffers
+        (tensor.pin_memory()) are read and written by the step kernel itself over PCIe; pageable ones are staged."""
+        n, m = self.num_envs, self.num_bodies
+        _native.check(self._lib.cavgym_step_host(
+            self._handle, self._host_buffer(actions, (m, 2, n), self.dtype, "actions"),
+            self._host_buffer(state_out, (m, 4, n), self.dtype, "state_out"), self._host_buffer(reward_out, (m, n), self.dtype, "reward_out"),
+            self._host_buffer(done_out, (n,), torch.uint8, "done_out"), self._host_buffer(winner_out, (n,), torch.int32, "winner_out"),
+            self._host_buffer(tangent_out, (n,), torch.uint8, "tangent_out")))
 
     def info(self, polygons=True, road_angles=True):
         """CAVEnv.info() for every env: {'body_polygons': [M, 8, N] (x of the four corners, then y), 'road_angles': [M, N]
@@ -161,6 +183,22 @@ class BatchedCAVEnv:
         out = (C.c_int64 * _abi.CAV_N_STATS)()
         _native.check(self._lib.cavgym_stats(self._handle, out))
         return dict(zip(_abi.STAT_NAMES, [int(v) for v in out]))
+
+    def set_episode_log(self, capacity):
+        """Keep a device ring of `capacity` per-episode rows (0: off); see drain_episodes."""
+        _native.check(self._lib.cavgym_set_episode_log(self._handle, int(capacity)))
+        self._episode_capacity = int(capacity)
+
+    def drain_episodes(self):
+        """(rows, dropped): the episodes scored since the last drain as a numpy structured array with the fields of
+        CavEpisodeRow (env, episode, timesteps, winner, liveness_sum), in the order they finished, and how many rows a
+        full ring lost."""
+        capacity = getattr(self, "_episode_capacity", 0)
+        rows = np.zeros(capacity, dtype=np.dtype([("env", "<i8"), ("episode", "<i4"), ("timesteps", "<i4"), ("winner", "<i4"),
+                                                  ("liveness_sum", "<i4")]))
+        n_rows, dropped = C.c_int64(), C.c_int64()
+        _native.check(self._lib.cavgym_drain_episodes(self._handle, C.c_void_p(rows.ctypes.data), capacity, C.byref(n_rows), C.byref(dropped)))
+        return rows[:n_rows.value], int(dropped.value)
 
     def launch_count(self):
         out = C.c_int64()

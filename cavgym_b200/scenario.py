@@ -44,6 +44,15 @@ class CompiledScenario:
     def pointer(self):
         return C.byref(self.struct)
 
+    def tables(self):
+        """The scenario as position-independent bytes: the CavScenario header with its two pointers blanked, the body
+        rows and the spawn rows.  Two compilations describe the same scenario iff their tables are equal."""
+        header = _abi.CavScenario.from_buffer_copy(self.struct)
+        header.bodies = C.cast(None, C.POINTER(_abi.CavBody))
+        header.spawns = C.cast(None, C.POINTER(_abi.CavSpawn))
+        rows, spawns = self.keepalive
+        return {"header": bytes(header), "bodies": bytes(rows), "spawns": bytes(spawns)[:C.sizeof(_abi.CavSpawn) * self.struct.n_spawns]}
+
 
 def _quad(shape):
     q = _abi.CavQuad()

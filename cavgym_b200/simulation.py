@@ -4,7 +4,9 @@
                       choose the joint action, `env.step` is one CUDA launch on a batch of one.  Same console / log lines.
   BatchedSimulation   the same experiment at batch scale: N concurrent copies of the config's scenario, on-device agents,
                       scoring and auto-reset inside the rollout kernel (cavgym_rollout); the run summary comes from the
-                      ten device counters (cavgym_stats), optionally summed over ranks with one all-reduce.
+                      device counters (cavgym_stats), optionally summed over ranks with one all-reduce; with an
+                      `episode_log` the per-episode rows come from the device ring (cavgym_drain_episodes), one per
+                      finished episode, in the reference's episode.log format.
 """
 import timeit
 
@@ -74,6 +76,28 @@ class BatchedSimulation:
         self.env = config.batched(num_envs, device=device, dtype=dtype, env_offset=env_offset)
         self.console = reporting.get_console(config.verbosity)
         self.run_file = reporting.get_run_file_logger(config.run_log) if config.run_log is not None else None
+        self.episode_file = reporting.get_episode_file_logger(config.episode_log) if config.episode_log is not None else None
+        self.episode_rows = []      # EpisodeResults of every drained episode when an episode log is kept (keep_rows / episode_log)
+        self.keep_rows = False
+        self.dropped_rows = 0
+
+    def _drain(self, resolution):
+        """Per-episode rows from the device ring -> reporting.EpisodeResults, numbered in finishing order (the reference
+        numbers episodes in running order, simulation.py:40); written to episode.log in the reference's row format
+        (reporting.py:157-158) with NaN for the per-episode wall-clock, which concurrent environments do not have."""
+        rows, dropped = self.env.drain_episodes()
+        self.dropped_rows += dropped
+        nan = float("nan")
+        for row in rows:
+            index = self._episodes_logged = getattr(self, "_episodes_logged", 0) + 1
+            interesting = int(row["winner"]) > 0
+            result = reporting.EpisodeResults(index, reporting.TimeResults(int(row["timesteps"]), nan, nan, resolution),
+                                              completed=int(row["timesteps"]) == self.config.max_timesteps, interesting=interesting,
+                                              score=-int(row["liveness_sum"]) if interesting else nan)
+            if self.keep_rows:
+                self.episode_rows.append((int(row["env"]), int(row["episode"]), result))
+            if self.episode_file:
+                self.episode_file.info(result.file_message())
 
     def _learner(self):
         """The Q-learning ego on the tensor API (config.json's stock ego option), or None when every agent is on the device."""
@@ -110,6 +134,9 @@ class BatchedSimulation:
         from . import sharding
         target = self.config.episodes if episodes is None else int(episodes)
         env = self.env
+        logging_rows = self.episode_file is not None or self.keep_rows
+        if logging_rows:   # an episode lasts tens of steps at least: room for every env to finish chunk/16 times between drains
+            env.set_episode_log(env.num_envs * max(1, self.chunk // 16) + 1024)
         env.reset()
         self.steps_run = 0
         start = timeit.default_timer()
@@ -121,8 +148,12 @@ class BatchedSimulation:
                 self._learning_steps(learner, self.chunk)
             self.steps_run += self.chunk
             stats = env.stats()          # synchronises
+            if logging_rows:
+                self._drain(env.time_resolution)
             if stats["episodes"] >= target:
                 break
+        if self.dropped_rows:
+            self.console.warning(f"{self.dropped_rows} episode row(s) did not fit the device ring and are missing from the episode log")
         torch.cuda.synchronize(env.device)
         runtime_ms = (timeit.default_timer() - start) * 1000
         if reduce:

@@ -125,6 +125,17 @@ typedef struct CavScenario {
 
 typedef struct CavEngine CavEngine;
 
+/* One finished episode as reporting.analyse_episode scores it (reporting.py:227-243) — the fields of an episode.log
+ * row (reporting.py:157-158) that exist for an environment of a batch.  interesting <=> winner > 0, score = -liveness_sum
+ * when interesting (else NaN), completed <=> timesteps == max_timesteps. */
+typedef struct CavEpisodeRow {
+  int64_t env;           /* global env id (shard offset included) */
+  int32_t episode;       /* the env's own episode count, 1 = its first episode */
+  int32_t timesteps;
+  int32_t winner;        /* info['winner'] of the last step, -1 when absent */
+  int32_t liveness_sum;  /* sum(env.episode_liveness[1:]) */
+} CavEpisodeRow;
+
 /* Indices of cavgym_stats' twelve int64 counters (reporting.py:227-269 definitions).  SUM_T / SUM_T2 run over every
  * finished episode; SUM_T_INTERESTING / SUM_T2_INTERESTING only over episodes with winner > 0, which is what the reference's
  * run summary reports as the timesteps of its "interesting" tests (reporting.py:246-255). */
@@ -185,6 +196,11 @@ int cavgym_replay(CavEngine* engine, int n_steps, const void* actions, void* sta
 int cavgym_step_host(CavEngine* engine, const void* actions, void* state_out, void* reward_out,
                      uint8_t* done_out, int32_t* winner_out, uint8_t* tangent_flag_out);
 
+/* CAVEnv.reset (environment.py:225-229) with HOST buffers, for callers that hold no device memory (the host-buffer twin
+ * of cavgym_reset, as cavgym_step_host is of cavgym_step): mask host u8[N] or NULL, init_state host real[M][4][N] or NULL
+ * are copied in; the post-reset state is copied to state_out (host real[M][4][N], nullable).  Synchronises. */
+int cavgym_reset_host(CavEngine* engine, const uint8_t* mask, const void* init_state, void* state_out);
+
 /* CAVEnv.info (environment.py:106-117) for the current state of every env, on demand (nothing on the step path reads it):
  * polygons_out   device real[M][8][N]: body_polygons, x of rear_left, front_left, front_right, rear_right, then y
  *                (bodies.py:116-117; PelicanCrossing: its static box), nullable;
@@ -199,6 +215,14 @@ int cavgym_info(CavEngine* engine, void* polygons_out, void* road_angle_out, cud
 int cavgym_stats(CavEngine* engine, int64_t* out);
 int cavgym_error_count(CavEngine* engine, int64_t* out);   /* envs with the invalid-action flag set */
 int cavgym_launch_count(CavEngine* engine, int64_t* out);  /* kernels launched by this engine so far */
+
+/* Per-episode rows (Simulation.run's episode.log, simulation.py:103-105): with capacity > 0 every episode scored from
+ * now on is also appended to a device ring of `capacity` rows (0 switches it off and frees nothing).  An episode that finds
+ * the ring full is still counted in cavgym_stats but its row is dropped; drain often enough. */
+int cavgym_set_episode_log(CavEngine* engine, int64_t capacity);
+/* Copies the rows appended since the last drain to `out` (HOST, room for max_rows) in append order, empties the ring,
+ * *n_rows = rows copied, *dropped = rows lost to a full ring or to max_rows.  Synchronises. */
+int cavgym_drain_episodes(CavEngine* engine, CavEpisodeRow* out, int64_t max_rows, int64_t* n_rows, int64_t* dropped);
 
 /* ---- engine-owned device buffers (zero-copy views for the host shim) --------------- */
 void* cavgym_state_ptr(CavEngine* engine);          /* real[M][4][N] */

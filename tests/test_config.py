@@ -94,3 +94,26 @@ def test_package_level_names_resolve():
     import cavgym_b200
     assert cavgym_b200.Config is cfg.Config and cavgym_b200.make_config is cfg.make_config
     assert callable(cavgym_b200.make) and "Pedestrians-v0" in cavgym_b200.examples.registered()
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("scenario,extra", [("pedestrians", {"num_pedestrians": 3}), ("crossroads", {}), ("bus-stop", {}),
+                                            ("pelican-crossing", {})])
+def test_reference_objects_compile_to_the_same_tables(scenario, extra):
+    """compile_scenario reads reference-style objects by protocol (class names, attributes): the bodies, constants and
+    config that the UNMODIFIED reference's own Config.setup builds (library/environment.py:59-101,
+    examples/environments/*.py) compile to byte-identical CavScenario tables as this repo's mirrors of those modules."""
+    import copy
+    from oracle import refload
+    from cavgym_b200.scenario import AgentSpec, compile_scenario
+    data = refload.stock_config_dict(scenario=scenario, tester="random", seed=5, collisions="all", offroad=True, **extra)
+    mods = refload.load()
+    theirs_config = mods["config"].make_config(copy.deepcopy(data))
+    _, their_env, _, _ = theirs_config.setup()
+    assert type(their_env.bodies[0]).__module__ == "library.bodies"          # really the reference's classes
+    mine_config = cfg.make_config(copy.deepcopy(data))
+    _, my_env, _, _ = mine_config.setup()
+    specs = [AgentSpec("noop")] + [AgentSpec("random", epsilon=0.01) for _ in my_env.bodies[1:]]
+    theirs = compile_scenario(their_env.bodies, their_env.constants, theirs_config, specs).tables()
+    mine = compile_scenario(my_env.bodies, my_env.constants, mine_config, specs).tables()
+    assert theirs == mine

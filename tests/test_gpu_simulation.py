@@ -84,3 +84,46 @@ def test_compat_view_info_matches_reference():
         observation, reward, done, info = env.step(joint_action)
         for agent, action, r in zip(agents, joint_action, reward):
             agent.process_feedback(previous, action, observation, r)
+
+
+def test_batched_simulation_writes_one_episode_row_per_episode(tmp_path):
+    """episode.log at batch scale (reporting.py:157-158): the rows the device ring collected are exactly the episodes the
+    counters saw — same count, same interesting set, same sums — and every row is an episode the oracle also finished,
+    env by env and episode by episode."""
+    from cavgym_b200.config import make_config
+    from cavgym_b200.simulation import BatchedSimulation
+    from oracle.oracle import Oracle
+    n = 1024
+    log = tmp_path / "episode.log"
+    config = make_config(dict(copy.deepcopy(STOCK), episodes=600, seed=5, episode_log=str(log),
+                              tester_config={"option": "random-constrained", "epsilon": 0.5}))
+    sim = BatchedSimulation(config, n, chunk=150)
+    sim.keep_rows = True
+    summary = sim.run()
+    stats = sim.env.stats()
+    rows = sim.episode_rows
+    assert sim.dropped_rows == 0 and len(rows) == stats["episodes"] == summary.episodes
+    assert sum(r.interesting for _, _, r in rows) == stats["interesting"]
+    assert sum(r.time.timesteps for _, _, r in rows) == stats["sum_t"]
+    assert sum(int(r.score) for _, _, r in rows if r.interesting) == stats["sum_score"]
+    assert len({(env, episode) for env, episode, _ in rows}) == len(rows)          # no episode twice
+    lines = log.read_text().strip().splitlines()
+    assert len(lines) == len(rows) and lines[0].split(",")[0] == "1" and len(lines[0].split(",")) == 5
+    # the oracle on the same Philox stream, stepped as far: per (env, episode) the same length and winner class
+    meta, _ = load_golden("pedestrians_rc_eps05_seed1")
+    oracle = Oracle(compile_from_meta(meta, mode="device"), n, seed=5, threads=8)
+    oracle.reset()
+    done_at, episode_no = {}, np.ones(n, np.int64)      # the first reset starts every env's episode 1
+    for _ in range(sim.steps_run):
+        oracle.rollout(1, auto_reset=False)
+        ended = np.nonzero(oracle.done_latch)[0]
+        for e in ended:
+            done_at[(int(e), int(episode_no[e]))] = (int(oracle.timestep[e]), int(oracle.winner_latch[e]) > 0)
+        if len(ended):
+            mask = np.zeros(n, np.uint8)
+            mask[ended] = 1
+            oracle.reset(mask=mask)
+            episode_no[ended] += 1
+    if stats["tangent"] == 0:
+        for env, episode, result in rows:
+            assert done_at[(env, episode)] == (result.time.timesteps, result.interesting), (env, episode)
