@@ -306,13 +306,16 @@ def run_ours(args):
     out["episode_stats"] = sharding.reduce_stats(env.stats(), device)
     env.close()
 
+    if not args.skip_configs:   # C3 and C5 are sharded over every rank (BASELINE configs[2], [4]); rank 0 reports
+        c3 = scenario_configs(torch, device, dtype, rank, world)
+        c5 = sweep_config(torch, device, dtype, rank, world)
+        if rank == 0:
+            out["scenario_configs"], out["sweep_config"] = c3, c5
     if rank == 0:
         if not args.skip_hbm:
             out["hbm_config"] = hbm_config(torch, device, dtype, peak_gbs)
-        if not args.skip_configs:   # the other BASELINE configs on this one GPU: reported beside the headline, not as it
-            out["scenario_configs"] = scenario_configs(torch, device, dtype)
+        if not args.skip_configs:   # C4 on this one GPU: reported beside the headline, not as it
             out["dense_config"] = dense_config(torch, device, dtype, skip_cpu=args.skip_cpu)
-            out["sweep_config"] = sweep_config(torch, device, dtype)
         if not args.skip_cpu:
             out["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_seconds)
         print(json.dumps(out))
@@ -347,7 +350,8 @@ def hbm_config(torch, device, dtype, peak_gbs):
     env.close()
     return {"workload": "pedestrians x 4,194,304 envs, 300 steps into their episodes, cavgym_step (one launch per step), "
                         "replayed actions, working set >> L2",
-            "kernel": f"step_kernel<{'double' if dtype == 'float64' else 'float'},2,false>", "envs": n,
+            "kernel": (kernel := f"step_tma_kernel<{'double' if dtype == 'float64' else 'float'},2,false>"), "envs": n,
+            "traffic": measured_traffic(kernel)[0], "traffic_note": measured_traffic(kernel)[1],
             "env_steps_per_sec": n / (mean_ms * 1e-3), "body_steps_per_sec": n * m / (mean_ms * 1e-3),
             "avg_launch_ms": round(mean_ms, 4), "min_launch_ms": round(ms[0], 4), "algorithmic_bytes_per_launch": bytes_launch,
             "achieved_gbs": round(achieved, 1), "peak_gbs": peak_gbs, "frac": round(achieved / peak_gbs, 4)}
@@ -364,31 +368,70 @@ def timed(torch, fn, repeats):
     return a.elapsed_time(b) / repeats
 
 
-def scenario_configs(torch, device, dtype, n=131072, steps=1000, chunk=100):
-    """BASELINE config C3, one GPU's share (1,048,576 envs over 8 GPUs = 131,072 per GPU): each of the four
-    examples/environments scenarios with the on-device agents Config.setup would build (ego noop; tester
-    random-constrained on the pedestrians scenario, random elsewhere — config.py:358-396), auto-reset, cavgym_rollout."""
+C3_ENVS = 1048576       # BASELINE configs[2]: each scenario at 1M envs, env-sharded over the GPUs of the run
+BYTES_PER_BODY_STEP_AGENTS = {"float64": {"noop": 72, "random": 88, "random-constrained": 152}, "float32": {"noop": 36, "random": 44, "random-constrained": 76}}
+
+
+def timed_all_ranks(torch, device, fn, repeats):
+    """Device milliseconds of `repeats` calls of fn() on this rank, bracketed by barriers; MAX over ranks."""
+    import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    torch.cuda.synchronize(device)
+    if multi:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(repeats):
+        fn()
+    b.record()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+    if multi:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def scenario_configs(torch, device, dtype, rank=0, world=1, total_envs=C3_ENVS, steps=1000, chunk=100):
+    """BASELINE config C3: each of the four examples/environments scenarios at 1,048,576 envs, sharded over the ranks of
+    this run (sharding.split_envs; 131,072 per GPU at 8 GPUs), with the on-device agents Config.setup would build (ego noop;
+    tester random-constrained on the pedestrians scenario, random elsewhere — config.py:358-396), auto-reset, cavgym_rollout.
+    Every rank runs its shard; time = max over ranks, counters summed with one all-reduce."""
     from helpers import compile_from_meta, load_golden
-    from cavgym_b200 import BatchedCAVEnv
+    from cavgym_b200 import BatchedCAVEnv, sharding
+    offset, n = sharding.split_envs(total_envs, world)[rank]
+    peak_gbs, _ = peaks()
     out = {}
     for name, golden in (("pedestrians", "pedestrians_rc_seed0"), ("crossroads", "crossroads_random_all_seed6"),
                          ("bus-stop", "busstop_random_all_seed8"), ("pelican-crossing", "pelican_random_all_seed10")):
         meta, _ = load_golden(golden)
         meta["config"]["tester_config"]["epsilon"] = EPSILON
-        env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=compile_from_meta(meta, mode="device"), device=device, seed=0)
+        env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=compile_from_meta(meta, mode="device"), device=device, seed=0,
+                            env_offset=offset)
         env.reset()
         env.rollout(chunk, auto_reset=True)
         torch.cuda.synchronize(device)
-        before = env.stats()
-        ms = timed(torch, lambda: env.rollout(chunk, auto_reset=True), steps // chunk) * (steps // chunk)
-        after = env.stats()
+        before = sharding.reduce_stats(env.stats(), device)
+        ms = timed_all_ranks(torch, device, lambda: env.rollout(chunk, auto_reset=True), steps // chunk)
+        after = sharding.reduce_stats(env.stats(), device)
         live = after["env_steps"] - before["env_steps"]
-        out[name] = {"bodies": env.num_bodies, "envs": n, "steps": steps, "env_steps_per_sec": live / (ms * 1e-3),
-                     "body_steps_per_sec": live * env.num_bodies / (ms * 1e-3), "episodes": after["episodes"] - before["episodes"],
-                     "collisions": meta["config"]["terminate_collisions"]}
+        m = env.num_bodies
+        # algorithmic bytes of one env-step with on-device agents (SURVEY 8d): ego 9 words, a tester 9 (noop) / 11 (random) /
+        # 19 (crossing agent) words, + 4 B liveness r/w per tester
+        tester = meta["config"]["tester_config"]["option"]
+        per_env_step = BYTES_PER_BODY_STEP_AGENTS[dtype]["noop"] + (m - 1) * (BYTES_PER_BODY_STEP_AGENTS[dtype][tester] + 8) + BYTES_PER_ENV_STEP_EXTRA
+        rate = live / (ms * 1e-3)
+        out[name] = {"bodies": m, "envs": total_envs, "envs_per_rank": n, "steps": steps, "env_steps_per_sec": rate,
+                     "body_steps_per_sec": rate * m, "episodes": after["episodes"] - before["episodes"],
+                     "collisions": meta["config"]["terminate_collisions"],
+                     "algorithmic_bytes_per_env_step": per_env_step,
+                     "algorithmic_gbs_per_gpu": round(rate * per_env_step / 1e9 / world, 1),
+                     "frac_of_hbm_peak_if_every_step_streamed": round(rate * per_env_step / 1e9 / world / peak_gbs, 4)}
         env.close()
-    return {"workload": "C3 share of one GPU: 131,072 envs per scenario, on-device Philox agents (eps=0.01), auto-reset, "
-                        f"cavgym_rollout {chunk} steps/launch, {steps} steps", "scenarios": out}
+    return {"workload": f"C3: {total_envs} envs per scenario over {world} GPU(s) ({n} on rank 0), on-device Philox agents (eps={EPSILON}), "
+                        f"auto-reset, cavgym_rollout {chunk} steps/launch, {steps} steps timed",
+            "note": "cavgym_rollout keeps the state in registers for the whole launch, so its DRAM traffic is 1/chunk of the per-step "
+                    "algorithmic figure; the fraction says how far the kernel is from the rate at which a per-step API could stream",
+            "scenarios": out}
 
 
 def dense_config(torch, device, dtype, n=100000, steps=100, chunk=50, skip_cpu=False):
@@ -439,31 +482,44 @@ def dense_config(torch, device, dtype, n=100000, steps=100, chunk=50, skip_cpu=F
             "cpu_baseline": cpu}
 
 
-def sweep_config(torch, device, dtype, n=1048576, steps=1000, chunk=100):
-    """BASELINE config C5 (experiments.py-style seed sweep): RandomConstrained testers searching for 'interesting' episodes,
-    one wave of 1,048,576 concurrent envs with auto-reset; episodes/s and the projected time for 10 M episodes."""
+C5_ENVS = 1048576          # concurrent envs of the seed sweep (global; split over the ranks of the run)
+C5_EPISODES = 10_000_000   # BASELINE configs[4]
+
+
+def sweep_config(torch, device, dtype, rank=0, world=1, total_envs=C5_ENVS, episodes=C5_EPISODES, chunk=500):
+    """BASELINE config C5 (experiments.py:95-122 as one batch): RandomConstrained testers searching for 'interesting'
+    episodes; 1,048,576 concurrent envs (global ids 0..2^20-1, split over the ranks) roll forward with auto-reset in
+    launches of `chunk` steps until the all-reduced episode count reaches 10 M.  Philox is keyed by the global env id and the
+    stop rule only looks at global counts, so every total below is identical for any number of GPUs
+    (tests/test_gpu_replay.py::test_sweep_totals_do_not_depend_on_the_split).  Mean +- 95 % CI as reporting.analyse_run."""
     from helpers import compile_from_meta, load_golden
-    from cavgym_b200 import BatchedCAVEnv
+    from cavgym_b200 import BatchedCAVEnv, sharding
+    from cavgym_b200.reporting import RunSummary
+    offset, n = sharding.split_envs(total_envs, world)[rank]
     out = {}
     for eps in (0.5, 0.01):
         meta, _ = load_golden("pedestrians_rc_seed0")
         meta["config"]["tester_config"]["epsilon"] = eps
-        env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=compile_from_meta(meta, mode="device"), device=device, seed=0)
+        env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=compile_from_meta(meta, mode="device"), device=device, seed=0,
+                            env_offset=offset)
         env.reset()
-        env.rollout(chunk, auto_reset=True)
-        torch.cuda.synchronize(device)
-        before = env.stats()
-        ms = timed(torch, lambda: env.rollout(chunk, auto_reset=True), steps // chunk) * (steps // chunk)
-        after = env.stats()
-        episodes = after["episodes"] - before["episodes"]
-        live = after["env_steps"] - before["env_steps"]
-        out[f"epsilon={eps}"] = {"episodes": episodes, "interesting": after["interesting"] - before["interesting"],
-                                 "env_steps_per_sec": live / (ms * 1e-3), "body_steps_per_sec": 2 * live / (ms * 1e-3),
-                                 "episodes_per_sec": episodes / (ms * 1e-3),
-                                 "seconds_for_10M_episodes": 1e7 / (episodes / (ms * 1e-3)) if episodes else None}
+        ms, steps, stats = 0.0, 0, sharding.reduce_stats(env.stats(), device)
+        while stats["episodes"] < episodes and steps < 40000:
+            ms += timed_all_ranks(torch, device, lambda: env.rollout(chunk, auto_reset=True), 1)
+            steps += chunk
+            stats = sharding.reduce_stats(env.stats(), device)       # the single all-reduce of the counters (untimed)
+        summary = RunSummary.from_stats(stats, ms, env.time_resolution)
+        out[f"epsilon={eps}"] = {"episodes": stats["episodes"], "interesting": stats["interesting"], "steps_per_env": steps,
+                                 "env_steps": stats["env_steps"], "seconds": ms * 1e-3,
+                                 "env_steps_per_sec": stats["env_steps"] / (ms * 1e-3), "body_steps_per_sec": 2 * stats["env_steps"] / (ms * 1e-3),
+                                 "episodes_per_sec": stats["episodes"] / (ms * 1e-3),
+                                 "timesteps_interesting": {"mean": summary.confidence_timesteps.value, "ci95": summary.confidence_timesteps.error},
+                                 "score_interesting": {"mean": summary.confidence_score.value, "ci95": summary.confidence_score.error},
+                                 "totals": {k: stats[k] for k in ("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2",
+                                                                  "sum_t_interesting", "sum_t2_interesting")}}
         env.close()
-    return {"workload": f"C5: pedestrians scenario, {n} concurrent envs, on-device RandomConstrained testers, auto-reset, "
-                        f"cavgym_rollout {chunk} steps/launch, {steps} steps timed", "runs": out}
+    return {"workload": f"C5: pedestrians scenario, {total_envs} concurrent envs over {world} GPU(s), on-device RandomConstrained testers, "
+                        f"auto-reset, cavgym_rollout {chunk} steps/launch, run until >= {episodes} episodes have finished", "runs": out}
 
 
 def oracle_trace(n_envs, n_steps, threads):

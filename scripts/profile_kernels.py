@@ -21,6 +21,7 @@ def main():
     parser.add_argument("--dtype", default="float64")
     parser.add_argument("--mode", default="all")
     parser.add_argument("--launches", type=int, default=4)
+    parser.add_argument("--replay-steps", type=int, default=0, help="steps fused per replay launch (default: bench.CHUNK)")
     parser.add_argument("--advance", type=int, default=0, help="steps to advance (fused replay) before the measured step launches")
     args = parser.parse_args()
     device = torch.device("cuda", 0)
@@ -38,7 +39,7 @@ def main():
         env.close()
     if args.mode in ("replay", "all"):
         n = 65536
-        steps = bench.CHUNK
+        steps = args.replay_steps or bench.CHUNK
         init, actions = bench.make_trace(torch, device, n, steps, args.dtype, 0)
         env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=args.dtype, compiled=bench.scenario("external"), device=device)
         env.reset(init_state=init)

@@ -328,6 +328,54 @@ def test_sharded_engines_match_one_engine(dtype):
     assert total == want and want["episodes"] > n
 
 
+def test_sweep_totals_do_not_depend_on_the_split():
+    """BASELINE config C5's claim: the seed sweep over a fixed GLOBAL env set gives identical totals however many GPUs share
+    it.  The same 8,192 global envs are run as 1, 2, 4 and 8 shards (sharding.split_envs; one engine per shard, as one rank
+    per GPU would hold them) for the same number of steps; every counter, summed over the shards, must be identical."""
+    from cavgym_b200 import sharding
+    meta, _ = load_golden("pedestrians_rc_eps05_seed1")
+    total, steps = 8192, 1500
+    want = None
+    for world in (1, 2, 4, 8):
+        summed = None
+        for offset, count in sharding.split_envs(total, world):
+            part = make_env(meta, count, "float64", mode="device", seed=0, env_offset=offset)
+            part.reset()
+            for _ in range(3):
+                part.rollout(steps // 3, auto_reset=True)
+            got = part.stats()
+            summed = got if summed is None else {k: summed[k] + got[k] for k in got}
+            part.close()
+        if want is None:
+            want = summed
+            assert want["episodes"] > total and want["interesting"] > 0
+        assert summed == want, world
+
+
+def test_two_engines_on_two_devices_in_one_process():
+    """The TMA kernels opt in to > 48 KB of shared memory per DEVICE: a second engine on another GPU of the same process must
+    get its own opt-in (the launchers cache it per device)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    meta, episodes = load_golden("pedestrians_rc_seed0")
+    ep = episodes[0]
+    n = 256
+    init = soa(np.repeat(ep["init_state"][None], n, axis=0))
+    actions = np.repeat(ep["actions"][:40][..., None], n, axis=-1)
+    outs = []
+    for index in (0, 1):
+        with torch.cuda.device(index):
+            env = make_env(meta, n, "float64", device=f"cuda:{index}")
+            env.reset(init_state=init)
+            env.step(actions[0])
+            out = env.replay(actions[1:])
+            outs.append(out["state"].cpu().numpy())
+            env.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert state_err(np.moveaxis(outs[0][:, :, :, 0], 0, 0), ep["state"][1:40]) < 1e-9
+
+
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 @pytest.mark.parametrize("name", __import__("helpers").INFO_CASES)
 def test_info_matches_reference(name, dtype):
