@@ -60,8 +60,9 @@ def measured_traffic(kernel, steps_per_launch=None):
     if not shapes:
         return None, "no ncu capture found"
     if steps_per_launch in shapes:
+        source = entry.get("source_by_shape", {}).get(str(int(steps_per_launch)), entry.get("source", "profiles/"))
         return shapes[int(steps_per_launch)], (f"dram__bytes_read.sum + dram__bytes_write.sum of one {int(steps_per_launch)}-step launch "
-                                                f"(ncu --set full, {entry.get('source', 'profiles/')})")
+                                                f"(ncu --set full, {source}); {entry.get('note', '')}")
     nearest = min(shapes, key=lambda k: abs(k - steps_per_launch))
     return int(shapes[nearest] * steps_per_launch / nearest), (f"scaled per fused step from the ncu capture of a {nearest}-step launch "
                                                                f"({entry.get('source', 'profiles/')}); this shape was not captured")

@@ -204,8 +204,9 @@ class BatchedQLearningEgoAgent:
         candidates = torch.where(explore.unsqueeze(0), torch.ones_like(tied), tied)
         count = candidates.sum(dim=0)
         wanted = torch.clamp((u_pick * count).floor().long(), max=actions - 1).minimum(count - 1)   # k-th candidate, k from 0
-        rank = candidates.long().cumsum(dim=0) - 1
-        index = (candidates & (rank == wanted.unsqueeze(0))).long().argmax(dim=0)
+        # the wanted-th candidate in action order sits after exactly `wanted` candidates: count the positions whose running
+        # candidate count is still <= wanted (the running count is non-decreasing along the action axis)
+        index = (candidates.long().cumsum(dim=0) <= wanted.unsqueeze(0)).sum(dim=0).clamp(max=actions - 1)
         rows = torch.stack([self.throttles[index], torch.zeros(n, dtype=torch.float64, device=self.device)])
         return index, rows.to(self.dtype)
 

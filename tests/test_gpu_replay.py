@@ -4,19 +4,30 @@ Bar (north star): body state within 1e-9 relative in fp64 mode and 1e-4 in fp32 
 liveness identical except on steps the engine flags as near-tangent.
 
 "Relative" is |dp| / max(1 px, |p|) for a position, |dv| / max(1, |v|), and the angle difference modulo 2 pi over
-max(1, |theta|) (helpers.state_err).  In fp32 mode the position scale is the largest |p| the body has reached so far in
-the episode (helpers.state_err_trajectory): up-to-1000-step float32 integrations are compared with the fp64 reference
-without teacher forcing, and a float32 sum keeps digits of the magnitudes that went through it, not of a coordinate
-that happens to pass near zero.  The strict per-step definition is kept for fp64.
+max(1, |theta|) (helpers.state_err) — the STRICT per-step definition.  Measured on every fixture
+(scripts/parity_report.py -> profiles/r2_parity_report.txt):
+
+  fp64   strict 1.1e-13 worst, rewards 1.3e-11, no event or liveness difference at all, <= 0.18 % of steps flagged
+  fp32   strict 3.0e-4 worst (a body whose coordinates were ~1,000 px and which later passes near the origin keeps the
+         absolute error of the large coordinates: 3e-4 px against |p| ~ 1 px), 2.8e-5 when the error is taken relative to
+         the largest |p| the body has reached so far (helpers.state_err_trajectory); rewards 2.7e-4; <= 4.2 % of steps
+         flagged (tau = 0.05 px); every event difference is on a flagged step.
+
+So fp32 mode meets 1e-4 on the trajectory scale and 5e-4 on the strict per-step scale; both are asserted below, next to the
+flagged fractions (measured value + margin).  The comparison of an episode continues through flagged steps as long as the
+events agree and ends at the first event difference (after it the two runs are different episodes).
 """
 import numpy as np
 import pytest
 
-from helpers import GOLDEN_CASES, compile_from_meta, load_golden, rel_err, soa, state_err, state_err_trajectory
+from helpers import GOLDEN_CASES, LEARN_CASES, compile_from_meta, load_golden, rel_err, soa, state_err, state_err_trajectory
 
 pytestmark = pytest.mark.gpu
 
 REL = {"float64": 1e-9, "float32": 1e-4}
+STRICT = {"float64": 1e-9, "float32": 5e-4}       # per-step |dp| / max(1, |p|): measured 1.1e-13 / 3.0e-4
+REWARD = {"float64": 1e-9, "float32": 5e-4}       # relative to max(1, |r|): measured 1.3e-11 / 2.7e-4
+FLAGGED = {"float64": 0.005, "float32": 0.06}     # fraction of steps flagged near-tangent: measured 0.0018 / 0.042
 
 
 def make_env(meta, n, dtype, mode="external", **kw):
@@ -35,16 +46,15 @@ def check_episode(traj, ep, col, dtype, liveness=None):
     tangent = traj["tangent"][:t_len, col].astype(bool)
     mismatch = (done != ep["done"]) | (winner != ep["winner"])
     assert not np.any(mismatch & ~tangent), f"unflagged event mismatch at steps {np.nonzero(mismatch & ~tangent)[0][:5]}"
-    if np.any(mismatch):  # a flagged near-tangent divergence: compare only up to it
+    if dtype == "float64":
+        assert not mismatch.any(), "fp64: no fixture has an event difference, flagged or not"
+    if np.any(mismatch):  # a flagged near-tangent divergence: the two runs are different episodes from here on
         t_len = int(np.nonzero(mismatch)[0][0])
-    err = state_err if dtype == "float64" else state_err_trajectory
-    assert err(state[:t_len], ep["state"][:t_len]) < REL[dtype]
-    reward_tol = 1e-9 if dtype == "float64" else 2e-3  # terminal rewards are +-6000: relative to max(1,|r|)
-    assert rel_err(reward[:t_len], ep["reward"][:t_len]) < reward_tol
-    if liveness is not None and not np.any(mismatch):
-        want = ep["liveness"][-1]
-        if dtype == "float64":
-            assert np.array_equal(liveness, want) or tangent.any()
+    assert state_err(state[:t_len], ep["state"][:t_len]) < STRICT[dtype]
+    assert state_err_trajectory(state[:t_len], ep["state"][:t_len]) < REL[dtype]
+    assert rel_err(reward[:t_len], ep["reward"][:t_len]) < REWARD[dtype]
+    if liveness is not None and not np.any(mismatch) and dtype == "float64":
+        assert np.array_equal(liveness, ep["liveness"][-1])
     return int(tangent.sum())
 
 
@@ -91,8 +101,7 @@ def test_step_by_step_matches_reference_fp64(name):
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
-@pytest.mark.parametrize("name", ["pedestrians_rc_seed0", "pedestrians3_rc_seed2", "busstop_random_all_seed8",
-                                  "pelican_random_all_seed10", "crossroads_random_ego_seed7"])
+@pytest.mark.parametrize("name", GOLDEN_CASES + LEARN_CASES)
 def test_fused_replay_matches_reference(name, dtype):
     """cavgym_replay (T steps in one launch) per golden episode with the reference's own time-out counter."""
     meta, episodes = load_golden(name)
@@ -104,7 +113,7 @@ def test_fused_replay_matches_reference(name, dtype):
         out = env.replay(ep["actions"][..., None])
         traj = {k: v.double().cpu().numpy() if v.dtype.is_floating_point else v.cpu().numpy() for k, v in out.items()}
         flagged += check_episode(traj, ep, 0, dtype, env.episode_liveness.cpu().numpy()[:, 0])
-    assert flagged < sum(ep["actions"].shape[0] for ep in episodes) * (0.02 if dtype == "float64" else 0.2)
+    assert flagged <= sum(ep["actions"].shape[0] for ep in episodes) * FLAGGED[dtype]
 
 
 def test_batched_replay_matches_oracle_65536_envs():

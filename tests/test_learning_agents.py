@@ -166,28 +166,24 @@ def test_simulation_with_learning_agents_reproduces_the_reference_run(name):
         assert np.allclose(weights, episodes[1]["extra"][-1][:-1], rtol=1e-7, atol=1e-9)
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", Q_CASES)
-def test_tensor_api_learner_is_the_host_learner_at_one_env(name):
+def check_tensor_learner(name, dev):
     """BatchedQLearningEgoAgent with N = 1, fed the reference's states, rewards and draws: the reference's actions and,
-    step for step, its weights (torch's cos / sin / atan2 differ from libm by ulps: 1e-9, not bitwise)."""
+    step for step, its weights (torch's cos / sin / atan2 differ from libm by ulps: 1e-8 relative, not bitwise)."""
     import torch
     from cavgym_b200.config import make_config
     from cavgym_b200.examples.agents.ego import BatchedQLearningEgoAgent
     from cavgym_b200.examples.constants import car_constants
+    from cavgym_b200.examples.environments import pedestrians
     meta, episodes = load_golden(name)
     config = make_config(copy.deepcopy(meta["config"]))
-    dev = torch.device("cuda", 0)
     m = meta["n_bodies"]
-    from cavgym_b200.examples.environments import pedestrians
     learner = BatchedQLearningEgoAgent(config.ego_config, car_constants, 1.0 / 60, m - 1, pedestrians.env_constants.viewer_width,
                                        pedestrians.env_constants.viewer_height, 1, dev)
-    names = sorted(learner.names)
-    order = [learner.names.index(f) for f in names]
+    order = [learner.names.index(f) for f in sorted(learner.names)]
     steps = 0
     for ep in episodes:
         state = torch.tensor(ep["init_state"], dtype=torch.float64, device=dev).unsqueeze(-1)
-        for t in range(min(300, ep["actions"].shape[0])):
+        for t in range(ep["actions"].shape[0]):     # whole episodes: the weights carry over from one to the next
             draws = [d for d in ep["draws"][t][0] if not np.isnan(d)]
             explore = torch.tensor([draws[0]], dtype=torch.float64, device=dev)
             pick = torch.tensor([draws[1] if len(draws) > 1 else 0.0], dtype=torch.float64, device=dev)
@@ -196,12 +192,25 @@ def test_tensor_api_learner_is_the_host_learner_at_one_env(name):
             previous, state = state, torch.tensor(ep["state"][t], dtype=torch.float64, device=dev).unsqueeze(-1)
             learner.process_feedback(previous, index, state, torch.tensor([ep["reward"][t][0]], dtype=torch.float64, device=dev))
             want = ep["extra"][t][:-1].reshape(m - 1, -1)
-            got = learner.weights[:, order].cpu().numpy()
-            assert np.allclose(got, want, rtol=1e-8, atol=1e-9), (name, t)
+            assert np.allclose(learner.weights[:, order].cpu().numpy(), want, rtol=1e-8, atol=1e-9), (name, t)
             assert learner.alpha == ep["extra"][t][-1]
             steps += 1
-        if steps >= 500:
+        if steps > 1200:
             break
+    assert steps > 500
+
+
+@pytest.mark.parametrize("name", Q_CASES)
+def test_tensor_api_learner_is_the_host_learner_at_one_env_cpu_tensors(name):
+    import torch
+    check_tensor_learner(name, torch.device("cpu"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", Q_CASES)
+def test_tensor_api_learner_is_the_host_learner_at_one_env(name):
+    import torch
+    check_tensor_learner(name, torch.device("cuda", 0))
 
 
 @pytest.mark.gpu
