@@ -129,6 +129,7 @@ struct StepIO {
   uint8_t* done_out;
   int32_t* winner_out;
   uint8_t* tangent_out;
+  int32_t ctas_per_sm;   // host side only: cap on resident CTAs per SM of the persistent step kernel (0 = as many as fit)
 };
 
 }  // namespace cav

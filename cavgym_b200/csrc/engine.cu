@@ -8,6 +8,11 @@
 #include <string>
 #include <vector>
 
+#ifndef CAV_HOST_CTAS_PER_SM
+#define CAV_HOST_CTAS_PER_SM 3
+#endif
+
+
 #include "kernels_dense.cuh"
 #include "kernels_small.cuh"
 
@@ -409,6 +414,8 @@ struct CavEngine {
   // host-buffer pipeline (cavgym_step_host)
   static constexpr int kPipe = 3;
   cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr};
+  int step_ctas_per_sm = 0;       // cap on resident CTAs per SM of the persistent step kernel for the next launch (0 = occupancy)
+  int host_ctas_per_sm = CAV_HOST_CTAS_PER_SM;   // the same for the zero-copy host path (cavgym_set_host_path)
   bool host_ready = false;        // streams and staging buffers of the host-buffer entry points all exist
   bool caller_work_pending = true;   // a call queued work on a caller stream since the last host-buffer call synchronised
   const void* host_seen[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // caller buffers of the last zero-copy call ...
@@ -670,11 +677,11 @@ static int step_range(CavEngine* eng, int64_t lo, int64_t hi, const void* action
                       uint8_t* done_out, int32_t* winner_out, uint8_t* tangent_out, cudaStream_t stream) {
   if (eng->dtype == CAV_F64) {
     EnvBuffers<double> buf = eng->buf64; buf.lo = lo; buf.hi = hi;
-    StepIO<double> io{(const double*)actions, (double*)state_out, (double*)reward_out, done_out, winner_out, tangent_out};
+    StepIO<double> io{(const double*)actions, (double*)state_out, (double*)reward_out, done_out, winner_out, tangent_out, eng->step_ctas_per_sm};
     return step_range_typed(eng, eng->sc64, buf, io, stream);
   }
   EnvBuffers<float> buf = eng->buf32; buf.lo = lo; buf.hi = hi;
-  StepIO<float> io{(const float*)actions, (float*)state_out, (float*)reward_out, done_out, winner_out, tangent_out};
+  StepIO<float> io{(const float*)actions, (float*)state_out, (float*)reward_out, done_out, winner_out, tangent_out, eng->step_ctas_per_sm};
   return step_range_typed(eng, eng->sc32, buf, io, stream);
 }
 
@@ -696,8 +703,8 @@ int cavgym_rollout(CavEngine* eng, int n_steps, int auto_reset, cudaStream_t str
   if (eng->has_external) return fail(CAV_ESTATE, "cavgym_rollout needs an on-device agent for every body");
   if (n_steps == 0) return CAV_OK;
   if (eng->dense) {
-    const StepIO<double> io64{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    const StepIO<float> io32{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const StepIO<double> io64{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    const StepIO<float> io32{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     rc = eng->dtype == CAV_F64 ? dense_run(eng, eng->sc64, eng->buf64, io64, n_steps, auto_reset, 0, stream)
                                : dense_run(eng, eng->sc32, eng->buf32, io32, n_steps, auto_reset, 0, stream);
     if (rc) return rc;
@@ -722,10 +729,10 @@ int cavgym_replay(CavEngine* eng, int n_steps, const void* actions, void* state_
   if (n_steps == 0) return CAV_OK;
   int launches = 0;
   if (eng->dtype == CAV_F64) {
-    StepIO<double> io{(const double*)actions, (double*)state_traj, (double*)reward_traj, done_traj, winner_traj, tangent_traj};
+    StepIO<double> io{(const double*)actions, (double*)state_traj, (double*)reward_traj, done_traj, winner_traj, tangent_traj, 0};
     rc = replay_typed(eng, eng->sc64, eng->buf64, io, n_steps, stream, &launches);
   } else {
-    StepIO<float> io{(const float*)actions, (float*)state_traj, (float*)reward_traj, done_traj, winner_traj, tangent_traj};
+    StepIO<float> io{(const float*)actions, (float*)state_traj, (float*)reward_traj, done_traj, winner_traj, tangent_traj, 0};
     rc = replay_typed(eng, eng->sc32, eng->buf32, io, n_steps, stream, &launches);
   }
   if (rc) return rc;
@@ -794,7 +801,12 @@ int cavgym_step_host(CavEngine* eng, const void* actions, void* state_out, void*
     if (all_mapped) {
       void** dev = eng->host_mapped;
       cudaStream_t s = eng->pipe[0];
+      // (the CTA count is a tuning knob of cavgym_set_host_path; measured at 65,536 envs: 157 / 155 / 155 us per call with
+      //  1 / 2 / 3 CTAs per SM, 157 us with the plain kernel on the same mapped buffers, 161-173 us with the actions brought
+      //  in by chunked DMA copies instead — the call is bound by the PCIe link, scripts/e2e_breakdown.py)
+      eng->step_ctas_per_sm = eng->host_ctas_per_sm;
       rc = step_range(eng, 0, n, dev[0], dev[1], dev[2], (uint8_t*)dev[3], (int32_t*)dev[4], (uint8_t*)dev[5], s);
+      eng->step_ctas_per_sm = 0;
       if (rc) return rc;
       CUDA_TRY(cudaStreamSynchronize(s));
       eng->caller_work_pending = false;
@@ -993,6 +1005,8 @@ int cavgym_set_dense_path(CavEngine* eng, int force) {
 int cavgym_set_host_path(CavEngine* eng, int zero_copy) {
   if (!eng) return fail(CAV_EINVAL, "engine is NULL");
   eng->zero_copy_host = zero_copy != 0;
+  // tuning: 1 = zero copy with the default CTA count, 2..8 = zero copy with (value - 1) CTAs per SM
+  if (zero_copy >= 1 && zero_copy <= 8) eng->host_ctas_per_sm = zero_copy == 1 ? CAV_HOST_CTAS_PER_SM : zero_copy - 1;
   return CAV_OK;
 }
 

@@ -523,7 +523,8 @@ bool launch_step_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const S
   const int sms = sm_count[dev].load(std::memory_order_relaxed);
   EnvBuffers<R> range = buf;
   range.hi = buf.lo + span;
-  const int64_t grid = tiles < (int64_t)sms * res ? tiles : (int64_t)sms * res;
+  const int per_sm = io.ctas_per_sm > 0 && io.ctas_per_sm < res ? io.ctas_per_sm : res;
+  const int64_t grid = tiles < (int64_t)sms * per_sm ? tiles : (int64_t)sms * per_sm;
   kernel<<<(unsigned)grid, kStepTile + 32, L::kSmemBytes, stream>>>(sc, range, io, t_global, tiles);
   *envs_done = span;
   return true;

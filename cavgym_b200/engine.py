@@ -72,6 +72,7 @@ class BatchedCAVEnv:
         self.winner = torch.full((n,), -1, dtype=torch.int32, device=self.device)
         self.tangent = torch.zeros(n, dtype=torch.uint8, device=self.device)
         self._keep = {}
+        self._host_seen = {}
 
     # ---- plumbing ----------------------------------------------------------------------
     def _view(self, getter, shape, typestr):
@@ -144,30 +145,38 @@ class BatchedCAVEnv:
                                               _ptr(out["done"]), _ptr(out["winner"]), _ptr(out["tangent"]), self._stream()))
         return out
 
+    _NUMPY = {torch.float64: np.dtype("f8"), torch.float32: np.dtype("f4"), torch.uint8: np.dtype("u1"), torch.int32: np.dtype("i4")}
+
     def _host_buffer(self, array, shape, dtype, name):
         """Raw host pointer of a numpy array / CPU tensor after checking it is what the kernel will read or write."""
         if array is None:
             return None
+        seen = self._host_seen.get(id(array))      # validated before: the cache holds the object, so its id cannot be reused
+        if seen is not None and seen[0] is array:
+            return seen[1]
+        pointer = None
         if isinstance(array, torch.Tensor):
-            ok = array.device.type == "cpu" and array.dtype == dtype and tuple(array.shape) == tuple(shape) and array.is_contiguous()
-            address = array.data_ptr()
-        else:
-            want = np.dtype({torch.float64: "f8", torch.float32: "f4", torch.uint8: "u1", torch.int32: "i4"}[dtype])
-            ok = isinstance(array, np.ndarray) and array.dtype == want and array.shape == tuple(shape) and array.flags.c_contiguous
-            address = array.ctypes.data if ok else 0
-        if not ok:
-            raise ValueError(f"{name} must be a contiguous host array of shape {tuple(shape)} and dtype {dtype}")
-        return C.c_void_p(address)
+            if array.dtype == dtype and array.shape == shape and array.device.type == "cpu" and array.is_contiguous():
+                pointer = array.data_ptr()
+        elif isinstance(array, np.ndarray) and array.dtype == self._NUMPY[dtype] and array.shape == shape and array.flags.c_contiguous:
+            pointer = array.ctypes.data
+        if pointer is not None:
+            if len(self._host_seen) > 4096:
+                self._host_seen.clear()
+            self._host_seen[id(array)] = (array, pointer)
+            return pointer
+        raise ValueError(f"{name} must be a contiguous host array of shape {tuple(shape)} and dtype {dtype}")
 
     def step_host(self, actions, state_out=None, reward_out=None, done_out=None, winner_out=None, tangent_out=None):
         """cavgym_step_host: host buffers in and out (numpy arrays or CPU tensors in the engine's layout).  Pinned buffers
         (tensor.pin_memory()) are read and written by the step kernel itself over PCIe; pageable ones are staged."""
         n, m = self.num_envs, self.num_bodies
-        _native.check(self._lib.cavgym_step_host(
-            self._handle, self._host_buffer(actions, (m, 2, n), self.dtype, "actions"),
-            self._host_buffer(state_out, (m, 4, n), self.dtype, "state_out"), self._host_buffer(reward_out, (m, n), self.dtype, "reward_out"),
-            self._host_buffer(done_out, (n,), torch.uint8, "done_out"), self._host_buffer(winner_out, (n,), torch.int32, "winner_out"),
-            self._host_buffer(tangent_out, (n,), torch.uint8, "tangent_out")))
+        check = self._host_buffer
+        rc = self._lib.cavgym_step_host(self._handle, check(actions, (m, 2, n), self.dtype, "actions"), check(state_out, (m, 4, n), self.dtype, "state_out"),
+                                        check(reward_out, (m, n), self.dtype, "reward_out"), check(done_out, (n,), torch.uint8, "done_out"),
+                                        check(winner_out, (n,), torch.int32, "winner_out"), check(tangent_out, (n,), torch.uint8, "tangent_out"))
+        if rc:
+            _native.check(rc)
 
     def info(self, polygons=True, road_angles=True):
         """CAVEnv.info() for every env: {'body_polygons': [M, 8, N] (x of the four corners, then y), 'road_angles': [M, N]
@@ -218,7 +227,7 @@ class BatchedCAVEnv:
 
     def set_host_path(self, zero_copy=True):
         """False makes step_host stage pinned buffers through device copies instead of the zero-copy launch."""
-        _native.check(self._lib.cavgym_set_host_path(self._handle, int(bool(zero_copy))))
+        _native.check(self._lib.cavgym_set_host_path(self._handle, int(zero_copy)))
 
     def set_tangent_tolerance(self, tau):
         _native.check(self._lib.cavgym_set_tangent_tolerance(self._handle, float(tau)))

@@ -262,7 +262,7 @@ int cavgym_set_dense_path(CavEngine* engine, int force);
 
 /* cavgym_step_host with pinned (page-locked, mapped) buffers runs as one launch that reads and writes host memory
  * directly over PCIe; zero_copy = 0 forces the staged path (chunked async copies through device buffers), which is also
- * what pageable buffers get. */
+ * what pageable buffers get.  Tuning values: 2..8 = zero copy with (zero_copy - 1) resident CTAs per SM. */
 int cavgym_set_host_path(CavEngine* engine, int zero_copy);
 
 /* CAVEnv.current_timestep (environment.py:90,222) is never reset by the reference;

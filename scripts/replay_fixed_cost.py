@@ -27,6 +27,8 @@ def main():
     parser.add_argument("--steps", default="1,2,5,10,20,40,80,160")
     parser.add_argument("--no-tma", action="store_true")
     parser.add_argument("--no-record", action="store_true")
+    parser.add_argument("--train", type=int, default=40, help="also time TRAIN launches of --train-steps steps issued back to back (one event pair)")
+    parser.add_argument("--train-steps", type=int, default=20)
     parser.add_argument("--chain", type=int, default=0, help="also time CHAIN consecutive launches (no kernel in between) of the longest step count / CHAIN")
     args = parser.parse_args()
     dev = torch.device("cuda", 0)
@@ -80,6 +82,23 @@ def main():
             tag = "queued " if gated else "starved"
             print(f"steps {steps:4d} {tag}: min {us[0]:8.1f}  med {us[len(us) // 2]:8.1f}  max {us[-1]:8.1f} us   "
                   f"med/step {us[len(us) // 2] / steps:6.2f} us")
+    if args.train:
+        steps, k = args.train_steps, args.train
+        totals = []
+        for rep in range(8):
+            env.reset(init_state=at_start)
+            torch.cuda.synchronize()
+            torch.cuda._sleep(int(0.01 * 1.9e9))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for j in range(k):
+                replay(args.start + (j * steps) % max(1, longest - steps + 1), steps)
+            b.record()
+            torch.cuda.synchronize()
+            totals.append(a.elapsed_time(b) * 1e3 / k)
+        totals.sort()
+        print(f"train of {k} x {steps} steps back to back: min {totals[0]:8.1f}  med {totals[len(totals) // 2]:8.1f} us per launch   "
+              f"{totals[len(totals) // 2] / steps:6.2f} us per step")
     if args.chain:
         k = args.chain
         steps = longest // k
