@@ -27,7 +27,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N_ENVS = 65536          # per GPU (weak scaling)
-SEGMENT = 500           # steps replayed from a fresh reset before resetting again (ego finishes at step 901)
+SEGMENT = 250           # steps replayed from a fresh reset before the whole batch is reset again: a finished env stays frozen
+                        # (and uncounted) until then — 3 % of the env-steps at 250, 10 % at 500 (the ego finishes at step 901)
 REGION_REPEATS = 50     # the --steps-long timed region is repeated this many times back to back (all launches pre-enqueued)
 CHUNK = 250             # steps fused per cavgym_replay launch (50: 16.0, 100: 17.9, 250: 20.3, 500: 20.8 G env-steps/s)
 HBM_ENVS = 4 * 1024 * 1024
@@ -136,6 +137,7 @@ def make_trace(torch, device, n_envs, n_steps, dtype, env_offset, advance=0):
 
 def run_ours(args):
     chunk = max(1, min(int(args.chunk), SEGMENT, args.steps))   # steps fused per cavgym_replay launch
+    segment = SEGMENT // chunk * chunk                          # whole launches between resets (240 steps at 20 per launch)
     import torch
     import torch.distributed as dist
     from cavgym_b200 import BatchedCAVEnv
@@ -150,7 +152,7 @@ def run_ours(args):
     bytes_env_step = m * BYTES_PER_BODY_STEP[dtype] + BYTES_PER_ENV_STEP_EXTRA
     peak_gbs, peak_src = peaks()
 
-    init, actions = make_trace(torch, device, n, SEGMENT, dtype, env_offset=sharding.shard_offset(rank, n))
+    init, actions = make_trace(torch, device, n, segment, dtype, env_offset=sharding.shard_offset(rank, n))
     env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=scenario("external"), device=device,
                         env_offset=sharding.shard_offset(rank, n))
     # Trajectory slabs: 5.24 MB per step.  Launches rotate over `slots` slabs so that >= 315 MB (2.5 x the 126 MB L2) are
@@ -172,12 +174,12 @@ def run_ours(args):
     launch_events, region_events, launch_no = [], [], [0]
 
     def advance(n_steps, cursor, timed):
-        """Replay n_steps starting at trace position `cursor` (resetting every SEGMENT steps); returns new cursor."""
+        """Replay n_steps starting at trace position `cursor` (resetting every `segment` steps); returns new cursor."""
         done = 0
         while done < n_steps:
             if cursor == 0:
                 env.reset(init_state=init)
-            take = min(chunk, n_steps - done, SEGMENT - cursor)
+            take = min(chunk, n_steps - done, segment - cursor)
             if timed:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
@@ -189,7 +191,7 @@ def run_ours(args):
                 b.record()
                 launch_events.append((a, b, take))
             done += take
-            cursor = (cursor + take) % SEGMENT
+            cursor = (cursor + take) % segment
         return cursor
 
     def barrier():
@@ -203,14 +205,14 @@ def run_ours(args):
     # every repetition is enqueued while a gate kernel keeps the stream busy, so no host launch latency sits between
     # the events: they time the GPU, not the Python loop (at --steps 20 one region is a single ~70 us launch).
     advance(args.warmup, 0, False)
-    cursor = 0   # the first timed region starts from a fresh reset: regions tile the SEGMENT-step trace whenever --steps divides it
+    cursor = 0   # the first timed region starts from a fresh reset: regions tile the segment-step trace whenever --steps divides it
     barrier()
     before, launches_before = env.stats(), env.launch_count()
     sampler = ClockSampler(local)
     sampler.start()
     sampler.ready.wait(timeout=10)    # NVML initialised before the timed region starts
     repeats = max(1, args.repeats)
-    launches_per_region = -(-args.steps // chunk) + args.steps // SEGMENT + 2
+    launches_per_region = -(-args.steps // chunk) + args.steps // segment + 2
     barrier()
     if args.profile_region:      # ncu --profile-from-start off: capture exactly the timed region
         torch.cuda.profiler.start()
@@ -286,17 +288,17 @@ def run_ours(args):
            "config": {"workload": "C2: pedestrians scenario (Car + SpawnPedestrian) x 65,536 envs per GPU, replayed joint "
                                   f"actions (on-device RandomConstrained eps=0.01 trace), cavgym_replay {steps_per_launch:g} steps/launch, "
                                   f"trajectories recorded, region of {args.steps} steps repeated {repeats}x",
-                      "envs_per_gpu": n, "bodies": m, "segment": SEGMENT,
+                      "envs_per_gpu": n, "bodies": m, "segment": segment,
                       "l2": f"{slots} rotating trajectory slabs ({slab_steps * 5.24e6 / 1e9:.2f} GB) and the action trace (1 GB) exceed L2; state is register resident",
                       "live_fraction": round(live_fraction, 4)},
            "roofline": roofline, "gpu_launches": int(gpu_launches), "clocks": clocks}
 
     if rank == 0 or world > 1:
         # ---- end to end through the host-buffer API (every rank; max over ranks) -------------
-        e2e_steps = max(3, args.e2e_steps)   # its own length: 20 calls of 0.15 ms would be a 3 ms measurement
+        e2e_steps = max(3, min(args.e2e_steps, segment - 3))   # its own length: 20 calls of 0.15 ms would be a 3 ms measurement
         np_dtype = "float64" if dtype == "float64" else "float32"
         import numpy as np
-        h_actions = torch.empty((SEGMENT, m, 2, n), dtype=env.dtype).pin_memory()
+        h_actions = torch.empty((segment, m, 2, n), dtype=env.dtype).pin_memory()
         h_actions.copy_(actions)
         h_state = torch.empty((m, 4, n), dtype=env.dtype).pin_memory()
         h_reward = torch.empty((m, n), dtype=env.dtype).pin_memory()

@@ -517,7 +517,7 @@ __device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const
   if (AGENTS && __any_sync(kFull, agent_invalid) && lane == 0) buf.err[e] = 1;   // cannot happen with the stock agents
 
   // ---- termination cascade (environment.py:148-206)
-  if (phase_sync) __syncthreads();   // (launch-uniform) the warps of the CTA enter each phase together: shared instruction fetches
+  if (phase_sync) { __syncwarp(); __syncthreads(); }   // (launch-uniform) the warps of the CTA enter each phase together: shared instruction fetches
   const DevType<R>& k0 = tb.types[sm.meta[0] & DM_TYPE_MASK];
   const R x0 = sm.x[0], y0 = sm.y[0], c0 = sm.c[0], s0 = sm.s[0];
   R ex0, ey0;
@@ -663,7 +663,7 @@ __device__ __forceinline__ void dense_transition(const DevScenario<R>& sc, const
   }
 
   // ---- rewards, liveness (environment.py:131-146), terminal rewards and winner (:208-220)
-  if (phase_sync) __syncthreads();
+  if (phase_sync) { __syncwarp(); __syncthreads(); }
   const R cstep = sc.cost_step;
   const R ego_rel = rmax(R(0), rmin(R(1), (W - x0) * sc.inv_W));
   const bool terminal = terminate || t_global == sc.max_timesteps - 1;

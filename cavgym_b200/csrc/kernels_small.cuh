@@ -12,6 +12,7 @@
 // Roofline: HBM-bound streaming; algorithmic bytes per body-step 88 B (fp64) / 44 B (fp32)
 // on replayed actions.  No shared memory: there is no reuse across envs.
 #pragma once
+#include <type_traits>
 #include "transition.cuh"
 
 namespace cav {
@@ -123,9 +124,11 @@ __device__ __forceinline__ void write_outputs(const EnvBuffers<R>& buf, const St
 // One transition of env e held in `env`, with all the bookkeeping shared by the three kernels: frozen envs, invalid
 // actions, outputs, latching and scoring.  Returns true if the episode ended in this step.  One output site: frozen
 // (finished, not yet reset) envs report reward 0 and their latched done / winner through the same stores.
-template <typename R, int M, bool AGENTS, bool GENERIC>
+// `ghost`: the lane steps a COPY of env e to keep its warp whole (rollout_kernel); nothing it does may be seen.
+template <typename R, int M, bool AGENTS, bool GENERIC, typename Phase = NoPhase>
 __device__ __forceinline__ bool advance(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t e,
-                                        int64_t t_global, EnvRegs<R, M>& env, const R (&ext)[M][2]) {
+                                        int64_t t_global, EnvRegs<R, M>& env, const R (&ext)[M][2], Phase phase = Phase(),
+                                        const bool ghost = false) {
   StepResult<R, M> res;
   bool ended = false;
   if (env.done) {  // frozen until reset
@@ -135,15 +138,15 @@ __device__ __forceinline__ bool advance(const DevScenario<R>& sc, const EnvBuffe
     res.winner = env.winner;
     res.tangent = false;
   } else {
-    transition<R, M, AGENTS, GENERIC>(sc, buf, e, t_global, env, ext, res);
-    if (res.invalid) buf.err[e] = 1;
-    if (res.tangent) count_tangent(buf.stats);
-    if (env.done) {
-      score_episode<R, M>(buf, env, e, AGENTS ? env.episode : -1);
-      ended = true;
+    transition<R, M, AGENTS, GENERIC, NoSink, Phase>(sc, buf, e, t_global, env, ext, res, NoSink(), phase);
+    if (!ghost) {
+      if (res.invalid) buf.err[e] = 1;
+      if (res.tangent) count_tangent(buf.stats);
+      if (env.done) score_episode<R, M>(buf, env, e, AGENTS ? env.episode : -1);
     }
+    ended = env.done != 0;
   }
-  write_outputs<R, M>(buf, io, e, env, res.reward, res.terminate, res.winner, res.tangent);
+  if (!ghost) write_outputs<R, M>(buf, io, e, env, res.reward, res.terminate, res.winner, res.tangent);
   return ended;
 }
 
@@ -206,38 +209,46 @@ __global__ void __launch_bounds__(kLoopThreads, CAV_MIN_BLOCKS_LOOP) replay_kern
 // The heterogeneous scenarios (crossroads, bus stop, pelican crossing) re-align the warps of a CTA once per step (bar.sync):
 // their transition is 5,000 warp-instructions of branchy code per step and the path is bound by instruction fetch
 //  — warps that drift apart over the fused steps each stream the code through the 32 KB instruction cache on
-// their own, warps that walk it together share the fetches.  Measured at 1,048,576 envs, 100 steps per launch: bus stop
-// 1.69 -> 1.89 G env-steps/s, pelican crossing 3.39 -> 3.60, crossroads 3.39 -> 3.46; the two-body pedestrians kernel loses
-// 11 % with the same barrier (its loop fits the cache), so it keeps running free.
+// their own, warps that walk it together share the fetches.  Measured at 1,048,576 envs, 100 steps per launch, with the
+// barrier at the top of the step and at the three phase boundaries inside the transition (CtaPhase): bus stop
+// 1.69 -> 2.03 G env-steps/s, crossroads 3.39 -> 3.60, pelican crossing 3.39 -> 3.55; the two-body pedestrians kernel loses
+// 11 % with a per-step barrier (its loop fits the cache), so it keeps running free.
 #ifndef CAV_ROLLOUT_SYNC_FROM_M
 #define CAV_ROLLOUT_SYNC_FROM_M 3
 #endif
+
 template <typename R, int M, bool GENERIC>
 __global__ void __launch_bounds__(kRolloutThreads, CAV_MIN_BLOCKS_ROLLOUT) rollout_kernel(const __grid_constant__ DevScenario<R> sc,
                                                            const __grid_constant__ EnvBuffers<R> buf, int64_t t_global,
                                                            int n_steps, int auto_reset) {
   const int64_t e_raw = buf.lo + (int64_t)blockIdx.x * kRolloutThreads + threadIdx.x;
   const bool in_range = e_raw < buf.hi;
-  const int64_t e = in_range ? e_raw : buf.lo;
   constexpr bool kSync = GENERIC && M >= CAV_ROLLOUT_SYNC_FROM_M;
-  if (!kSync && !in_range) return;
+  using Phase = typename std::conditional<kSync, CtaPhase, NoPhase>::type;
+  // Barriers need every lane of every warp of the CTA to run every step: auto-reset (no env stays finished) and, for the
+  // lanes of a ragged last CTA that have no env, a copy of the batch's last env stepped as a ghost.
+  const bool sync_on = kSync && auto_reset != 0;
+  if (!in_range && !sync_on) return;
+  const bool ghost = !in_range;
+  const int64_t e = in_range ? e_raw : buf.hi - 1;
+  Phase phase;
+  if constexpr (kSync) phase.on = sync_on;
   EnvRegs<R, M> env;
   load_env<R, M, true>(sc, buf, e, env);
   const StepIO<R> io = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   R ext[M][2];
   load_actions<R, M>(nullptr, buf.n, e, ext);
-  bool was_reset = false, stopped = !in_range;
+  bool was_reset = false;
   for (int t = 0; t < n_steps; ++t) {
-    if (kSync) __syncthreads();
-    if (stopped) { if (kSync) continue; else break; }
+    if (sync_on) { __syncwarp(); __syncthreads(); }
     if (env.done) {
-      if (!auto_reset) { stopped = true; continue; }
+      if (!auto_reset) break;
       reset_env<R, M>(sc, buf, nullptr, e, env);
       was_reset = true;
     }
-    advance<R, M, true, GENERIC>(sc, buf, io, e, t_global + t, env, ext);
+    advance<R, M, true, GENERIC, Phase>(sc, buf, io, e, t_global + t, env, ext, phase, ghost);
   }
-  if (!in_range) return;
+  if (ghost) return;
   if (auto_reset && env.done) { reset_env<R, M>(sc, buf, nullptr, e, env); was_reset = true; }
   store_env<R, M, true>(sc, buf, e, env, was_reset);
 }

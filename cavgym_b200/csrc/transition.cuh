@@ -131,6 +131,20 @@ struct StepResult {
 struct NoSink {
   template <typename E> __device__ __forceinline__ void operator()(const E&) const {}
 };
+// `phase()` is called at the three phase boundaries of a transition (after the joint action, after body.step, after the
+// termination cascade) — by EVERY thread that enters the transition, on every path out of it.  CtaPhase makes each a
+// block-wide barrier: a kernel whose threads all run one transition per step (the rollout kernels of the heterogeneous
+// scenarios) keeps the warps of a CTA inside the same phase, so they share instruction fetches.
+constexpr int kTransitionPhases = 3;
+struct NoPhase { static constexpr bool kBarrier = false; __device__ __forceinline__ void operator()() const {} };
+// The barrier is `bar.sync` (aligned): all 32 lanes of a warp must arrive together, so a kernel that uses CtaPhase makes
+// EVERY lane run the transition on every step (lanes without an env of their own step a copy of a neighbour's with the side
+// effects switched off, kernels_small.cuh) and re-converges the warp before each barrier.  `on` is launch-uniform.
+struct CtaPhase {
+  static constexpr bool kBarrier = true;
+  bool on;
+  __device__ __forceinline__ void operator()() const { if (on) { __syncwarp(); __syncthreads(); } }
+};
 
 // `moved(env)` is called once, right after body.step: a kernel that stages state in shared memory writes the new
 // state there at that point, so x, y, v, theta need not stay in registers through the geometry.
@@ -162,31 +176,31 @@ struct NoSink {
 #endif
 
 #define CAV_BODY_LOOP _Pragma("unroll")
-template <typename R, int M, bool AGENTS, bool GENERIC, typename Sink = NoSink>
+template <typename R, int M, bool AGENTS, bool GENERIC, typename Sink = NoSink, typename Phase = NoPhase>
 __device__ __forceinline__ void transition_unrolled(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, int64_t t_global,
                                                     EnvRegs<R, M>& env, const R (&ext)[M][2], StepResult<R, M>& out,
-                                                    Sink moved = Sink()) {
+                                                    Sink moved = Sink(), Phase phase = Phase()) {
 #include "transition_body.inc"
 }
 #undef CAV_BODY_LOOP
 
 #define CAV_BODY_LOOP _Pragma("unroll 1")
-template <typename R, int M, bool AGENTS, bool GENERIC, typename Sink = NoSink>
+template <typename R, int M, bool AGENTS, bool GENERIC, typename Sink = NoSink, typename Phase = NoPhase>
 __device__ __forceinline__ void transition_rolled(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, int64_t t_global,
                                                   EnvRegs<R, M>& env, const R (&ext)[M][2], StepResult<R, M>& out,
-                                                  Sink moved = Sink()) {
+                                                  Sink moved = Sink(), Phase phase = Phase()) {
 #include "transition_body.inc"
 }
 #undef CAV_BODY_LOOP
 
-template <typename R, int M, bool AGENTS, bool GENERIC, typename Sink = NoSink>
+template <typename R, int M, bool AGENTS, bool GENERIC, typename Sink = NoSink, typename Phase = NoPhase>
 __device__ __forceinline__ void transition(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t e, int64_t t_global,
                                            EnvRegs<R, M>& env, const R (&ext)[M][2], StepResult<R, M>& out,
-                                           Sink moved = Sink()) {
+                                           Sink moved = Sink(), Phase phase = Phase()) {
   if constexpr ((GENERIC && M >= CAV_ROLLED_FROM_M) || (!GENERIC && AGENTS && M >= CAV_ROLLED_HOMOGENEOUS_FROM_M) ||
                 (!GENERIC && !AGENTS && M >= CAV_ROLLED_HOMOGENEOUS_REPLAY_FROM_M) ||
-                (AGENTS && CAV_ROLL_AGENTS != 0 && M >= 2)) transition_rolled<R, M, AGENTS, GENERIC, Sink>(sc, buf, e, t_global, env, ext, out, moved);
-  else transition_unrolled<R, M, AGENTS, GENERIC, Sink>(sc, buf, e, t_global, env, ext, out, moved);
+                (AGENTS && CAV_ROLL_AGENTS != 0 && M >= 2)) transition_rolled<R, M, AGENTS, GENERIC, Sink, Phase>(sc, buf, e, t_global, env, ext, out, moved, phase);
+  else transition_unrolled<R, M, AGENTS, GENERIC, Sink, Phase>(sc, buf, e, t_global, env, ext, out, moved, phase);
 }
 
 // reporting.analyse_episode (reporting.py:227-243) for an env whose episode just ended.  The lanes of a warp that end their

@@ -120,6 +120,31 @@ def test_dense_rollout_with_device_agents_is_bitwise_equal_to_thread_per_env_rol
     assert results[0][5]["episodes"] >= n
 
 
+@pytest.mark.parametrize("name", ["busstop_random_all_seed8", "pelican_random_all_seed10", "crossroads_random_all_seed6"])
+def test_rollout_without_auto_reset_on_a_ragged_batch(name):
+    """The heterogeneous rollout kernels put block-wide barriers inside the step (kernels_small.cuh): lanes without an env
+    (130 envs = four warps and two lanes) and envs that finished and stay finished (auto_reset off) must pass the same
+    barriers as the lanes that are stepping.  Thread-per-env and warp-per-env paths must agree bitwise, and finished envs
+    must stop where they ended."""
+    meta, _ = load_golden(name)
+    n = 130
+    results = []
+    for dense in (False, True):
+        env = make(compile_from_meta(meta, mode="device"), n, "float64", seed=4)
+        env.set_dense_path(dense)
+        env.reset()
+        env.rollout(500, auto_reset=False)
+        frozen = env.state.clone()
+        finished = env.done_latch.clone() != 0
+        env.rollout(300, auto_reset=False)
+        state = env.state.cpu().numpy()
+        assert np.array_equal(state[:, :, finished.cpu().numpy()], frozen.cpu().numpy()[:, :, finished.cpu().numpy()])
+        results.append((state, env.timestep.cpu().numpy(), env.done_latch.cpu().numpy(), env.stats()))
+    assert np.array_equal(results[0][0], results[1][0]) and np.array_equal(results[0][1], results[1][1])
+    assert np.array_equal(results[0][2], results[1][2]) and results[0][3] == results[1][3]
+    assert results[0][2].any()
+
+
 # ------------------------------------------------------------------ dense traffic (C4) vs the oracle
 def check_against_oracle(got, want, dtype):
     """Trajectories [T, ...]: events identical off flagged steps; state / rewards compared up to the first flagged
