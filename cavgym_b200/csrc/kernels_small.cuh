@@ -258,13 +258,16 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__
                                                          const __grid_constant__ EnvBuffers<R> buf, const uint8_t* mask,
                                                          const R* init, int first_time) {
   const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (e >= buf.hi || (mask && !mask[e])) return;
+  const bool mine = e < buf.hi && (!mask || mask[e]);
+  // an unfinished episode is abandoned: keep its steps in the env-step total.  One atomic per warp, not per env: a reset of
+  // a whole batch mid-episode would otherwise queue 65,536 atomics on one counter (35 us for a 5 us kernel).
+  unsigned long long abandoned = 0;
+  if (mine && !first_time && !buf.done[e]) abandoned = (unsigned long long)buf.t_ep[e];
+  abandoned = warp_sum(abandoned);
+  if ((threadIdx.x & 31) == 0 && abandoned) atomicAdd(&buf.stats[CAV_STAT_ENV_STEPS], abandoned);
+  if (!mine) return;
   EnvRegs<R, M> env;
   env.episode = first_time ? -1 : buf.episode[e];
-  if (!first_time && !buf.done[e]) {  // an unfinished episode is abandoned: keep its steps in the env-step total
-    const int32_t t = buf.t_ep[e];
-    if (t > 0) atomicAdd(&buf.stats[CAV_STAT_ENV_STEPS], (unsigned long long)t);
-  }
   reset_env<R, M>(sc, buf, init, e, env);
   store_env<R, M, true>(sc, buf, e, env, true);
   if (first_time) buf.err[e] = 0;

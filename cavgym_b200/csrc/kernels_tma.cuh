@@ -107,6 +107,11 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // make this thread's shared-memory writes (generic proxy) visible to the bulk-copy engine (async proxy)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Programmatic dependent launch (launch_replay_tma): `launch_dependents` lets the next kernel of the stream start its CTAs
+// as soon as SM resources free up; `wait` blocks until the previous grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // One SoA row as the producer sees it: where its segment for unit 0 (tile 0 / step 0) starts in HBM, how far the next
 // unit's segment is, where it lives in a stage, and the element size (segment bytes = envs in the tile * elem).
 struct TmaRow {
@@ -361,6 +366,7 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
   const int64_t tile_lo = buf.lo + (int64_t)blockIdx.x * T;   // first env of this CTA's tile
   const uint32_t cnt = (uint32_t)((buf.hi - tile_lo) < T ? (buf.hi - tile_lo) : T);
   constexpr int n_in = M * 2;
+  pdl_launch_dependents();
 
   if (tid == 0) {
 #pragma unroll
@@ -420,6 +426,10 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
   }
 
   // ================= consumer warps
+  // The set-up above and the producer's first action loads do not depend on the previous launch and overlap its tail; the
+  // env state does (the previous launch wrote it): read it once the programmatic dependency has resolved.  Everything this
+  // kernel writes follows from here (the producer's stores wait for the consumers' first step).
+  pdl_wait();
   const bool active = (uint32_t)tid < cnt;
   const int64_t e = tile_lo + (active ? tid : 0);
   EnvRegs<R, M> env;
@@ -561,7 +571,20 @@ bool launch_replay_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const
   EnvBuffers<R> range = buf;
   range.hi = buf.lo + span;
   const int64_t tiles = (span + kReplayTile - 1) / kReplayTile;
-  kernel<<<(unsigned)tiles, kReplayTile + 32, L::kSmemBytes, stream>>>(sc, range, io, t_global, n_steps);
+  // Programmatic dependent launch: behind another replay launch in the stream this grid's CTAs start (barrier set-up, first
+  // action loads) while that grid drains, and read the env state after griddepcontrol.wait; behind any other kernel the
+  // attribute changes nothing.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)tiles);
+  cfg.blockDim = dim3(kReplayTile + 32);
+  cfg.dynamicSmemBytes = L::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kernel, sc, range, io, t_global, n_steps) != cudaSuccess) return false;
   *envs_done = span;
   return true;
   }
