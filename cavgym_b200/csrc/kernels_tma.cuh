@@ -152,6 +152,10 @@ __global__ void __launch_bounds__(kStepTile + 32, CAV_MIN_BLOCKS_TMA) step_tma_k
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);   // [stages] tile landed (producer -> consumers)
   uint64_t* done = full + kTmaStages;                                    // [stages] tile computed (consumers -> producer)
+  // [stages] bit k: state row k (body k / 4, component k % 4) changed for some env of the tile.  A row nobody changed — the
+  // velocity and heading of a body that neither accelerates nor turns: three of the eight rows in the stock scenario — is
+  // not written back to the engine's state.
+  uint32_t* changed = reinterpret_cast<uint32_t*>(smem + L::kBarOffset + 64);
   TmaRow* in_rows = reinterpret_cast<TmaRow*>(smem + L::kTableOffset);
   TmaRow* out_rows = in_rows + L::kMaxRows;
   __shared__ int n_in_s, n_out_s, in_elems_s;
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(kStepTile + 32, CAV_MIN_BLOCKS_TMA) step_tma_k
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kTmaStages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kStepWarps); }
+    for (int s = 0; s < kTmaStages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kStepWarps); changed[s] = 0u; }
     mbar_fence_init();
     // row tables (a few dozen entries, once per CTA)
     int ni = 0, no = 0, elems = 0;
@@ -222,11 +226,15 @@ __global__ void __launch_bounds__(kStepTile + 32, CAV_MIN_BLOCKS_TMA) step_tma_k
       unsigned char* st = smem + s * L::kStageBytes;
       const uint32_t cnt = envs_in(tile);
       mbar_wait(&done[s], parity);   // every consumer warp has written its results for this tile
+      const uint32_t dirty = changed[s];   // (the consumers' atomicOr precedes their arrival on done[s])
       for (int r = lane; r < n_out; r += 32) {
+        if (r < M * 4 && !(dirty >> r & 1u)) continue;   // the first M * 4 output rows are the engine's state, in place
         const TmaRow row = out_rows[r];
         bulk_store(reinterpret_cast<void*>(row.gbase + (unsigned long long)tile * row.unit_stride), st + row.smem_off, row.elem * cnt);
       }
       bulk_commit();
+      __syncwarp();
+      if (lane == 0) changed[s] = 0u;      // before the stage is handed out again (ordered by the arrival in issue_loads)
       const int64_t next = tile + (int64_t)kTmaStages * stride;
       if (next < n_tiles) {
         bulk_wait_read_all();   // the stores above have read the stage: it may be overwritten
@@ -245,6 +253,7 @@ __global__ void __launch_bounds__(kStepTile + 32, CAV_MIN_BLOCKS_TMA) step_tma_k
     const uint32_t parity = (uint32_t)(it / kTmaStages) & 1u;
     unsigned char* st = smem + s * L::kStageBytes;
     mbar_wait(&full[s], parity);
+    uint32_t mine_changed = 0u;
     if ((uint32_t)tid < envs_in(tile)) {
       // ---- this thread's env: shared memory -> registers
       const int64_t e = lo + tile * T + tid;
@@ -288,7 +297,11 @@ __global__ void __launch_bounds__(kStepTile + 32, CAV_MIN_BLOCKS_TMA) step_tma_k
 #pragma unroll
           for (int b = 0; b < M; ++b)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) sS[(b * 4 + c) * T + tid] = now.s[b][c];
+            for (int c = 0; c < 4; ++c) {
+              const R was = sS[(b * 4 + c) * T + tid];
+              if (!(was == now.s[b][c])) mine_changed |= 1u << (b * 4 + c);
+              sS[(b * 4 + c) * T + tid] = now.s[b][c];
+            }
         };
         transition<R, M, false, GENERIC>(sc, buf, e, t_global, env, ext, res, moved);
         if (res.invalid) buf.err[e] = 1;
@@ -315,9 +328,13 @@ __global__ void __launch_bounds__(kStepTile + 32, CAV_MIN_BLOCKS_TMA) step_tma_k
       st[L::oTangent + tid] = res.tangent ? 1 : 0;
     }
     // ---- hand the tile to the producer: writes visible to the bulk-copy engine, one arrival per warp
+    mine_changed = __reduce_or_sync(0xffffffffu, mine_changed);
     fence_async_smem();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&done[s]);
+    if (lane == 0) {
+      if (mine_changed) atomicOr(&changed[s], mine_changed);
+      mbar_arrive(&done[s]);
+    }
   }
 }
 
