@@ -3,7 +3,7 @@
 Environments are independent (reference library/environment.py:119-223 has no cross-env term; the reference itself
 parallelises by process, experiments.py:121-122), so rank r of R owns the contiguous global env range
 [r * n, (r + 1) * n) (weak scaling, n envs per GPU), the Philox streams are keyed by the GLOBAL env id
-(cavgym_set_shard), and there is no collective in the step.  Only the ten episode counters (reporting.py:227-269) are
+(cavgym_set_shard), and there is no collective in the step.  Only the twelve episode counters (reporting.py:227-269) are
 summed at the end with ONE all-reduce (NCCL over NVLink on the GPU box, gloo in the CPU tests).
 """
 import os
@@ -39,7 +39,7 @@ def split_envs(total_envs, world):
 
 
 def reduce_stats(stats, device=None, group=None):
-    """Sum the episode counters of every rank: one all-reduce of ten int64 words.  `stats` is the dict returned by
+    """Sum the episode counters of every rank: one all-reduce of twelve int64 words.  `stats` is the dict returned by
     BatchedCAVEnv.stats(); returns the same dict summed over ranks (unchanged without a process group)."""
     import torch
     import torch.distributed as dist
