@@ -2,8 +2,8 @@
 scenario is written with.  In this engine a Body is a DESCRIPTOR — init_state,
 constants and class (Car / Pedestrian / SpawnPedestrian / ...) are compiled by
 cavgym_b200/scenario.py into the device tables; the per-step integration
-(reference DynamicBody.step :214-275) runs in csrc/step_kernels.cuh for all
-environments at once.  `body.state` is refreshed from the device by the
+(reference DynamicBody.step :214-275) runs in the CUDA kernels (csrc/agents.cuh: body_step,
+shared by every kernel through csrc/transition.cuh) for all environments at once.  `body.state` is refreshed from the device by the
 single-environment compat view (library/environment.py) after every step.
 """
 import math
@@ -111,7 +111,7 @@ class DynamicBody(Body, Occlusion):
 
     def stopping_zones(self):
         """Braking and reaction zones ahead of the body (reference :122-135); the device
-        evaluates the same construction every step (csrc/geometry.cuh: ego_zones)."""
+        evaluates the same construction every step (csrc/geometry.cuh: EgoFrame, ego_margins)."""
         braking = (self.state.velocity ** 2) / (2 * -self.constants.min_throttle)
         total = braking + self.state.velocity * REACTION_TIME
         if total == 0 or self.steering_angle != 0:

@@ -32,6 +32,10 @@ def build(name):
     cfg = refload.stock_config_dict(**CASES[name])
     config = mods["config"].make_config(json.loads(json.dumps(cfg)))
     _, env, agents, _ = config.setup()
+    for agent in agents:   # a RandomAgent ego is built on an unseeded import-time generator (config.py:305-310): seed it, like trace.record
+        own = getattr(agent, "np_random", None)
+        if own is not None and own is not env.np_random:
+            agent.np_random = np.random.RandomState(10_000 + int(cfg.get("seed") or 0))
     state = env.reset()
     info = env.info()
     for agent in agents:
