@@ -127,3 +127,28 @@ def test_batched_simulation_writes_one_episode_row_per_episode(tmp_path):
     if stats["tangent"] == 0:
         for env, episode, result in rows:
             assert done_at[(env, episode)] == (result.time.timesteps, result.interesting), (env, episode)
+
+
+def test_episode_ring_reports_what_it_dropped():
+    """A full ring drops rows but not counts: drained + dropped = episodes scored since the last drain, and the ring is empty
+    and usable again afterwards."""
+    from helpers import compile_from_meta as compile_, load_golden as load
+    from cavgym_b200 import BatchedCAVEnv
+    meta, _ = load("pedestrians_rc_eps05_seed1")
+    env = BatchedCAVEnv(None, None, None, num_envs=512, dtype="float64", compiled=compile_(meta, mode="device"), seed=2)
+    env.set_episode_log(100)
+    env.reset()
+    env.rollout(1000, auto_reset=True)
+    episodes = env.stats()["episodes"]
+    rows, dropped = env.drain_episodes()
+    assert episodes > 512 and len(rows) == 100 and dropped == episodes - 100
+    assert np.all(rows["episode"] >= 1) and np.all((rows["timesteps"] >= 1) & (rows["timesteps"] <= 1000))
+    assert np.all((rows["env"] >= 0) & (rows["env"] < 512))
+    env.rollout(50, auto_reset=True)
+    rows2, dropped2 = env.drain_episodes()
+    assert len(rows2) + dropped2 == env.stats()["episodes"] - episodes
+    env.set_episode_log(0)
+    env.rollout(50, auto_reset=True)      # ring off: scoring continues, nothing is appended
+    with pytest.raises(Exception):
+        env.drain_episodes()
+    env.close()
