@@ -4,11 +4,13 @@
                              table, one TD(0) update per step.  Draw for draw and operation for operation the reference's
                              arithmetic, so a run through `Simulation` reproduces the reference's actions and weights
                              (tests/test_learning_agents.py, fixtures recorded from the unmodified reference).
-  BatchedQLearningEgoAgent   the same learner on the tensor API of BatchedCAVEnv: N environments feed ONE weight table.
-                             Features, Q values, the greedy choice and the TD targets are torch expressions over [N] on the
-                             device the engine steps on (no host round trip per step); the N transitions of a batch step
-                             are applied as one averaged update.  With N = 1 and the same draws it is the reference's
-                             update sequence (checked against the host class).
+  BatchedQLearningEgoAgent   the same learner on the tensor API of BatchedCAVEnv.  Features, Q values, the greedy choice and
+                             the TD targets are torch expressions over [N] on the device the engine steps on (no host round
+                             trip per step).  Two forms: `shared=True` — N environments feed ONE weight table, the N
+                             transitions of a batch step applied as one averaged update (with N = 1 and the same draws it is
+                             the reference's update sequence, checked against the host class); `shared=False` — every
+                             environment is its OWN learner (own table, own alpha / gamma / epsilon): N independent runs of
+                             the reference's agent side by side, which is what experiments.py's grid is (cavgym_b200/experiments.py).
 
 Features (ego.py:96-145), per opponent i, after a two-step no-steering look-ahead of the ego under the candidate throttle
 and of the opponent under zero throttle — both clamped with the EGO's velocity limits, as the reference does:
@@ -127,29 +129,52 @@ class BatchedQLearningEgoAgent:
 
     choose_action(state [M,4,N]) -> (action index [N] int64, ego action rows [2,N]); process_feedback(previous_state,
     action index, state, ego reward [N], live [N] bool) applies  w += alpha * mean_e(difference_e * features_e)  over the
-    live environments and advances the alpha schedule once.  `weights` is [opponents, features]."""
+    live environments (shared table, `weights` [opponents, features]) or  w_e += alpha_e * difference_e * features_e  per
+    environment (independent learners, `weights` [N, opponents, features]) and advances the alpha schedule once."""
 
     def __init__(self, q_learning_config, ego_constants, time_resolution, num_opponents, width, height, num_envs, device,
-                 num_actions=5, dtype=None, seed=0):
+                 num_actions=5, dtype=None, seed=0, shared=True, alpha=None, gamma=None, epsilon=None):
+        """`alpha` = (start, stop, num_steps), `gamma`, `epsilon`: per-environment overrides of the config's values, each a
+        scalar or a length-N sequence (independent learners of a hyper-parameter grid)."""
         import torch
         self.torch = torch
         self.device, self.dtype = device, dtype or torch.float64
-        self.epsilon, self.gamma = float(q_learning_config.epsilon), float(q_learning_config.gamma)
-        schedule = q_learning_config.alpha
-        self._alphas = np.linspace(start=schedule.start, stop=schedule.stop, num=schedule.num_steps, endpoint=True)
-        self._alpha_at, self.target_alpha = 0, schedule.stop
-        self.k, self.dt = ego_constants, float(time_resolution)
+        self.shared = bool(shared)
         self.num_envs, self.num_opponents = int(num_envs), int(num_opponents)
+
+        def per_env(value, default):
+            value = default if value is None else value
+            if np.ndim(value) == 0:
+                return float(value)
+            return torch.as_tensor(np.asarray(value, dtype=np.float64), device=device).reshape(self.num_envs)
+
+        schedule = q_learning_config.alpha
+        start, stop, num_steps = alpha if alpha is not None else (schedule.start, schedule.stop, schedule.num_steps)
+        self.epsilon, self.gamma = per_env(epsilon, q_learning_config.epsilon), per_env(gamma, q_learning_config.gamma)
+        self._alpha_start, self._alpha_stop, self._alpha_steps = per_env(start, None), per_env(stop, None), per_env(num_steps, None)
+        if all(np.ndim(v) == 0 for v in (start, stop, num_steps)):   # the reference's own table of values, bit for bit
+            self._alphas = np.linspace(start=start, stop=stop, num=int(num_steps), endpoint=True)
+        else:
+            self._alphas = None
+        self._alpha_at, self.target_alpha = 0, stop
+        self.k, self.dt = ego_constants, float(time_resolution)
         self.bounds = feature_bounds(q_learning_config.features, width, height)
         self.names = list(self.bounds)
         self.throttles = torch.linspace(ego_constants.min_throttle, ego_constants.max_throttle, num_actions, dtype=torch.float64, device=device)
-        self.weights = torch.zeros((self.num_opponents, len(self.names)), dtype=torch.float64, device=device)
+        table = (self.num_opponents, len(self.names))
+        self.weights = torch.zeros(table if self.shared else (self.num_envs,) + table, dtype=torch.float64, device=device)
         self.generator = torch.Generator(device=device)
         self.generator.manual_seed(int(seed))
 
     @property
     def alpha(self):
-        return float(self._alphas[self._alpha_at]) if self._alpha_at < len(self._alphas) else float(self.target_alpha)
+        """Learning rate of the coming update: a float, or [N] when the schedules differ per environment."""
+        if self._alphas is not None:
+            return float(self._alphas[self._alpha_at]) if self._alpha_at < len(self._alphas) else float(self.target_alpha)
+        torch = self.torch
+        steps = torch.as_tensor(self._alpha_steps, dtype=torch.float64, device=self.device)
+        at = torch.minimum(torch.full_like(steps, float(self._alpha_at)), steps - 1.0)
+        return self._alpha_start + (self._alpha_stop - self._alpha_start) * at / (steps - 1.0)   # np.linspace, element by element
 
     def _ahead(self, rows, throttle):
         """rows [4, ...] -> (x, y, heading) after the look-ahead; `throttle` broadcasts against rows[0]."""
@@ -187,7 +212,8 @@ class BatchedQLearningEgoAgent:
     def q_values(self, state):
         """([A, N] Q values, features)"""
         features = self.features(state)
-        return (features * self.weights.view(1, self.num_opponents, -1, 1)).sum(dim=(1, 2)), features
+        weights = self.weights.view(1, self.num_opponents, -1, 1) if self.shared else self.weights.permute(1, 2, 0).unsqueeze(0)
+        return (features * weights).sum(dim=(1, 2)), features
 
     def choose_action(self, state, u_explore=None, u_pick=None):
         """epsilon-greedy per environment; ties for the largest Q value are broken uniformly, in action order, like
@@ -220,6 +246,12 @@ class BatchedQLearningEgoAgent:
         if live is None:
             live = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
         weight = live.to(torch.float64)
+        if not self.shared:   # N independent learners: each env applies its own update, as the reference's agent does
+            alpha = self.alpha
+            alpha = alpha.view(-1, 1, 1) if torch.is_tensor(alpha) else alpha
+            self.weights = self.weights + alpha * (difference * weight).view(-1, 1, 1) * chosen
+            self._alpha_at += 1
+            return
         packed = torch.cat([((difference * weight).view(-1, 1, 1) * chosen).sum(dim=0).reshape(-1), weight.sum().view(1)])
         if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
             torch.distributed.all_reduce(packed)   # env-sharded ranks learn ONE table: sum of the updates and of the live counts
@@ -228,5 +260,5 @@ class BatchedQLearningEgoAgent:
 
     def feature_weights(self):
         """{opponent index: {feature: weight}} like the host agent's table."""
-        table = self.weights.cpu().tolist()
+        table = (self.weights if self.shared else self.weights.mean(dim=0)).cpu().tolist()   # independent learners: their mean
         return {i + 1: dict(zip(self.names, table[i])) for i in range(self.num_opponents)}

@@ -200,6 +200,39 @@ def check_tensor_learner(name, dev):
     assert steps > 500
 
 
+def test_independent_learners_are_side_by_side_copies_of_the_reference_agent():
+    """shared=False: every env is its own learner with its own alpha schedule, gamma and epsilon (the grid of experiments.py in
+    one batch).  Three envs fed the inputs of one recorded run — two with the run's hyper-parameters, one with another
+    gamma: the first two end every step with the reference's weights and learning rate, the third does not."""
+    import torch
+    from cavgym_b200.config import make_config
+    from cavgym_b200.examples.agents.ego import BatchedQLearningEgoAgent
+    from cavgym_b200.examples.constants import car_constants
+    from cavgym_b200.examples.environments import pedestrians
+    meta, episodes = load_golden("learn_qego3_rc_seed21")
+    config = make_config(copy.deepcopy(meta["config"]))
+    q, m, n = config.ego_config, meta["n_bodies"], 3
+    learner = BatchedQLearningEgoAgent(q, car_constants, 1.0 / 60, m - 1, pedestrians.env_constants.viewer_width,
+                                       pedestrians.env_constants.viewer_height, n, torch.device("cpu"), shared=False,
+                                       alpha=([q.alpha.start] * n, [q.alpha.stop] * n, [q.alpha.num_steps] * n),
+                                       gamma=[q.gamma, q.gamma, 0.5 * q.gamma], epsilon=[q.epsilon] * n)
+    order = [learner.names.index(f) for f in sorted(learner.names)]
+    for ep in episodes:
+        state = torch.tensor(ep["init_state"]).unsqueeze(-1).expand(-1, -1, n).contiguous()
+        for t in range(ep["actions"].shape[0]):
+            draws = [d for d in ep["draws"][t][0] if not np.isnan(d)]
+            index, rows = learner.choose_action(state, torch.tensor([draws[0]] * n), torch.tensor([draws[1] if len(draws) > 1 else 0.0] * n))
+            assert rows[:, 0].tolist() == rows[:, 1].tolist() == ep["actions"][t][0].tolist()
+            index[2] = index[0]      # keep the third learner on the recorded trajectory: only its update differs
+            previous, state = state, torch.tensor(ep["state"][t]).unsqueeze(-1).expand(-1, -1, n).contiguous()
+            learner.process_feedback(previous, index, state, torch.tensor([ep["reward"][t][0]] * n))
+            want = ep["extra"][t][:-1].reshape(m - 1, -1)
+            for e in (0, 1):
+                assert np.allclose(learner.weights[e][:, order].numpy(), want, rtol=1e-8, atol=1e-9), (t, e)
+            assert np.allclose(learner.alpha.numpy(), ep["extra"][t][-1], rtol=1e-12)
+    assert not np.allclose(learner.weights[2][:, order].numpy(), want, rtol=1e-3)
+
+
 @pytest.mark.parametrize("name", Q_CASES)
 def test_tensor_api_learner_is_the_host_learner_at_one_env_cpu_tensors(name):
     import torch
@@ -229,3 +262,25 @@ def test_batched_simulation_runs_the_stock_q_learning_ego():
     assert stats["env_steps"] == 256 * sim.steps_run     # every env is live on every step (finished ones are reset at once)
     table = sim.learner.feature_weights()
     assert any(abs(w) > 0 for w in table[1].values()) and all(np.isfinite(list(table[1].values())))
+
+
+@pytest.mark.gpu
+def test_experiments_grid_runs_as_one_batch(tmp_path):
+    """cavgym_b200.experiments: grid points of (alpha, gamma, epsilon) as independent learners in one batch, testers on the
+    device; every grid point gets the reference's config.json / episode.log / run.log."""
+    from cavgym_b200 import experiments
+    from cavgym_b200.config import AgentType
+    grid = [(0.1, 0.9, 0.1), (0.5, 0.5, 0.5), (0.9, 0.1, 0.9), (0.5, 0.9, 0.0)]
+    summaries, learner = experiments.run_tester_type(AgentType.RANDOM_CONSTRAINED, grid, runs=3, episodes=3, log_root=str(tmp_path))
+    assert set(summaries) == set(grid) and learner.weights.shape[0] == 12
+    for point, summary in summaries.items():
+        assert summary.episodes == 9 and 9 <= summary.timesteps <= 9 * 1000
+        log_dir = tmp_path / f"tester=random-constrained/alpha={point[0]}/gamma={point[1]}/epsilon={point[2]}"
+        rows = (log_dir / "episode.log").read_text().strip().splitlines()
+        assert len(rows) == 9 and all(len(r.split(",")) == 5 for r in rows)
+        assert len((log_dir / "run.log").read_text().strip().split(",")) == 10
+        assert json.loads((log_dir / "config.json").read_text())["ego_config"]["gamma"] == point[1]
+    weights = learner.weights.cpu().numpy()
+    assert np.isfinite(weights).all() and np.abs(weights).max() > 0
+    assert not np.allclose(weights[0], weights[3])          # different hyper-parameters learn different tables
+
