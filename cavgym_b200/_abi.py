@@ -102,6 +102,8 @@ PROTOTYPES = {
     "cavgym_bodies_step": (C.c_int, [C.POINTER(CavBodyType), C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, c_stream]),
     "cavgym_geometry_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_stream]),
     "cavgym_zones_probe": (C.c_int, [C.POINTER(CavBodyType), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_stream]),
+    "cavgym_host_alloc": (C.c_int, [C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "cavgym_host_free": (C.c_int, [C.c_void_p]),
     "cavgym_last_error": (C.c_char_p, []),
     "cavgym_version": (C.c_char_p, []),
 }

@@ -566,6 +566,19 @@ extern "C" {
 const char* cavgym_last_error(void) { return g_error.c_str(); }
 const char* cavgym_version(void) { return "cavgym_b200 0.1.0 (sm_100a)"; }
 
+int cavgym_host_alloc(size_t bytes, int write_combined, void** out) {
+  if (!out || bytes == 0) return fail(CAV_EINVAL, "out is NULL or bytes is 0");
+  *out = nullptr;
+  CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocMapped | cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+  return CAV_OK;
+}
+
+int cavgym_host_free(void* ptr) {
+  if (!ptr) return CAV_OK;
+  CUDA_TRY(cudaFreeHost(ptr));
+  return CAV_OK;
+}
+
 int cavgym_create(const CavScenario* tables, int64_t n_envs, int dtype, int device, uint64_t seed, CavEngine** out) {
   if (!tables || !out) return fail(CAV_EINVAL, "tables/out is NULL");
   *out = nullptr;

@@ -264,6 +264,32 @@ class BatchedCAVEnv:
         return state_rows, rewards, done_flag, winner_index, liveness, taken
 
 
+class HostBuffer:
+    """A page-locked, device-mapped host array from cavgym_host_alloc, as a numpy array (`.array`).  write_combined=True is for
+    buffers the host only writes and the GPU reads — the joint actions of step_host."""
+
+    def __init__(self, shape, dtype, write_combined=False):
+        self._lib = _native.load()
+        self.array = None
+        count = int(np.prod(shape))
+        self._ptr = C.c_void_p()
+        _native.check(self._lib.cavgym_host_alloc(count * np.dtype(dtype).itemsize, int(bool(write_combined)), C.byref(self._ptr)))
+        ctype = np.ctypeslib.as_ctypes_type(np.dtype(dtype))
+        self.array = np.ctypeslib.as_array(C.cast(self._ptr, C.POINTER(ctype)), shape=(count,)).reshape(shape)
+
+    def close(self):
+        if getattr(self, "_ptr", None) and self._ptr.value:
+            self.array = None
+            self._lib.cavgym_host_free(self._ptr)
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def bodies_step(constants, states, actions, time_resolution, dtype="float64", device=None):
     """DynamicBody.step (reference library/bodies.py:214-275) for a list of independent bodies of one type,
     run by the stand-alone CUDA kinematics kernel.  states [n][4], actions [n][2] -> new states [n][4]."""

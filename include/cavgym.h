@@ -26,6 +26,7 @@
 #ifndef CAVGYM_H
 #define CAVGYM_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -293,6 +294,13 @@ int cavgym_zones_probe(const CavBodyType* type, const void* state, const void* s
                        int64_t n, int dtype, cudaStream_t stream);
 
 const char* cavgym_last_error(void);
+/* Page-locked, device-mapped host memory for the buffers of cavgym_step_host / cavgym_reset_host (what a caller without
+ * PyTorch uses instead of tensor.pin_memory()).  write_combined != 0 allocates write-combined memory: meant for buffers the
+ * host only WRITES and the GPU reads (the joint actions) — GPU reads of it do not snoop the CPU caches; host reads of it are
+ * slow.  Free with cavgym_host_free. */
+int cavgym_host_alloc(size_t bytes, int write_combined, void** out);
+int cavgym_host_free(void* ptr);
+
 const char* cavgym_version(void);
 
 #ifdef __cplusplus

@@ -34,12 +34,24 @@ class BatchedCAVEnv:
         self.handle = C.c_void_p()
         code = _abi.CAV_F64 if self.dtype == np.float64 else _abi.CAV_F32
         _native.check(self.lib.cavgym_create(self.tables.pointer(), self.n, code, int(device), int(seed or 0), C.byref(self.handle)))
-        self.state = np.zeros((self.m, 4, self.n), self.dtype)
-        self.reward = np.zeros((self.m, self.n), self.dtype)
-        self.done = np.zeros(self.n, np.uint8)
-        self.winner = np.full(self.n, -1, np.int32)
-        self.tangent = np.zeros(self.n, np.uint8)
-        self._noop = np.zeros((self.m, 2, self.n), self.dtype)
+        # page-locked, device-mapped arrays (cavgym_host_alloc): cavgym_step_host then runs as ONE launch that reads the
+        # actions from and writes the results to these arrays over PCIe; pageable arrays work too, through staged copies
+        self._pinned = []
+        self.actions = self._host_array((self.m, 2, self.n), self.dtype)
+        self.state = self._host_array((self.m, 4, self.n), self.dtype)
+        self.reward = self._host_array((self.m, self.n), self.dtype)
+        self.done = self._host_array((self.n,), np.uint8)
+        self.winner = self._host_array((self.n,), np.int32)
+        self.tangent = self._host_array((self.n,), np.uint8)
+        self.winner[:] = -1
+
+    def _host_array(self, shape, dtype):
+        ptr, count = C.c_void_p(), int(np.prod(shape))
+        _native.check(self.lib.cavgym_host_alloc(count * np.dtype(dtype).itemsize, 0, C.byref(ptr)))
+        self._pinned.append(ptr)
+        array = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(np.dtype(dtype)))), shape=(count,)).reshape(shape)
+        array[...] = 0
+        return array
 
     @staticmethod
     def _p(array):
@@ -57,9 +69,10 @@ class BatchedCAVEnv:
     def step(self, actions):
         """CAVEnv.step over all envs: one fused launch, copies in and out included (cavgym_step_host).  Envs whose joint
         action is invalid (environment.py:120) are left untouched and counted by cavgym_error_count."""
-        actions = np.ascontiguousarray(actions, self.dtype)
-        assert actions.shape == (self.m, 2, self.n), "actions must be [bodies, 2, envs]"
-        _native.check(self.lib.cavgym_step_host(self.handle, self._p(actions), self._p(self.state), self._p(self.reward), self._p(self.done),
+        assert np.shape(actions) == (self.m, 2, self.n), "actions must be [bodies, 2, envs]"
+        if actions is not self.actions:
+            self.actions[...] = actions          # (write into batch.actions directly to skip this copy)
+        _native.check(self.lib.cavgym_step_host(self.handle, self._p(self.actions), self._p(self.state), self._p(self.reward), self._p(self.done),
                                                 self._p(self.winner), self._p(self.tangent)))
         return self.state, self.reward, self.done.astype(bool), self.winner
 
@@ -72,3 +85,7 @@ class BatchedCAVEnv:
         if self.handle:
             self.lib.cavgym_destroy(self.handle)
             self.handle = C.c_void_p()
+            self.actions = self.state = self.reward = self.done = self.winner = self.tangent = None
+            for ptr in self._pinned:
+                self.lib.cavgym_host_free(ptr)
+            self._pinned = []

@@ -42,6 +42,14 @@ for ctas in (1, 2, 3):
     run(f"zero copy, TMA-staged kernel, {ctas} CTA(s) per SM")
 env.set_host_path(1)
 run("default path, reward + done only", outputs=False)
+from cavgym_b200.engine import HostBuffer
+wc = HostBuffer((steps + 3, m, 2, n), "float64", write_combined=True)
+wc.array[...] = h_actions.numpy()
+pinned_joint = joint
+joint = [wc.array[t] for t in range(steps + 3)]
+env.set_host_path(1)
+run("zero copy, actions in WRITE-COMBINED pinned memory")
+joint = pinned_joint
 env.set_step_path(False)
 run("zero copy, plain kernel (LDG / STG on mapped memory)")
 env.set_step_path(True)
