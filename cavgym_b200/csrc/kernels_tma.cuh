@@ -50,6 +50,10 @@ namespace cav {
 #define CAV_TMA_STAGES 3
 #endif
 constexpr int kTmaStages = CAV_TMA_STAGES;
+#ifndef CAV_REPLAY_STAGES
+#define CAV_REPLAY_STAGES CAV_TMA_STAGES
+#endif
+constexpr int kReplayStages = CAV_REPLAY_STAGES;   // pipeline depth of replay_tma_kernel (over time steps)
 constexpr int kMaxSmemPerBlock = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
 constexpr int kMaxDevices = 64;                // per-device caches of the launchers below
 // The TMA-staged kernels pay off while three CTAs (step) / two 256-thread CTAs (replay) fit an SM, i.e. for one or two
@@ -62,6 +66,9 @@ constexpr int kMaxDevices = 64;                // per-device caches of the launc
 constexpr int kStepWarps = CAV_TMA_STEP_WARPS, kStepTile = 32 * kStepWarps;
 constexpr int kReplayWarps = CAV_TMA_REPLAY_WARPS, kReplayTile = 32 * kReplayWarps;
 
+#ifndef CAV_MBAR_SUSPEND_NS
+#define CAV_MBAR_SUSPEND_NS 0
+#endif
 // ---------------------------------------------------------------- PTX: mbarrier and bulk asynchronous copies
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -80,11 +87,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
+#if CAV_MBAR_SUSPEND_NS > 0
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"   // suspend (no issue slots) up to the hint, woken on completion
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#endif
       "selp.u32 %0, 1, 0, p;\n"
       "}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
+#if CAV_MBAR_SUSPEND_NS > 0
+        , "r"((uint32_t)CAV_MBAR_SUSPEND_NS)
+#endif
       : "memory");
   return ok != 0;
 }
@@ -354,7 +368,7 @@ struct ReplayLayout {
   static constexpr int oTangent = oDoneOut + T;           // u8 [T]       out
   static constexpr int kStageBytes = ((oTangent + T + 127) / 128) * 128;
   static constexpr int kMaxRows = M * 4 + M * 2 + M + 4;
-  static constexpr int kBarOffset = kTmaStages * kStageBytes;
+  static constexpr int kBarOffset = kReplayStages * kStageBytes;
   static constexpr int kTableOffset = kBarOffset + 128;
   static constexpr int kSmemBytes = kTableOffset + 2 * kMaxRows * (int)sizeof(TmaRow);
 };
@@ -373,8 +387,8 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
   constexpr int T = kReplayTile;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
-  uint64_t* done = full + kTmaStages;
-  uint64_t* empty = done + kTmaStages;
+  uint64_t* done = full + kReplayStages;
+  uint64_t* empty = done + kReplayStages;
   TmaRow* in_rows = reinterpret_cast<TmaRow*>(smem + L::kTableOffset);
   TmaRow* out_rows = in_rows + L::kMaxRows;
   __shared__ int n_out_s;
@@ -387,7 +401,7 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kTmaStages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kReplayWarps); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kReplayStages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kReplayWarps); mbar_init(&empty[s], 1); }
     mbar_fence_init();
     int no = 0;
     auto out = [&](void* base, int64_t rows_per_step, int64_t row, int elem, int off) {
@@ -419,10 +433,10 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
                   &full[s]);
       }
     };
-    for (int t = 0; t < kTmaStages && t < n_steps; ++t) issue_loads(t, t);
+    for (int t = 0; t < kReplayStages && t < n_steps; ++t) issue_loads(t, t);
     for (int t = 0; t < n_steps; ++t) {
-      const int s = t % kTmaStages;
-      const uint32_t parity = (uint32_t)(t / kTmaStages) & 1u;
+      const int s = t % kReplayStages;
+      const uint32_t parity = (uint32_t)(t / kReplayStages) & 1u;
       unsigned char* st = smem + s * L::kStageBytes;
       mbar_wait(&done[s], parity);
       for (int r = lane; r < n_out; r += 32) {
@@ -430,13 +444,13 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
         bulk_store(reinterpret_cast<void*>(row.gbase + (unsigned long long)t * row.unit_stride), st + row.smem_off, row.elem * cnt);
       }
       bulk_commit();
-      if (t + kTmaStages < n_steps) issue_loads(s, t + kTmaStages);   // the action rows of stage s were consumed
+      if (t + kReplayStages < n_steps) issue_loads(s, t + kReplayStages);   // the action rows of stage s were consumed
       // every lane waits until all but the newest S - 2 of its store groups have read shared memory; then the stage of
       // step t - (S - 2) may be written again
-      asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kTmaStages >= 2 ? kTmaStages - 2 : 0) : "memory");
+      asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kReplayStages >= 2 ? kReplayStages - 2 : 0) : "memory");
       __syncwarp();
-      const int freed = t - (kTmaStages >= 2 ? kTmaStages - 2 : 0);
-      if (freed >= 0 && lane == 0) mbar_arrive(&empty[freed % kTmaStages]);
+      const int freed = t - (kReplayStages >= 2 ? kReplayStages - 2 : 0);
+      if (freed >= 0 && lane == 0) mbar_arrive(&empty[freed % kReplayStages]);
     }
     bulk_wait_read_all();
     return;
@@ -453,8 +467,8 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
   load_env<R, M, false>(sc, buf, e, env);
   const bool was_live = env.done == 0;
   for (int t = 0; t < n_steps; ++t) {
-    const int s = t % kTmaStages;
-    const uint32_t parity = (uint32_t)(t / kTmaStages) & 1u;
+    const int s = t % kReplayStages;
+    const uint32_t parity = (uint32_t)(t / kReplayStages) & 1u;
     unsigned char* st = smem + s * L::kStageBytes;
     mbar_wait(&full[s], parity);
     StepResult<R, M> res;
