@@ -19,7 +19,7 @@ CAV_N_STATS = 12
 CAV_F64, CAV_F32 = 0, 1
 CAV_BODY_DYNAMIC, CAV_BODY_PELICAN = 0, 1
 CAV_FLAG_PEDESTRIAN, CAV_FLAG_SPAWN = 1, 2
-CAV_AGENT_EXTERNAL, CAV_AGENT_NOOP, CAV_AGENT_RANDOM, CAV_AGENT_RANDOM_CONSTRAINED, CAV_AGENT_PROXIMITY = range(5)
+CAV_AGENT_EXTERNAL, CAV_AGENT_NOOP, CAV_AGENT_RANDOM, CAV_AGENT_RANDOM_CONSTRAINED, CAV_AGENT_PROXIMITY, CAV_AGENT_ELECTION = range(6)
 CAV_COLLISIONS_NONE, CAV_COLLISIONS_EGO, CAV_COLLISIONS_ALL = range(3)
 STAT_NAMES = ("episodes", "interesting", "sum_t", "sum_t2", "sum_score", "sum_score2", "env_steps", "body_steps",
               "tangent", "errors", "sum_t_interesting", "sum_t2_interesting")

@@ -13,7 +13,8 @@ of experiments.py:95-119 build configs with them.
 
 The Q-learning ego (examples/agents/ego.py) and the election tester (examples/agents/pedestrian.py, examples/election.py)
 run host-side on the single-environment view like in the reference; at batch scale the Q-learning ego has a tensor-API
-form (BatchedQLearningEgoAgent, driven by BatchedSimulation).  Not provided: the keyboard ego (interactive) and the
+form (BatchedQLearningEgoAgent, driven by BatchedSimulation) and the election testers are an on-device agent kind
+(CAV_AGENT_ELECTION: the arbitration of examples/election.py runs inside the step kernel).  Not provided: the keyboard ego (interactive) and the
 Q-learning TESTER (the reference's own raises TypeError at its first update, pedestrian.py:128, 247).  Render mode has no
 viewer here (pyglet is not part of the engine): a render config runs headless and says so once.  Every option still
 parses, validates and round-trips; building an unavailable one raises NotImplementedError, as the reference does for
@@ -152,8 +153,7 @@ OPTIONS = {
 ENV_IDS = {Scenario.PELICAN_CROSSING: "PelicanCrossing-v0", Scenario.BUS_STOP: "BusStop-v0", Scenario.CROSSROADS: "Crossroads-v0",
            Scenario.PEDESTRIANS: "Pedestrians-v0"}
 _HOST_ONLY = {AgentType.KEYBOARD: "the keyboard agent is interactive (render mode)",
-              AgentType.Q_LEARNING: "Q-learning agents update their weights on the host (ego: BatchedQLearningEgoAgent on the tensor API)",
-              AgentType.ELECTION: "the election tester is arbitrated on the host (examples/election.py)"}
+              AgentType.Q_LEARNING: "Q-learning agents update their weights on the host (ego: BatchedQLearningEgoAgent on the tensor API)"}
 _UNAVAILABLE = {"ego": {AgentType.KEYBOARD: _HOST_ONLY[AgentType.KEYBOARD]},
                 "tester": {AgentType.Q_LEARNING: "the reference's Q-learning tester fails at its first process_feedback "
                                                  "(pedestrian.py:128, 247: LinSpace * float), there is no behaviour to reproduce"}}
@@ -230,6 +230,8 @@ class Config:
                 specs.append(AgentSpec("random-constrained", epsilon=tester.epsilon))
             elif isinstance(body, body_lib.Pedestrian) and tester.agent is AgentType.PROXIMITY:
                 specs.append(AgentSpec("proximity", threshold=tester.threshold))
+            elif isinstance(body, body_lib.Pedestrian) and tester.agent is AgentType.ELECTION:
+                specs.append(AgentSpec("election", threshold=tester.threshold))   # arbitrated inside the step kernel
             else:
                 raise NotImplementedError   # config.py:396: e.g. random-constrained on a Car
         return specs

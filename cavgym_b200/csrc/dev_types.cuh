@@ -80,7 +80,7 @@ struct DevScenario {
   R cl[4];       // centre line start x,y end x,y
   // Headings bodies are created with (spawn orientations, init orientations): cos/sin evaluated ON THE HOST
   // with the C library the reference's math.cos/math.sin use.
-  int32_t hc_n, hc_pad;
+  int32_t hc_n, has_election;   // has_election: some body is driven by CAV_AGENT_ELECTION (Election.result runs every step)
   R hc_theta[CAV_HEADING_CACHE], hc_cos[CAV_HEADING_CACHE], hc_sin[CAV_HEADING_CACHE];
   Aabb<R> road_bb[CAV_MAX_ROADS];
   Box<R> road_box[CAV_MAX_ROADS];
@@ -108,6 +108,7 @@ struct EnvBuffers {
   int32_t* t_ep;        // [N]
   int32_t* episode;     // [N]
   int32_t* winner;      // [N]
+  int32_t* active;      // [N] Election.active_player (election.py:12), 0 = None; survives resets like the reference's object
   uint8_t* done;        // [N] 0 live, 1 done, 2 cut off at max_timesteps
   uint8_t* err;         // [N]
   unsigned long long* stats;  // [CAV_N_STATS]

@@ -179,6 +179,8 @@ static void convert(const CavScenario& in, double tau, DevScenario<R>& out) {
     if (b > 0) homogeneous = homogeneous && (in.bodies[b].flags & CAV_FLAG_PEDESTRIAN);
   }
   out.homogeneous = homogeneous ? 1 : 0;
+  out.has_election = 0;
+  for (int b = 0; b < in.n_bodies && b < CAV_SMALL_M; ++b) if (in.bodies[b].agent == CAV_AGENT_ELECTION) out.has_election = 1;
   // heading cache: orientations bodies start with, cos/sin from the host C library (what math.cos/math.sin call)
   auto remember = [&out](double theta) {
     const R th = (R)theta;
@@ -455,6 +457,7 @@ static int setup_buffers(CavEngine* eng, EnvBuffers<R>& buf) {
   if ((rc = dev_alloc(eng, &buf.t_ep, (size_t)n))) return rc;
   if ((rc = dev_alloc(eng, &buf.episode, (size_t)n))) return rc;
   if ((rc = dev_alloc(eng, &buf.winner, (size_t)n))) return rc;
+  if ((rc = dev_alloc(eng, &buf.active, (size_t)n))) return rc;
   if ((rc = dev_alloc(eng, &buf.done, (size_t)n))) return rc;
   if ((rc = dev_alloc(eng, &buf.err, (size_t)n))) return rc;
   if ((rc = dev_alloc(eng, &buf.stats, (size_t)CAV_N_STATS))) return rc;
@@ -606,8 +609,10 @@ int cavgym_create(const CavScenario* tables, int64_t n_envs, int dtype, int devi
       return fail(CAV_EINVAL, "body type_id out of range");
     if ((body.flags & CAV_FLAG_SPAWN) && (body.spawn_id < 0 || body.spawn_id >= tables->n_spawns || !tables->spawns))
       return fail(CAV_EINVAL, "spawn_id out of range");
-    if (body.agent < CAV_AGENT_EXTERNAL || body.agent > CAV_AGENT_PROXIMITY) return fail(CAV_EINVAL, "unknown agent kind");
-    if ((body.agent == CAV_AGENT_RANDOM_CONSTRAINED || body.agent == CAV_AGENT_PROXIMITY) &&
+    if (body.agent < CAV_AGENT_EXTERNAL || body.agent > CAV_AGENT_ELECTION) return fail(CAV_EINVAL, "unknown agent kind");
+    if (body.agent == CAV_AGENT_ELECTION && tables->n_bodies > CAV_SMALL_M)
+      return fail(CAV_EINVAL, "election agents are arbitrated in the thread-per-env kernels: at most CAV_SMALL_M bodies");
+    if ((body.agent == CAV_AGENT_RANDOM_CONSTRAINED || body.agent == CAV_AGENT_PROXIMITY || body.agent == CAV_AGENT_ELECTION) &&
         !(body.kind == CAV_BODY_DYNAMIC && (body.flags & CAV_FLAG_PEDESTRIAN)))
       return fail(CAV_EINVAL, "crossing agents need a Pedestrian body (config.py:358-396)");
   }
@@ -1011,6 +1016,7 @@ int cavgym_set_step_path(CavEngine* eng, int use_tma) {
 int cavgym_set_dense_path(CavEngine* eng, int force) {
   if (!eng) return fail(CAV_EINVAL, "engine is NULL");
   if (eng->m > CAV_SMALL_M && !force) return fail(CAV_EINVAL, "more than CAV_SMALL_M bodies: only the warp-per-environment kernels apply");
+  if (force && eng->sc64.has_election) return fail(CAV_EINVAL, "election agents run in the thread-per-environment kernels only");
   eng->dense = force != 0 || eng->m > CAV_SMALL_M;
   return CAV_OK;
 }

@@ -53,6 +53,7 @@ __device__ __forceinline__ void load_env(const DevScenario<R>& sc, const EnvBuff
 #pragma unroll
   for (int b = 1; b < M; ++b) env.live[b] = buf.liveness[(int64_t)b * n + e];
   env.episode = AGENTS ? buf.episode[e] : 0;
+  env.active = AGENTS && M >= 3 && sc.has_election ? buf.active[e] : 0;
 #pragma unroll
   for (int b = 0; b < M; ++b) {
 #pragma unroll
@@ -100,6 +101,7 @@ __device__ __forceinline__ void store_env(const DevScenario<R>& sc, const EnvBuf
   buf.t_ep[e] = env.t_ep;
   if (all || env.done) { buf.done[e] = env.done; buf.winner[e] = env.winner; }
   if (all) buf.episode[e] = env.episode;
+  if (AGENTS && M >= 3 && sc.has_election) buf.active[e] = env.active;
 }
 
 template <typename R, int M>
@@ -268,6 +270,7 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__
   if (!mine) return;
   EnvRegs<R, M> env;
   env.episode = first_time ? -1 : buf.episode[e];
+  env.active = first_time || !sc.has_election ? 0 : buf.active[e];   // the Election object outlives episodes (election.py:12)
   reset_env<R, M>(sc, buf, init, e, env);
   store_env<R, M, true>(sc, buf, e, env, true);
   if (first_time) buf.err[e] = 0;

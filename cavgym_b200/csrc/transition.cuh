@@ -31,6 +31,7 @@ struct EnvRegs {
   R cs[M][2];        // cos, sin of the heading (EnvBuffers::cs)
   int32_t live[M];   // episode_liveness (environment.py:144-146); [0] unused
   int32_t t_ep, episode, winner;
+  int32_t active;    // Election.active_player (0 = None); only kernels with on-device agents carry it
   uint32_t live_dirty;  // bit b: live[b] changed since it was loaded
   uint32_t cs_dirty;  // bit b: cs[b] changed since it was loaded
   uint32_t ag_dirty;  // bit b: ag[b] changed since it was loaded
@@ -49,7 +50,8 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 
 template <typename R, int M>
 __device__ __forceinline__ bool uses_agent_state(const DevScenario<R>& sc, int b) {
-  return sc.bodies[b].agent == CAV_AGENT_RANDOM_CONSTRAINED || sc.bodies[b].agent == CAV_AGENT_PROXIMITY;
+  return sc.bodies[b].agent == CAV_AGENT_RANDOM_CONSTRAINED || sc.bodies[b].agent == CAV_AGENT_PROXIMITY ||
+         sc.bodies[b].agent == CAV_AGENT_ELECTION;
 }
 
 // Body b as a box / as a pose; b must be a compile-time constant at the call site (unrolled loops).

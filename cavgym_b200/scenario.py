@@ -14,7 +14,8 @@ from typing import List, Optional, Sequence
 from . import _abi
 
 AGENT_CODES = {"external": _abi.CAV_AGENT_EXTERNAL, "noop": _abi.CAV_AGENT_NOOP, "random": _abi.CAV_AGENT_RANDOM,
-               "random-constrained": _abi.CAV_AGENT_RANDOM_CONSTRAINED, "proximity": _abi.CAV_AGENT_PROXIMITY}
+               "random-constrained": _abi.CAV_AGENT_RANDOM_CONSTRAINED, "proximity": _abi.CAV_AGENT_PROXIMITY,
+               "election": _abi.CAV_AGENT_ELECTION}
 COLLISION_CODES = {"none": _abi.CAV_COLLISIONS_NONE, "ego": _abi.CAV_COLLISIONS_EGO, "all": _abi.CAV_COLLISIONS_ALL}
 
 
@@ -118,7 +119,7 @@ def compile_scenario(bodies: Sequence, constants, env_config, agents: Optional[S
             row.kind = _abi.CAV_BODY_PELICAN
             row.init_state[:] = [float(body.init_state.value), 0.0, 0.0, 0.0]
             row.static_box = _quad(body.bounding_box())
-            if agent.kind in ("random-constrained", "proximity"):
+            if agent.kind in ("random-constrained", "proximity", "election"):
                 raise NotImplementedError("crossing agents need a Pedestrian body")  # config.py:358-396
         elif is_a(body, "DynamicBody"):
             row.kind = _abi.CAV_BODY_DYNAMIC
@@ -130,7 +131,7 @@ def compile_scenario(bodies: Sequence, constants, env_config, agents: Optional[S
             row.type_id = type_rows.index(key)
             if is_a(body, "Pedestrian"):
                 row.flags |= _abi.CAV_FLAG_PEDESTRIAN
-            elif agent.kind in ("random-constrained", "proximity"):
+            elif agent.kind in ("random-constrained", "proximity", "election"):
                 raise NotImplementedError("crossing agents need a Pedestrian body")  # config.py:358-396
             row.init_state[:] = [float(v) for v in body.init_state]
             if is_a(body, "SpawnPedestrian"):

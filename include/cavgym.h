@@ -67,7 +67,9 @@ enum { CAV_AGENT_EXTERNAL = 0,            /* action comes from the `actions` buf
        CAV_AGENT_NOOP = 1,                /* NoopAgent            (template.py:24-37) */
        CAV_AGENT_RANDOM = 2,              /* RandomAgent          (template.py:40-62) */
        CAV_AGENT_RANDOM_CONSTRAINED = 3,  /* RandomConstrainedAgent (pedestrian.py:72-75) */
-       CAV_AGENT_PROXIMITY = 4 };         /* ProximityAgent       (pedestrian.py:78-91) */
+       CAV_AGENT_PROXIMITY = 4,           /* ProximityAgent       (pedestrian.py:78-91) */
+       CAV_AGENT_ELECTION = 5 };          /* ElectionAgent arbitrated by Election (pedestrian.py:94-116, election.py:4-57);
+                                             scenarios of at most CAV_SMALL_M bodies */
 
 enum { CAV_COLLISIONS_NONE = 0, CAV_COLLISIONS_EGO = 1, CAV_COLLISIONS_ALL = 2 }; /* config.py:237-240 */
 

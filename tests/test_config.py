@@ -86,8 +86,8 @@ def test_agent_specs_follow_the_reference_compatibility_rules():
     assert specs[0].kind == "external"       # the tensor-API learner supplies the ego's action; testers stay on the device
     with pytest.raises(NotImplementedError, match="no on-device form"):
         cfg.make_config(stock(ego_config={"option": "keyboard"}, mode_config=render)).agent_specs(peds)
-    with pytest.raises(NotImplementedError, match="no on-device form"):   # arbitrated on the host (examples/election.py)
-        cfg.make_config(stock(tester_config={"option": "election", "threshold": 5.0})).agent_specs(peds)
+    specs = cfg.make_config(stock(tester_config={"option": "election", "threshold": 5.0})).agent_specs(peds)
+    assert [s.kind for s in specs] == ["noop", "election", "election", "election"] and specs[1].threshold == 5.0
 
 
 def test_package_level_names_resolve():

@@ -284,3 +284,52 @@ def test_experiments_grid_runs_as_one_batch(tmp_path):
     assert np.isfinite(weights).all() and np.abs(weights).max() > 0
     assert not np.allclose(weights[0], weights[3])          # different hyper-parameters learn different tables
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", ELECTION_CASES)
+def test_device_election_agents_follow_the_reference(name, dtype):
+    """CAV_AGENT_ELECTION: the ElectionAgents and the arbitration of examples/election.py inside the step kernel (no random
+    draws are involved: proximity triggers, closest voter wins).  Consecutive reference episodes in ONE engine, because the
+    reference's Election object — and its active player — outlives episodes: executed joint actions, crossing-agent state,
+    body state and events must be the reference's."""
+    from cavgym_b200 import BatchedCAVEnv
+    meta, episodes = load_golden(name)
+    env = BatchedCAVEnv(None, None, None, num_envs=1, dtype=dtype, compiled=compile_from_meta(meta, mode="device"), device="cuda:0")
+    env.set_action_logging(True)
+    tol = 1e-9 if dtype == "float64" else 1e-4
+    compared = 0
+    for ep in episodes:
+        env.reset(init_state=soa(ep["init_state"][None]))
+        env.set_global_timestep(int(ep["t_global_start"]))
+        for t in range(ep["actions"].shape[0]):
+            state, reward, done, winner, tangent = env.step(None)
+            if bool(tangent[0]) and (bool(done[0]) != bool(ep["done"][t]) or int(winner[0]) != int(ep["winner"][t])):
+                break      # a flagged near-tangent divergence (fp32): different episodes from here on
+            assert bool(done[0]) == bool(ep["done"][t]) and int(winner[0]) == int(ep["winner"][t]), (name, t)
+            got_actions = env.actions_taken.double().cpu().numpy()[..., 0]
+            assert np.max(np.abs(got_actions - ep["actions"][t])) < (1e-9 if dtype == "float64" else 2e-3), (name, t)
+            from helpers import state_err_trajectory
+            assert state_err(state.double().cpu().numpy()[..., 0], ep["state"][t]) < (tol if dtype == "float64" else 5e-4), (name, t)
+            if dtype == "float64":
+                crossing = ~np.isnan(ep["agent_state"][t]).all(axis=1)
+                got = env.agent_state.cpu().numpy()[..., 0]
+                assert np.array_equal(np.isnan(got), np.isnan(ep["agent_state"][t])), (name, t)
+                assert np.allclose(got[crossing], ep["agent_state"][t][crossing], rtol=1e-9, atol=1e-9, equal_nan=True), (name, t)
+            compared += 1
+    assert compared > 500
+    env.close()
+
+
+@pytest.mark.gpu
+def test_batched_simulation_with_election_testers():
+    """tester_config election at batch scale: three election pedestrians per env on the device, rollout + scoring in-kernel."""
+    from cavgym_b200.config import make_config
+    from cavgym_b200.simulation import BatchedSimulation
+    meta, _ = load_golden("learn_election3_seed22")
+    config = make_config(dict(copy.deepcopy(meta["config"]), episodes=2000))
+    sim = BatchedSimulation(config, 2048, chunk=250)
+    summary = sim.run()
+    stats = sim.env.stats()
+    assert stats["episodes"] >= 2000 and stats["errors"] == 0 and summary.interesting == stats["interesting"] > 0
