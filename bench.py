@@ -469,18 +469,26 @@ def dense_config(torch, device, dtype, n=100000, steps=100, chunk=50, skip_cpu=F
     bodies = dense_traffic.make_bodies(np_random=np.random.RandomState(0), road_map=road_map)
     cfg = SimpleNamespace(terminate_collisions="all", terminate_ego_zones=True, terminate_ego_offroad=False, max_timesteps=1000,
                           reward_win=6000.0, reward_draw=2000.0, cost_step=4.0)
-    specs = [AgentSpec("random-constrained", epsilon=2e-4) if isinstance(b, Pedestrian) else AgentSpec("noop") for b in bodies]
     m = len(bodies)
-    env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=compile_scenario(bodies, constants, cfg, specs), device=device, seed=1)
-    env.reset()
-    for _ in range(2):
-        env.rollout(chunk, auto_reset=True)
-    torch.cuda.synchronize(device)
-    before = env.stats()
-    ms = timed(torch, lambda: env.rollout(chunk, auto_reset=True), steps // chunk) * (steps // chunk)
-    after = env.stats()
+
+    def measure(epsilon):
+        specs = [AgentSpec("random-constrained", epsilon=epsilon) if isinstance(b, Pedestrian) else AgentSpec("noop") for b in bodies]
+        env = BatchedCAVEnv(None, None, None, num_envs=n, dtype=dtype, compiled=compile_scenario(bodies, constants, cfg, specs), device=device, seed=1)
+        env.reset()
+        for _ in range(2):
+            env.rollout(chunk, auto_reset=True)
+        torch.cuda.synchronize(device)
+        before = env.stats()
+        ms = timed(torch, lambda: env.rollout(chunk, auto_reset=True), steps // chunk) * (steps // chunk)
+        after = env.stats()
+        env.close()
+        return specs, ms, before, after
+
+    # the pedestrians' crossing rate decides how many of the 256 are mid-crossing (turning, off the pavement) at any time:
+    # eps = 2e-4 keeps ~5 % of them crossing, the reference's config.json value 0.01 nearly all of them
+    _, ms_ref, before_ref, after_ref = measure(EPSILON)
+    specs, ms, before, after = measure(2e-4)
     live = after["env_steps"] - before["env_steps"]
-    env.close()
     rate = live / (ms * 1e-3)
     real = 8 if dtype == "float64" else 4
     cpu = None
@@ -501,6 +509,8 @@ def dense_config(torch, device, dtype, n=100000, steps=100, chunk=50, skip_cpu=F
             "env_steps_per_sec": rate, "body_steps_per_sec": rate * m, "pair_tests_per_sec": rate * (m * (m - 1) // 2),
             "ms_per_batch_step": ms / steps, "episodes": after["episodes"] - before["episodes"], "tangent": after["tangent"] - before["tangent"],
             "algorithmic_gbs": rate * m * 11 * real / 1e9, "bound": "instruction fetch / latency (DESIGN.md 4.4, 4.5), not HBM",
+            "at_reference_epsilon": {"epsilon": EPSILON, "env_steps_per_sec": (after_ref["env_steps"] - before_ref["env_steps"]) / (ms_ref * 1e-3),
+                                     "episodes": after_ref["episodes"] - before_ref["episodes"]},
             "cpu_baseline": cpu}
 
 
