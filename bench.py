@@ -324,6 +324,23 @@ def run_ours(args):
                       "steps": e2e_steps, "api": "cavgym_step_host, pinned host buffers, zero copy: one TMA-staged launch per step reads the actions "
                              "from and writes state/reward/done/winner/tangent to host memory over PCIe"}
 
+        if dtype == "float64":   # side number: the same call with the float32 wire format (half the PCIe bytes; not the headline)
+            w_actions = h_actions.float().pin_memory()
+            w_state, w_reward = h_state.float().pin_memory(), h_reward.float().pin_memory()
+            w_joint = [w_actions[t_] for t_ in range(3 + e2e_steps)]
+            env.reset(init_state=init)
+            for t_ in range(3):
+                env.step_host(w_joint[t_], w_state, w_reward, h_done, h_winner, h_tangent)
+            torch.cuda.synchronize(device)
+            s0, t0 = env.stats(), time.perf_counter()
+            for t_ in range(e2e_steps):
+                env.step_host(w_joint[3 + t_], w_state, w_reward, h_done, h_winner, h_tangent)
+            torch.cuda.synchronize(device)
+            wire_s = time.perf_counter() - t0
+            out["e2e"]["float32_wire"] = {"value": (env.stats()["env_steps"] - s0["env_steps"]) / wire_s, "unit": "env-steps/s (this rank)",
+                                          "h2d_bytes_per_step": m * 2 * n * 4, "d2h_bytes_per_step": m * 4 * n * 4 + m * n * 4 + n * 6,
+                                          "api": "cavgym_step_host_f32: fp64 engine, float32 actions / state / rewards on the wire"}
+
     # ---- episode statistics: the single NCCL reduce over NVLink ---------------------
     out["episode_stats"] = sharding.reduce_stats(env.stats(), device)
     env.close()

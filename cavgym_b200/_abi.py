@@ -76,6 +76,7 @@ PROTOTYPES = {
     "cavgym_rollout": (C.c_int, [c_engine_p, C.c_int, C.c_int, c_stream]),
     "cavgym_replay": (C.c_int, [c_engine_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_stream]),
     "cavgym_step_host": (C.c_int, [c_engine_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cavgym_step_host_f32": (C.c_int, [c_engine_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cavgym_reset_host": (C.c_int, [c_engine_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cavgym_info": (C.c_int, [c_engine_p, C.c_void_p, C.c_void_p, c_stream]),
     "cavgym_stats": (C.c_int, [c_engine_p, C.POINTER(C.c_int64)]),

@@ -133,4 +133,14 @@ struct StepIO {
   int32_t ctas_per_sm;   // host side only: cap on resident CTAs per SM of the persistent step kernel (0 = as many as fit)
 };
 
+// cavgym_step_host_f32: joint actions and results cross the host link as float32 while the engine steps in its own type.
+struct WireIO32 {
+  const float* actions;  // [M][2][N]
+  float* state_out;      // [M][4][N], nullable
+  float* reward_out;     // [M][N], nullable
+  uint8_t* done_out;
+  int32_t* winner_out;
+  uint8_t* tangent_out;
+};
+
 }  // namespace cav

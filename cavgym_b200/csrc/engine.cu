@@ -860,6 +860,38 @@ int cavgym_step_host(CavEngine* eng, const void* actions, void* state_out, void*
   return CAV_OK;
 }
 
+int cavgym_step_host_f32(CavEngine* eng, const float* actions, float* state_out, float* reward_out, uint8_t* done_out,
+                         int32_t* winner_out, uint8_t* tangent_flag_out) {
+  int rc = check_engine(eng);
+  if (rc) return rc;
+  if (eng->dtype != CAV_F64) return fail(CAV_ESTATE, "the float32 wire format is for fp64 engines; a float32 engine uses cavgym_step_host");
+  if (eng->dense) return fail(CAV_ESTATE, "the float32 wire format is implemented by the thread-per-environment kernels (at most CAV_SMALL_M bodies)");
+  if (!actions && eng->has_external) return fail(CAV_EINVAL, "actions is NULL but a body has CAV_AGENT_EXTERNAL");
+  if ((rc = host_setup(eng))) return rc;
+  if (eng->caller_work_pending) CUDA_TRY(cudaDeviceSynchronize());
+  const void* host[6] = {actions, state_out, reward_out, done_out, winner_out, tangent_flag_out};
+  void* dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < 6; ++i) {
+    if (!host[i]) continue;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host[i]) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+      cudaGetLastError();
+      return fail(CAV_ESTATE, "cavgym_step_host_f32 needs page-locked, device-mapped buffers (cavgym_host_alloc / pin_memory)");
+    }
+    dev[i] = attr.devicePointer;
+  }
+  const WireIO32 wire{(const float*)dev[0], (float*)dev[1], (float*)dev[2], (uint8_t*)dev[3], (int32_t*)dev[4], (uint8_t*)dev[5]};
+  cudaStream_t s = eng->pipe[0];
+  if (!small_launchers<double>(eng->m)->step_wire32(eng->sc64, eng->buf64, wire, eng->t_global, eng->has_device_agents, s))
+    return fail(CAV_ESTATE, "float32 wire kernels are not compiled for this engine type");
+  rc = launch_check(eng, "step kernel (float32 wire)");
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(s));
+  eng->caller_work_pending = false;
+  eng->t_global += 1;
+  return CAV_OK;
+}
+
 // CAVEnv.reset with HOST buffers (the host-buffer twin of cavgym_reset, for callers that hold no device memory):
 // mask u8[N] and init_state real[M][4][N] are copied in (each nullable), the post-reset state is copied out (nullable).
 int cavgym_reset_host(CavEngine* eng, const uint8_t* mask, const void* init_state, void* state_out) {

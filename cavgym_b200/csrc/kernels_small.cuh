@@ -130,7 +130,7 @@ __device__ __forceinline__ void write_outputs(const EnvBuffers<R>& buf, const St
 template <typename R, int M, bool AGENTS, bool GENERIC, typename Phase = NoPhase>
 __device__ __forceinline__ bool advance(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepIO<R>& io, int64_t e,
                                         int64_t t_global, EnvRegs<R, M>& env, const R (&ext)[M][2], Phase phase = Phase(),
-                                        const bool ghost = false) {
+                                        const bool ghost = false, R* reward_sink = nullptr) {
   StepResult<R, M> res;
   bool ended = false;
   if (env.done) {  // frozen until reset
@@ -149,6 +149,10 @@ __device__ __forceinline__ bool advance(const DevScenario<R>& sc, const EnvBuffe
     ended = env.done != 0;
   }
   if (!ghost) write_outputs<R, M>(buf, io, e, env, res.reward, res.terminate, res.winner, res.tangent);
+  if (reward_sink) {
+#pragma unroll
+    for (int b = 0; b < M; ++b) reward_sink[b] = res.reward[b];
+  }
   return ended;
 }
 
@@ -174,6 +178,37 @@ __global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_STEP) step_kernel(con
     const bool was_live = env.done == 0;
     advance<R, M, AGENTS, GENERIC>(sc, buf, io, e, t_global, env, ext);
     if (was_live) store_env<R, M, AGENTS>(sc, buf, e, env, false);
+  }
+}
+
+// cavgym_step_host_f32: the step of an engine of type R with float32 buffers on the host side of the link — actions are
+// widened on load, state and rewards narrowed on store; the engine's own state stays in R.
+template <typename R, int M, bool AGENTS, bool GENERIC>
+__global__ void __launch_bounds__(kThreads, CAV_MIN_BLOCKS_STEP) step_wire32_kernel(const __grid_constant__ DevScenario<R> sc,
+                                                               const __grid_constant__ EnvBuffers<R> buf,
+                                                               const __grid_constant__ WireIO32 wire, int64_t t_global) {
+  const int64_t e = buf.lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (e >= buf.hi) return;
+  const int64_t n = buf.n;
+  EnvRegs<R, M> env;
+  R ext[M][2], reward[M];
+  load_env<R, M, AGENTS>(sc, buf, e, env);
+#pragma unroll
+  for (int b = 0; b < M; ++b) {
+    ext[b][0] = wire.actions ? R(wire.actions[((int64_t)b * 2 + 0) * n + e]) : R(0);
+    ext[b][1] = wire.actions ? R(wire.actions[((int64_t)b * 2 + 1) * n + e]) : R(0);
+  }
+  const bool was_live = env.done == 0;
+  const StepIO<R> io = {nullptr, nullptr, nullptr, wire.done_out, wire.winner_out, wire.tangent_out, 0};
+  advance<R, M, AGENTS, GENERIC>(sc, buf, io, e, t_global, env, ext, NoPhase(), false, reward);
+  if (was_live) store_env<R, M, AGENTS>(sc, buf, e, env, false);
+#pragma unroll
+  for (int b = 0; b < M; ++b) {
+    if (wire.state_out) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) wire.state_out[((int64_t)b * 4 + c) * n + e] = (float)env.s[b][c];
+    }
+    if (wire.reward_out) wire.reward_out[(int64_t)b * n + e] = (float)reward[b];
   }
 }
 
@@ -288,6 +323,8 @@ struct SmallLaunchers {
   bool (*step_tma)(const DevScenario<R>&, const EnvBuffers<R>&, const StepIO<R>&, int64_t t_global, cudaStream_t, int64_t* envs_done);
   bool (*replay_tma)(const DevScenario<R>&, const EnvBuffers<R>&, const StepIO<R>&, int64_t t_global, int n_steps, cudaStream_t,
                      int64_t* envs_done);
+  // step with float32 host-side buffers (cavgym_step_host_f32); false = not compiled for this engine type
+  bool (*step_wire32)(const DevScenario<R>&, const EnvBuffers<R>&, const WireIO32&, int64_t t_global, bool agents, cudaStream_t);
 };
 
 template <typename R> inline unsigned grid_for(const EnvBuffers<R>& buf, int threads = kThreads) {
@@ -305,6 +342,23 @@ void launch_step(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const StepI
   } else {
     if (agents) step_kernel<R, M, true, true><<<grid, kThreads, 0, stream>>>(sc, buf, io, t_global);
     else step_kernel<R, M, false, true><<<grid, kThreads, 0, stream>>>(sc, buf, io, t_global);
+  }
+}
+template <typename R, int M>
+bool launch_step_wire32(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const WireIO32& wire, int64_t t_global, bool agents,
+                        cudaStream_t stream) {
+  if constexpr (!std::is_same<R, double>::value) {
+    return false;   // a float32 engine already has float32 buffers: cavgym_step_host
+  } else {
+    const unsigned grid = grid_for(buf);
+    if (sc.homogeneous) {
+      if (agents) step_wire32_kernel<R, M, true, false><<<grid, kThreads, 0, stream>>>(sc, buf, wire, t_global);
+      else step_wire32_kernel<R, M, false, false><<<grid, kThreads, 0, stream>>>(sc, buf, wire, t_global);
+    } else {
+      if (agents) step_wire32_kernel<R, M, true, true><<<grid, kThreads, 0, stream>>>(sc, buf, wire, t_global);
+      else step_wire32_kernel<R, M, false, true><<<grid, kThreads, 0, stream>>>(sc, buf, wire, t_global);
+    }
+    return true;
   }
 }
 template <typename R, int M>

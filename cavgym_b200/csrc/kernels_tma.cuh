@@ -624,7 +624,7 @@ bool launch_replay_tma(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const
 template <typename R, int M>
 constexpr SmallLaunchers<R> make_launchers() {
   return {&launch_step<R, M>, &launch_replay<R, M>, &launch_rollout<R, M>, &launch_reset<R, M>, &launch_step_tma<R, M>,
-          &launch_replay_tma<R, M>};
+          &launch_replay_tma<R, M>, &launch_step_wire32<R, M>};
 }
 
 }  // namespace cav

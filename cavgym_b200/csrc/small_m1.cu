@@ -6,8 +6,8 @@ namespace cav {
 extern const SmallLaunchers<double> kSmallF64M1;
 extern const SmallLaunchers<float> kSmallF32M1;
 #ifdef CAV_STUB
-const SmallLaunchers<double> kSmallF64M1 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-const SmallLaunchers<float> kSmallF32M1 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+const SmallLaunchers<double> kSmallF64M1 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+const SmallLaunchers<float> kSmallF32M1 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 #else
 const SmallLaunchers<double> kSmallF64M1 = make_launchers<double, 1>();
 const SmallLaunchers<float> kSmallF32M1 = make_launchers<float, 1>();

@@ -6,8 +6,8 @@ namespace cav {
 extern const SmallLaunchers<double> kSmallF64M3;
 extern const SmallLaunchers<float> kSmallF32M3;
 #ifdef CAV_STUB
-const SmallLaunchers<double> kSmallF64M3 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-const SmallLaunchers<float> kSmallF32M3 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+const SmallLaunchers<double> kSmallF64M3 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+const SmallLaunchers<float> kSmallF32M3 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 #else
 const SmallLaunchers<double> kSmallF64M3 = make_launchers<double, 3>();
 const SmallLaunchers<float> kSmallF32M3 = make_launchers<float, 3>();

@@ -6,8 +6,8 @@ namespace cav {
 extern const SmallLaunchers<double> kSmallF64M4;
 extern const SmallLaunchers<float> kSmallF32M4;
 #ifdef CAV_STUB
-const SmallLaunchers<double> kSmallF64M4 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-const SmallLaunchers<float> kSmallF32M4 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+const SmallLaunchers<double> kSmallF64M4 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+const SmallLaunchers<float> kSmallF32M4 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 #else
 const SmallLaunchers<double> kSmallF64M4 = make_launchers<double, 4>();
 const SmallLaunchers<float> kSmallF32M4 = make_launchers<float, 4>();

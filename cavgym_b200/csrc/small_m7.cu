@@ -6,8 +6,8 @@ namespace cav {
 extern const SmallLaunchers<double> kSmallF64M7;
 extern const SmallLaunchers<float> kSmallF32M7;
 #ifdef CAV_STUB
-const SmallLaunchers<double> kSmallF64M7 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-const SmallLaunchers<float> kSmallF32M7 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+const SmallLaunchers<double> kSmallF64M7 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+const SmallLaunchers<float> kSmallF32M7 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 #else
 const SmallLaunchers<double> kSmallF64M7 = make_launchers<double, 7>();
 const SmallLaunchers<float> kSmallF32M7 = make_launchers<float, 7>();

@@ -6,8 +6,8 @@ namespace cav {
 extern const SmallLaunchers<double> kSmallF64M8;
 extern const SmallLaunchers<float> kSmallF32M8;
 #ifdef CAV_STUB
-const SmallLaunchers<double> kSmallF64M8 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-const SmallLaunchers<float> kSmallF32M8 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+const SmallLaunchers<double> kSmallF64M8 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+const SmallLaunchers<float> kSmallF32M8 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 #else
 const SmallLaunchers<double> kSmallF64M8 = make_launchers<double, 8>();
 const SmallLaunchers<float> kSmallF32M8 = make_launchers<float, 8>();

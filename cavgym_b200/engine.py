@@ -32,6 +32,10 @@ def _ptr(tensor):
     return None if tensor is None else C.c_void_p(tensor.data_ptr())
 
 
+def _is_float32(array):
+    return array is not None and (array.dtype == torch.float32 if isinstance(array, torch.Tensor) else getattr(array, "dtype", None) == np.float32)
+
+
 def _require_cuda(device):
     if not torch.cuda.is_available():
         raise RuntimeError("cavgym_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
@@ -169,12 +173,18 @@ class BatchedCAVEnv:
 
     def step_host(self, actions, state_out=None, reward_out=None, done_out=None, winner_out=None, tangent_out=None):
         """cavgym_step_host: host buffers in and out (numpy arrays or CPU tensors in the engine's layout).  Pinned buffers
-        (tensor.pin_memory()) are read and written by the step kernel itself over PCIe; pageable ones are staged."""
+        (tensor.pin_memory()) are read and written by the step kernel itself over PCIe; pageable ones are staged.
+        A float64 engine also takes float32 actions / state_out / reward_out (all three the same type): the float32 WIRE
+        format of cavgym_step_host_f32 — half the bytes over the link, the engine still steps in double."""
         n, m = self.num_envs, self.num_bodies
         check = self._host_buffer
-        rc = self._lib.cavgym_step_host(self._handle, check(actions, (m, 2, n), self.dtype, "actions"), check(state_out, (m, 4, n), self.dtype, "state_out"),
-                                        check(reward_out, (m, n), self.dtype, "reward_out"), check(done_out, (n,), torch.uint8, "done_out"),
-                                        check(winner_out, (n,), torch.int32, "winner_out"), check(tangent_out, (n,), torch.uint8, "tangent_out"))
+        real = self.dtype
+        if self.dtype == torch.float64 and _is_float32(actions if actions is not None else (state_out if state_out is not None else reward_out)):
+            real = torch.float32
+        call = self._lib.cavgym_step_host if real == self.dtype else self._lib.cavgym_step_host_f32
+        rc = call(self._handle, check(actions, (m, 2, n), real, "actions"), check(state_out, (m, 4, n), real, "state_out"),
+                  check(reward_out, (m, n), real, "reward_out"), check(done_out, (n,), torch.uint8, "done_out"),
+                  check(winner_out, (n,), torch.int32, "winner_out"), check(tangent_out, (n,), torch.uint8, "tangent_out"))
         if rc:
             _native.check(rc)
 

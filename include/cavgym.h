@@ -199,6 +199,14 @@ int cavgym_replay(CavEngine* engine, int n_steps, const void* actions, void* sta
 int cavgym_step_host(CavEngine* engine, const void* actions, void* state_out, void* reward_out,
                      uint8_t* done_out, int32_t* winner_out, uint8_t* tangent_flag_out);
 
+/* cavgym_step_host for an fp64 engine with a float32 WIRE format: actions, state_out and reward_out are float32 host
+ * arrays (same shapes); the engine widens the actions, steps in double and narrows the results, so half the bytes cross
+ * PCIe.  What the caller gives up is the last 29 bits of every action and observation, nothing else: the engine's state and
+ * all events stay those of the fp64 engine fed the widened actions.  Buffers must be page-locked and device-mapped
+ * (cavgym_host_alloc, tensor.pin_memory()); scenarios of at most CAV_SMALL_M bodies; CAV_ESTATE otherwise. */
+int cavgym_step_host_f32(CavEngine* engine, const float* actions, float* state_out, float* reward_out, uint8_t* done_out,
+                         int32_t* winner_out, uint8_t* tangent_flag_out);
+
 /* CAVEnv.reset (environment.py:225-229) with HOST buffers, for callers that hold no device memory (the host-buffer twin
  * of cavgym_reset, as cavgym_step_host is of cavgym_step): mask host u8[N] or NULL, init_state host real[M][4][N] or NULL
  * are copied in; the post-reset state is copied to state_out (host real[M][4][N], nullable).  Synchronises. */

@@ -337,6 +337,38 @@ def test_sharded_engines_match_one_engine(dtype):
     assert total == want and want["episodes"] > n
 
 
+def test_float32_wire_format_is_the_fp64_engine_on_widened_actions():
+    """cavgym_step_host_f32: float32 actions in, float32 state / rewards out, fp64 engine.  Against a second fp64 engine stepped
+    on the device with the widened actions: the engine states are BITWISE equal, the outputs are their float32 roundings, the
+    events identical."""
+    import torch
+    meta, episodes = load_golden("learn_election3_seed22")      # four bodies; episodes of 116, 901, 218 and 79 steps
+    k, n, steps = len(episodes), 4096, 250
+    init = soa(np.stack([episodes[e % k]["init_state"] for e in range(n)]))
+    actions = np.zeros((steps, meta["n_bodies"], 2, n))
+    for j, ep in enumerate(episodes):
+        a = ep["actions"][:steps]
+        actions[:a.shape[0], :, :, j::k] = a[..., None]
+    actions *= 1.0 - 1e-4 * np.random.RandomState(0).uniform(0.1, 1.0, actions.shape)   # inside the bounds, not float32-representable
+    wire = torch.tensor(actions, dtype=torch.float32).pin_memory()
+    a, b = make_env(meta, n, "float64"), make_env(meta, n, "float64")
+    a.reset(init_state=init)
+    b.reset(init_state=init)
+    h_state = torch.empty((meta["n_bodies"], 4, n), dtype=torch.float32).pin_memory()
+    h_reward = torch.empty((meta["n_bodies"], n), dtype=torch.float32).pin_memory()
+    h_done, h_winner = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory()
+    h_tangent = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for t in range(steps):
+        a.step_host(wire[t], h_state, h_reward, h_done, h_winner, h_tangent)
+        state, reward, done, winner, tangent = b.step(wire[t].double().cuda())
+        assert torch.equal(a.state, b.state), t
+        assert torch.equal(h_state, state.float().cpu()) and torch.equal(h_reward, reward.float().cpu()), t
+        assert torch.equal(h_done, done.cpu()) and torch.equal(h_winner, winner.cpu()) and torch.equal(h_tangent, tangent.cpu()), t
+    assert a.stats() == b.stats() and a.stats()["episodes"] > n // 2 and a.stats()["errors"] == 0
+    with pytest.raises(Exception, match="page-locked"):
+        a.step_host(wire[0].clone(), h_state, h_reward, h_done, h_winner, h_tangent)      # pageable actions
+
+
 def test_sweep_totals_do_not_depend_on_the_split():
     """BASELINE config C5's claim: the seed sweep over a fixed GLOBAL env set gives identical totals however many GPUs share
     it.  The same 8,192 global envs are run as 1, 2, 4 and 8 shards (sharding.split_envs; one engine per shard, as one rank
