@@ -33,6 +33,17 @@ constexpr int kLoopThreads = CAV_LOOP_THREADS;
 #define CAV_MIN_BLOCKS_ROLLOUT 4
 #endif
 constexpr int kRolloutThreads = CAV_ROLLOUT_THREADS;
+// The heterogeneous kernels of four or more bodies synchronise their warps at every phase boundary (CtaPhase): the more warps
+// walk the code together, the more instruction fetches are shared.  Measured, 1,048,576 envs x 100 steps (ms per launch, four
+// launches): bus stop 128 threads 39 / 50 / 52 / 52, 256 threads 37 / 43 / 44 / 44, 512 threads 40 / 42 / 42 / 43; pelican
+// crossing 128: 28 / 27 / 29 / 30, 256: 27 / 28 / 31 / 31; crossroads (three bodies) is best at 128.
+#ifndef CAV_ROLLOUT_THREADS_SYNCED
+#define CAV_ROLLOUT_THREADS_SYNCED 256
+#endif
+template <bool GENERIC, int M> __host__ __device__ constexpr int rollout_threads() { return GENERIC && M >= 4 ? CAV_ROLLOUT_THREADS_SYNCED : kRolloutThreads; }
+template <bool GENERIC, int M> __host__ __device__ constexpr int rollout_min_blocks() {
+  return GENERIC && M >= 4 ? (CAV_MIN_BLOCKS_ROLLOUT * kRolloutThreads) / CAV_ROLLOUT_THREADS_SYNCED : CAV_MIN_BLOCKS_ROLLOUT;
+}
 #ifndef CAV_MIN_BLOCKS_STEP
 #define CAV_MIN_BLOCKS_STEP 4
 #endif
@@ -255,10 +266,10 @@ __global__ void __launch_bounds__(kLoopThreads, CAV_MIN_BLOCKS_LOOP) replay_kern
 #endif
 
 template <typename R, int M, bool GENERIC>
-__global__ void __launch_bounds__(kRolloutThreads, CAV_MIN_BLOCKS_ROLLOUT) rollout_kernel(const __grid_constant__ DevScenario<R> sc,
+__global__ void __launch_bounds__((rollout_threads<GENERIC, M>()), (rollout_min_blocks<GENERIC, M>())) rollout_kernel(const __grid_constant__ DevScenario<R> sc,
                                                            const __grid_constant__ EnvBuffers<R> buf, int64_t t_global,
                                                            int n_steps, int auto_reset) {
-  const int64_t e_raw = buf.lo + (int64_t)blockIdx.x * kRolloutThreads + threadIdx.x;
+  const int64_t e_raw = buf.lo + (int64_t)blockIdx.x * rollout_threads<GENERIC, M>() + threadIdx.x;
   const bool in_range = e_raw < buf.hi;
   constexpr bool kSync = GENERIC && M >= CAV_ROLLOUT_SYNC_FROM_M;
   using Phase = typename std::conditional<kSync, CtaPhase, NoPhase>::type;
@@ -370,8 +381,9 @@ void launch_replay(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const Ste
 template <typename R, int M>
 void launch_rollout(const DevScenario<R>& sc, const EnvBuffers<R>& buf, int64_t t_global, int n_steps, int auto_reset,
                     cudaStream_t stream) {
-  if (sc.homogeneous) rollout_kernel<R, M, false><<<grid_for(buf, kRolloutThreads), kRolloutThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
-  else rollout_kernel<R, M, true><<<grid_for(buf, kRolloutThreads), kRolloutThreads, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
+  constexpr int plain = rollout_threads<false, M>(), synced = rollout_threads<true, M>();
+  if (sc.homogeneous) rollout_kernel<R, M, false><<<grid_for(buf, plain), plain, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
+  else rollout_kernel<R, M, true><<<grid_for(buf, synced), synced, 0, stream>>>(sc, buf, t_global, n_steps, auto_reset);
 }
 template <typename R, int M>
 void launch_reset(const DevScenario<R>& sc, const EnvBuffers<R>& buf, const uint8_t* mask, const R* init, int first_time,
