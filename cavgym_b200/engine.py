@@ -171,6 +171,29 @@ class BatchedCAVEnv:
             return pointer
         raise ValueError(f"{name} must be a contiguous host array of shape {tuple(shape)} and dtype {dtype}")
 
+    def replay_host(self, actions, state=None, reward=None, done=None, winner=None, tangent=None):
+        """cavgym_replay with PINNED HOST tensors: T fused steps in one launch whose kernel reads the joint actions [T,M,2,N]
+        from and writes the trajectories ([T,M,4,N] state, [T,M,N] reward, [T,N] done / winner / tangent; each optional) to host
+        memory over PCIe — reads of later steps overlap writes of earlier ones, which one cavgym_step_host call per step cannot
+        do.  Returns when the results are in the host tensors."""
+        n, m = self.num_envs, self.num_bodies
+        t = int(actions.shape[0])
+        wanted = (("actions", actions, (t, m, 2, n), self.dtype), ("state", state, (t, m, 4, n), self.dtype),
+                  ("reward", reward, (t, m, n), self.dtype), ("done", done, (t, n), torch.uint8), ("winner", winner, (t, n), torch.int32),
+                  ("tangent", tangent, (t, n), torch.uint8))
+        pointers = []
+        for name, tensor, shape, dtype in wanted:
+            if tensor is None:
+                pointers.append(None)
+                continue
+            if not (isinstance(tensor, torch.Tensor) and tensor.device.type == "cpu" and tensor.is_pinned() and tensor.dtype == dtype
+                    and tuple(tensor.shape) == shape and tensor.is_contiguous()):
+                raise ValueError(f"{name} must be a pinned, contiguous CPU tensor of shape {shape} and dtype {dtype}")
+            pointers.append(C.c_void_p(tensor.data_ptr()))
+        stream = torch.cuda.current_stream(self.device)
+        _native.check(self._lib.cavgym_replay(self._handle, t, *pointers, C.c_void_p(stream.cuda_stream)))
+        stream.synchronize()
+
     def step_host(self, actions, state_out=None, reward_out=None, done_out=None, winner_out=None, tangent_out=None):
         """cavgym_step_host: host buffers in and out (numpy arrays or CPU tensors in the engine's layout).  Pinned buffers
         (tensor.pin_memory()) are read and written by the step kernel itself over PCIe; pageable ones are staged.

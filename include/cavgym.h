@@ -189,7 +189,9 @@ int cavgym_rollout(CavEngine* engine, int n_steps, int auto_reset, cudaStream_t 
 
 /* Replayed joint actions, n_steps transitions in one launch:
  * actions real[T][M][2][N]; trajectory outputs (each nullable) state real[T][M][4][N],
- * reward real[T][M][N], done u8[T][N], winner i32[T][N], tangent u8[T][N]. */
+ * reward real[T][M][N], done u8[T][N], winner i32[T][N], tangent u8[T][N].
+ * Every pointer may also be page-locked, device-mapped HOST memory (cavgym_host_alloc, tensor.pin_memory()): the kernel
+ * then streams actions in and trajectories out over PCIe inside the launch (BatchedCAVEnv.replay_host). */
 int cavgym_replay(CavEngine* engine, int n_steps, const void* actions, void* state_traj, void* reward_traj,
                   uint8_t* done_traj, int32_t* winner_traj, uint8_t* tangent_traj, cudaStream_t stream);
 

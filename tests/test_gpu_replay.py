@@ -488,3 +488,32 @@ def test_device_agents_follow_reference_with_replayed_draws(name):
             d = g[:, 3:] - w[:, 3:]                                            # target / prior orientation: angles, +pi == -pi
             assert np.max(np.abs(np.arctan2(np.sin(d), np.cos(d))), initial=0.0) < 1e-9, (name, e, t)
     assert flagged < 0.02 * sum(ep["actions"].shape[0] for ep in episodes)
+
+
+def test_replay_on_pinned_host_tensors_equals_replay_on_device_tensors():
+    """BatchedCAVEnv.replay_host: cavgym_replay reading its actions from and writing its trajectories to pinned host memory.
+    Bitwise the device-buffer replay, over several calls (chunked like a caller would) and with optional outputs left out."""
+    import torch
+    meta, episodes = load_golden("pedestrians_rc_eps05_seed1")
+    k, n, steps = len(episodes), 2048, 90
+    init = soa(np.stack([episodes[e % k]["init_state"] for e in range(n)]))
+    actions = np.zeros((steps, meta["n_bodies"], 2, n))
+    for j, ep in enumerate(episodes):
+        actions[:, :, :, j::k] = ep["actions"][:steps][..., None]
+    a, b = make_env(meta, n, "float64"), make_env(meta, n, "float64")
+    a.reset(init_state=init)
+    b.reset(init_state=init)
+    want = b.replay(actions)
+    h_actions = torch.tensor(actions).pin_memory()
+    m = meta["n_bodies"]
+    out = {"state": torch.empty((steps, m, 4, n), dtype=torch.float64).pin_memory(), "reward": torch.empty((steps, m, n), dtype=torch.float64).pin_memory(),
+           "done": torch.empty((steps, n), dtype=torch.uint8).pin_memory(), "winner": torch.empty((steps, n), dtype=torch.int32).pin_memory(),
+           "tangent": torch.empty((steps, n), dtype=torch.uint8).pin_memory()}
+    for at in range(0, steps, 30):
+        a.replay_host(h_actions[at:at + 30], **{key: value[at:at + 30] for key, value in out.items()})
+    for key in out:
+        assert torch.equal(out[key], want[key].cpu()), key
+    assert torch.equal(a.state, b.state) and a.stats() == b.stats()
+    a.replay_host(h_actions[:5], reward=out["reward"][:5])                  # only the rewards
+    with pytest.raises(ValueError, match="pinned"):
+        a.replay_host(torch.tensor(actions[:5]), reward=out["reward"][:5])  # pageable actions
