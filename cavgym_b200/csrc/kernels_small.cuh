@@ -264,6 +264,9 @@ __global__ void __launch_bounds__(kLoopThreads, CAV_MIN_BLOCKS_LOOP) replay_kern
 #ifndef CAV_ROLLOUT_SYNC_FROM_M
 #define CAV_ROLLOUT_SYNC_FROM_M 3
 #endif
+#ifndef CAV_ROLLOUT_SYNC_HOMOGENEOUS   // tuning: barriers in the homogeneous (pedestrians family) rollout kernels too
+#define CAV_ROLLOUT_SYNC_HOMOGENEOUS 0
+#endif
 
 template <typename R, int M, bool GENERIC>
 __global__ void __launch_bounds__((rollout_threads<GENERIC, M>()), (rollout_min_blocks<GENERIC, M>())) rollout_kernel(const __grid_constant__ DevScenario<R> sc,
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__((rollout_threads<GENERIC, M>()), (rollout_min_
                                                            int n_steps, int auto_reset) {
   const int64_t e_raw = buf.lo + (int64_t)blockIdx.x * rollout_threads<GENERIC, M>() + threadIdx.x;
   const bool in_range = e_raw < buf.hi;
-  constexpr bool kSync = GENERIC && M >= CAV_ROLLOUT_SYNC_FROM_M;
+  constexpr bool kSync = (GENERIC && M >= CAV_ROLLOUT_SYNC_FROM_M) || (CAV_ROLLOUT_SYNC_HOMOGENEOUS != 0 && !GENERIC);
   using Phase = typename std::conditional<kSync, CtaPhase, NoPhase>::type;
   // Barriers need every lane of every warp of the CTA to run every step: auto-reset (no env stays finished) and, for the
   // lanes of a ragged last CTA that have no env, a copy of the batch's last env stepped as a ghost.
