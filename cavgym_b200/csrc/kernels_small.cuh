@@ -144,7 +144,7 @@ __device__ __forceinline__ bool advance(const DevScenario<R>& sc, const EnvBuffe
                                         const bool ghost = false, R* reward_sink = nullptr) {
   StepResult<R, M> res;
   bool ended = false;
-  if (env.done) {  // frozen until reset
+  if (CAV_UNLIKELY(env.done != 0)) {  // frozen until reset
 #pragma unroll
     for (int b = 0; b < M; ++b) res.reward[b] = R(0);
     res.terminate = env.done == 1;
@@ -153,9 +153,9 @@ __device__ __forceinline__ bool advance(const DevScenario<R>& sc, const EnvBuffe
   } else {
     transition<R, M, AGENTS, GENERIC, NoSink, Phase>(sc, buf, e, t_global, env, ext, res, NoSink(), phase);
     if (!ghost) {
-      if (res.invalid) buf.err[e] = 1;
-      if (res.tangent) count_tangent(buf.stats);
-      if (env.done) score_episode<R, M>(buf, env, e, AGENTS ? env.episode : -1);
+      if (CAV_UNLIKELY(res.invalid)) buf.err[e] = 1;
+      if (CAV_UNLIKELY(res.tangent)) count_tangent(buf.stats);
+      if (CAV_UNLIKELY(env.done != 0)) score_episode<R, M>(buf, env, e, AGENTS ? env.episode : -1);
     }
     ended = env.done != 0;
   }
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__((rollout_threads<GENERIC, M>()), (rollout_min_
   bool was_reset = false;
   for (int t = 0; t < n_steps; ++t) {
     if (sync_on) { __syncwarp(); __syncthreads(); }
-    if (env.done) {
+    if (CAV_UNLIKELY(env.done != 0)) {
       if (!auto_reset) break;
       reset_env<R, M>(sc, buf, nullptr, e, env);
       was_reset = true;
