@@ -117,3 +117,23 @@ def test_reference_objects_compile_to_the_same_tables(scenario, extra):
     theirs = compile_scenario(their_env.bodies, their_env.constants, theirs_config, specs).tables()
     mine = compile_scenario(my_env.bodies, my_env.constants, mine_config, specs).tables()
     assert theirs == mine
+
+
+def test_experiments_grid_configs_are_the_reference_grid():
+    """cavgym_b200.experiments builds, per grid point, the config the reference's experiments.py:40-82 builds (same scenario,
+    rewards, feature set and tester settings), with a constant learning rate where the reference passes a float."""
+    from cavgym_b200 import experiments
+    from cavgym_b200.config import AgentType
+    log_dir, config = experiments.make_config(AgentType.PROXIMITY, 0.5, 0.9, 0.1, log_root="out")
+    assert log_dir == "out/tester=proximity/alpha=0.5/gamma=0.9/epsilon=0.1"
+    data = config.to_data()
+    assert data["ego_config"]["option"] == "q-learning" and data["ego_config"]["alpha"] == {"start": 0.5, "stop": 0.5, "num_steps": 2}
+    assert data["ego_config"]["gamma"] == 0.9 and data["ego_config"]["epsilon"] == 0.1
+    assert data["ego_config"]["feature_config"] == {"distance_x": False, "distance_y": False, "distance": True, "relative_angle": True,
+                                                    "heading": True, "on_road": False, "inverse_distance": False}
+    assert data["tester_config"] == {"option": "proximity", "threshold": 544.0}
+    assert data["scenario_config"]["num_pedestrians"] == 1 and data["episodes"] == 10 and data["seed"] == 0
+    assert cfg.make_config(data).to_data() == data            # round trip
+    assert experiments.make_tester_config(AgentType.RANDOM).epsilon == 0.01
+    assert experiments.make_tester_config(AgentType.RANDOM_CONSTRAINED).epsilon == 0.5
+    assert len(experiments.ALPHAS) * len(experiments.GAMMAS) * len(experiments.EPSILONS) * len(experiments.TESTER_TYPES) == 81
