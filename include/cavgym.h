@@ -268,6 +268,13 @@ int cavgym_set_action_logging(CavEngine* engine, int enabled);
  * everywhere (A/B measurements, parity of the two paths). */
 int cavgym_set_step_path(CavEngine* engine, int use_tma);
 
+/* cavgym_rollout of a heterogeneous scenario of 3..CAV_SMALL_M bodies (crossroads, bus stop, pelican crossing:
+ * examples/environments/*.py) has a second implementation: a team of M warps per 32 environments, one warp per body, bodies
+ * in registers and meeting through shared memory (kernels_team.cuh).  Results are bitwise those of the thread-per-environment
+ * kernel; measured it is no faster, so it is opt-in: team = 1 selects it, 0 (default) goes back.  Scenarios of
+ * the Pedestrians-v0 family, one- and two-body scenarios and election agents always run thread per environment. */
+int cavgym_set_rollout_path(CavEngine* engine, int team);
+
 /* Scenarios with more than CAV_SMALL_M bodies always run the warp-per-environment kernels (one env per warp, bodies
  * staged in shared memory, fp32 broad phase + exact narrow phase for the all-pairs collision test of
  * environment.py:156-177); force = 1 selects them for a small scenario too (parity of the two paths), 0 goes back. */
