@@ -131,6 +131,11 @@ struct StepIO {
   int32_t* winner_out;
   uint8_t* tangent_out;
   int32_t ctas_per_sm;   // host side only: cap on resident CTAs per SM of the persistent step kernel (0 = as many as fit)
+  // replay_tma_kernel, launch chaining (kernels_tma.cuh): tile_gen[i] = sequence number of the last replay launch that has
+  // written tile i's env state back; a launch with `chained` set waits for its own tiles' seq - 1 instead of for the whole
+  // previous grid.  Engine-owned; null = no chaining.
+  int32_t* tile_gen;
+  int32_t seq, chained;
 };
 
 // cavgym_step_host_f32: joint actions and results cross the host link as float32 while the engine steps in its own type.

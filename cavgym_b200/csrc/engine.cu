@@ -14,8 +14,11 @@
 
 
 #include "kernels_dense.cuh"
+#ifndef CAV_REPLAY_CHAIN   // 0: every replay launch waits for the whole previous grid (A/B)
+#define CAV_REPLAY_CHAIN 1
+#endif
 #include "kernels_team.cuh"
-#include "kernels_small.cuh"
+#include "kernels_tma.cuh"   // (tma_span, kReplayTile for the replay launch chain; includes kernels_small.cuh)
 
 namespace cav {
 
@@ -421,6 +424,12 @@ struct CavEngine {
   int step_ctas_per_sm = 0;       // cap on resident CTAs per SM of the persistent step kernel for the next launch (0 = occupancy)
   int host_ctas_per_sm = CAV_HOST_CTAS_PER_SM;   // the same for the zero-copy host path (cavgym_set_host_path)
   bool host_ready = false;        // streams and staging buffers of the host-buffer entry points all exist
+  // launch chaining of the TMA replay kernel (kernels_tma.cuh): sequence number of the last launch, the API call it was made
+  // in, its stream and env range; the next cavgym_replay chains to it iff it is the very next API call on this engine
+  int32_t* d_tile_gen = nullptr;
+  int32_t replay_seq = 0;
+  int64_t api_calls = 0, chain_call = -2, chain_lo = 0, chain_span = 0;
+  cudaStream_t chain_stream = nullptr;
   bool caller_work_pending = true;   // a call queued work on a caller stream since the last host-buffer call synchronised
   const void* host_seen[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // caller buffers of the last zero-copy call ...
   void* host_mapped[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};       // ... and their device addresses
@@ -463,6 +472,7 @@ static int setup_buffers(CavEngine* eng, EnvBuffers<R>& buf) {
   if ((rc = dev_alloc(eng, &buf.done, (size_t)n))) return rc;
   if ((rc = dev_alloc(eng, &buf.err, (size_t)n))) return rc;
   if ((rc = dev_alloc(eng, &buf.stats, (size_t)CAV_N_STATS))) return rc;
+  if (!eng->d_tile_gen && (rc = dev_alloc(eng, &eng->d_tile_gen, (size_t)(n / kReplayTile + 2)))) return rc;
   std::vector<DevSpawn<R>> spawns;
   for (const CavSpawn& s : eng->spawns) spawns.push_back(to_spawn<R>(s));
   DevSpawn<R>* d_spawns = nullptr;
@@ -502,6 +512,7 @@ static int check_engine(CavEngine* eng) {
   if (!eng) return fail(CAV_EINVAL, "engine is NULL");
   cudaError_t err = cudaSetDevice(eng->device);
   if (err != cudaSuccess) return fail(CAV_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(err));
+  eng->api_calls += 1;   // every entry point passes here once: replay launches chain only across ADJACENT calls
   return CAV_OK;
 }
 
@@ -559,8 +570,19 @@ static int replay_typed(CavEngine* eng, const DevScenario<R>& sc, EnvBuffers<R> 
   const SmallLaunchers<R>* k = small_launchers<R>(eng->m);
   if (eng->use_tma) {
     int64_t taken = 0;
-    if (!k->replay_tma(sc, buf, io, eng->t_global, n_steps, stream, &taken)) return fail(CAV_ECUDA, "TMA replay kernel set-up failed");
-    if (taken > 0) { buf.lo += taken; ++*launches; }
+    StepIO<R> chain = io;
+    chain.tile_gen = eng->d_tile_gen;
+    chain.seq = eng->replay_seq + 1;
+    // chained to the previous launch iff that was the previous API call on this engine, on this stream, over these envs
+    const int64_t span = tma_span(buf, io, kReplayTile, io.done_out != nullptr || io.tangent_out != nullptr);
+    chain.chained = eng->d_tile_gen && CAV_REPLAY_CHAIN && eng->chain_call == eng->api_calls - 1 && eng->chain_stream == stream &&
+                    eng->chain_lo == buf.lo && eng->chain_span == span;
+    if (!k->replay_tma(sc, buf, chain, eng->t_global, n_steps, stream, &taken)) return fail(CAV_ECUDA, "TMA replay kernel set-up failed");
+    if (taken > 0) {
+      eng->replay_seq += 1;
+      eng->chain_call = eng->api_calls; eng->chain_stream = stream; eng->chain_lo = buf.lo; eng->chain_span = taken;
+      buf.lo += taken; ++*launches;
+    }
   }
   if (buf.lo < buf.hi) { k->replay(sc, buf, io, eng->t_global, n_steps, stream); ++*launches; }
   return CAV_OK;

@@ -126,6 +126,35 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Launch chaining of replay_tma_kernel.  Consecutive cavgym_replay launches over the same tiles depend on each other tile by
+// tile only: CTA i of a launch needs the env state CTA i of the previous launch wrote, nothing else.  So instead of waiting
+// for the whole previous grid (griddepcontrol.wait: its slowest CTA, its drain and the ramp of this one — a third of a 20-step
+// launch), a chained launch waits for ITS tile's sequence number, published with release semantics by the CTA that finished
+// the tile, and the launches of a train overlap like the iterations of one persistent kernel.  No deadlock: a grid only
+// starts once every CTA of the grid before it is resident or done (that is when its launch_dependents resolves), so the CTA
+// waited for is always running or finished.  A wait that outlasts two seconds traps instead of hanging the device.
+__device__ __forceinline__ int32_t ld_acquire_gpu(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int32_t* p, int32_t v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void wait_tile_generation(const int32_t* gen, int32_t want) {
+  if (ld_acquire_gpu(gen) == want) return;
+  const unsigned long long start = global_timer_ns();
+  while (ld_acquire_gpu(gen) != want) {
+    __nanosleep(200);
+    if (global_timer_ns() - start > 2000000000ull) __trap();
+  }
+}
+
 // One SoA row as the producer sees it: where its segment for unit 0 (tile 0 / step 0) starts in HBM, how far the next
 // unit's segment is, where it lives in a stage, and the element size (segment bytes = envs in the tile * elem).
 struct TmaRow {
@@ -452,7 +481,14 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
       const int freed = t - (kReplayStages >= 2 ? kReplayStages - 2 : 0);
       if (freed >= 0 && lane == 0) mbar_arrive(&empty[freed % kReplayStages]);
     }
-    bulk_wait_read_all();
+    if (io.tile_gen) {
+      // the tile is published below: its trajectory rows must have LANDED by then (a launch three slabs later may write the
+      // same rows of a rotating slab), not just have left shared memory
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kReplayTile + 32) : "memory");
+    } else {
+      bulk_wait_read_all();
+    }
     return;
   }
 
@@ -460,7 +496,8 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
   // The set-up above and the producer's first action loads do not depend on the previous launch and overlap its tail; the
   // env state does (the previous launch wrote it): read it once the programmatic dependency has resolved.  Everything this
   // kernel writes follows from here (the producer's stores wait for the consumers' first step).
-  pdl_wait();
+  if (io.chained) wait_tile_generation(io.tile_gen + blockIdx.x, io.seq - 1);   // this tile's state is in place (see above)
+  else pdl_wait();
   const bool active = (uint32_t)tid < cnt;
   const int64_t e = tile_lo + (active ? tid : 0);
   EnvRegs<R, M> env;
@@ -510,6 +547,10 @@ __global__ void __launch_bounds__(kReplayTile + 32, CAV_MIN_BLOCKS_REPLAY) repla
     if (lane == 0) mbar_arrive(&done[s]);
   }
   if (active && was_live) store_env<R, M, false>(sc, buf, e, env, false);
+  if (io.tile_gen) {   // publish the tile: every consumer's state is stored, then one release store of this launch's number
+    asm volatile("bar.sync 1, %0;" ::"n"(kReplayTile + 32) : "memory");   // with the producer warp: its bulk stores have landed
+    if (tid == 0) { __threadfence(); st_release_gpu(io.tile_gen + blockIdx.x, io.seq); }
+  }
 }
 
 // ================================================================ host side

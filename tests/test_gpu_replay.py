@@ -237,6 +237,49 @@ def test_tma_replay_kernel_is_bitwise_equal_to_plain_kernel(name, dtype, n):
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("n", [224 * 300, 224 * 37 + 48])
+def test_chained_replay_launches_are_bitwise_equal_to_the_plain_kernel(dtype, n):
+    """Back-to-back cavgym_replay launches chain tile by tile (kernels_tma.cuh: a CTA waits for ITS tile's sequence number,
+    not for the whole previous grid), so consecutive launches overlap on the device.  A train of launches issued without any
+    synchronisation in between — chunks of different lengths, a whole-batch reset and a masked reset in the middle, which
+    break the chain — must leave the same trajectories, state, latches and counters as the plain kernel."""
+    import torch
+    meta, episodes = load_golden("pedestrians_rc_seed0")
+    m, k = meta["n_bodies"], len(episodes)
+    t_max = 260
+    init = soa(np.stack([episodes[e % k]["init_state"] for e in range(n)]))
+    actions = np.zeros((t_max, m, 2, n))
+    for j, ep in enumerate(episodes):
+        a = ep["actions"][:t_max]
+        actions[:a.shape[0], :, :, j::k] = a[..., None]
+    envs = [make_env(meta, n, dtype), make_env(meta, n, dtype)]
+    envs[1].set_step_path(use_tma=False)
+    acts = torch.tensor(actions, dtype=envs[0].dtype, device=envs[0].device)
+    mask = torch.zeros(n, dtype=torch.bool, device=envs[0].device)
+    mask[::3] = True
+    results = []
+    for env in envs:
+        env.reset(init_state=init)
+        outs, t = [], 0
+        for i, chunk in enumerate([5, 5, 5, 1, 2, 20, 20, 20, 3, 7, 20, 20, 5, 5, 40, 40, 20, 20]):
+            if i == 8:
+                env.reset(init_state=init)          # breaks the chain: the next launch waits for the whole stream again
+            if i == 13:
+                env.reset(mask=mask)
+            outs.append(env.replay(acts[t:t + chunk], record=("state", "reward", "done", "winner", "tangent") if i % 2 else ("state",)))
+            t += chunk
+        results.append((outs, env))
+    torch.cuda.synchronize()
+    for a, b in zip(results[0][0], results[1][0]):
+        for key in a:
+            if a[key] is not None:
+                assert torch.equal(a[key], b[key]), key
+    for attr in ("state", "episode_liveness", "timestep", "done_latch", "winner_latch"):
+        assert torch.equal(getattr(envs[0], attr), getattr(envs[1], attr)), attr
+    assert envs[0].stats() == envs[1].stats()
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
 def test_road_kerb_and_corner_shares_match_oracle(dtype):
     """percentage_intersects (geometry.py:80-87) on the engine's closed-form paths: pedestrians are placed astride the
     kerbs and the four corners of the road with random headings (and a few clear of it / inside it), stepped with small
