@@ -267,9 +267,15 @@ def run_ours(args):
                 "algorithmic_bytes_per_env_step": bytes_env_step, "launches": replay_launches,
                 "steps_per_launch": steps_per_launch, "avg_launch_ms": round(kernel_ms / replay_launches, 5),
                 "isolated_launch_ms": round(isolated_ms, 5),
+                "frac_isolated": round(bytes_per_launch / (isolated_ms * 1e-3) / 1e9 / peak_gbs, 4),
+                "launch_chaining": "consecutive cavgym_replay launches chain tile by tile (a CTA waits for its own tile's sequence "
+                                   "number, not for the whole previous grid: kernels_tma.cuh), so back-to-back launches OVERLAP on the "
+                                   "device — ramp, tail and drain of one launch are covered by its neighbours",
                 "timing": "avg_launch_ms = device time of the timed region (one CUDA event pair around all launches, issued back to "
-                          "back) / launches; isolated_launch_ms = mean of per-launch event pairs in a separate pass (events between "
-                          "launches serialise them)",
+                          "back) / launches, i.e. the time per launch at which the train advances; isolated_launch_ms = mean of "
+                          "per-launch event pairs in a separate pass (an event between two launches serialises them: the duration "
+                          "of one launch alone, what ncu's serialised launch list also shows); frac is from the first, "
+                          "frac_isolated from the second",
                 "note": "65,536 envs: the state (4 MiB) stays in registers for the whole launch; actions stream in and "
                         "trajectories stream out through HBM (slabs larger than L2)"}
 

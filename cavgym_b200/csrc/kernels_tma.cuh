@@ -132,7 +132,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // launch), a chained launch waits for ITS tile's sequence number, published with release semantics by the CTA that finished
 // the tile, and the launches of a train overlap like the iterations of one persistent kernel.  No deadlock: a grid only
 // starts once every CTA of the grid before it is resident or done (that is when its launch_dependents resolves), so the CTA
-// waited for is always running or finished.  A wait that outlasts two seconds traps instead of hanging the device.
+// waited for is always running or finished.  A wait that outlasts ten seconds traps instead of hanging the device.
 __device__ __forceinline__ int32_t ld_acquire_gpu(const int32_t* p) {
   int32_t v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -151,7 +151,7 @@ __device__ __forceinline__ void wait_tile_generation(const int32_t* gen, int32_t
   const unsigned long long start = global_timer_ns();
   while (ld_acquire_gpu(gen) != want) {
     __nanosleep(200);
-    if (global_timer_ns() - start > 2000000000ull) __trap();
+    if (global_timer_ns() - start > 10000000000ull) __trap();
   }
 }
 
