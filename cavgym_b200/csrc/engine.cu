@@ -147,10 +147,18 @@ static void convert(const CavScenario& in, double tau, DevScenario<R>& out) {
   for (int i = 0; i < in.n_roads; ++i) {
     roads[i] = to_quad<R>(in.roads[i]);
     out.road_bb[i] = host_aabb(roads[i]);
-    bool axis = true;  // every corner lies on a corner of the AABB
+    // Axis-aligned: every corner lies on a corner of the AABB — up to a thousandth of the near-tangent tolerance.  The side
+    // roads of the crossroads scenario are make_rectangle(...).transform(+-pi/2, ...) (assets.py, crossroads.py:10-49): their
+    // corners come out as 718.9999999999999 / 719.0, a skew of 1e-13 px that fp32 rounds away and fp64 does not.  Held to
+    // exact equality, every body near those roads went through the general clipper (18 % of the rollout kernel's warp
+    // instructions at 1.2 active lanes: crossroads ran twice as fast in fp32 as in fp64); the closed forms on the AABB differ
+    // from the skewed quad by ~1e-13 px, four orders below what a decision may depend on without being flagged.
+    const R snap = (R)(tau * 1e-3);
+    auto on = [snap](R v, R bound) { return std::fabs((double)v - (double)bound) <= (double)snap; };
+    bool axis = true;
     for (int c = 0; c < 4; ++c)
-      axis = axis && (roads[i].x[c] == out.road_bb[i].x0 || roads[i].x[c] == out.road_bb[i].x1) &&
-             (roads[i].y[c] == out.road_bb[i].y0 || roads[i].y[c] == out.road_bb[i].y1);
+      axis = axis && (on(roads[i].x[c], out.road_bb[i].x0) || on(roads[i].x[c], out.road_bb[i].x1)) &&
+             (on(roads[i].y[c], out.road_bb[i].y0) || on(roads[i].y[c], out.road_bb[i].y1));
     out.road_axis[i] = axis ? 1 : 0;
     out.road_rect[i] = to_box(roads[i], out.road_box[i]) ? 1 : 0;
   }
