@@ -253,11 +253,24 @@ __device__ __noinline__ R steering_towards(const DevType<R>& k, R v, R theta, R 
   const R tta = wrap_angle(target - theta);
   const R csa = tta < R(0) ? k.smin : k.smax;
   const R wb = k.wheelbase;
-  const R mta = (csa < R(0) ? R(-2) : R(2)) * dt * v / (csa < R(0) ? k.max_turn_smin : k.max_turn_smax);
-  // At full lock (the turn wanted exceeds what one step allows) the inverse below is atan(|tan(limit)|) = |limit| exactly in
-  // real arithmetic — the reference lands within an ulp of it and then clamps — so the limit itself is returned: no atan,
-  // sqrt or division on 13 of the 14 steps of a crossing turn, and body_step then takes its cached full-lock constants.
-  if (tta / mta > R(1)) return csa;
+  // At full lock (the turn wanted exceeds what one step allows: tta / mta > 1 with mta = +-2 dt v / max_turn, the largest
+  // turn of one step) the inverse below is atan(|tan(limit)|) = |limit| exactly in real arithmetic — the reference lands within
+  // an ulp of it and then clamps — so the limit itself is returned: no atan, sqrt or division on 13 of the 14 steps of a
+  // crossing turn, and body_step then takes its cached full-lock constants.
+  // The test itself is two IEEE divisions (~90 instructions at one or two active lanes per warp); the quotient of the two
+  // rounded divisions is within 4 ulp of |tta| max_turn / (2 dt v), so unless that ratio is within 16 ulp of 1 the products
+  // decide it — and when it is, the divisions do.
+  const R max_turn = csa < R(0) ? k.max_turn_smin : k.max_turn_smax;
+  const R reach = R(2) * dt * v;
+  bool full_lock;
+  const R want = rabs(tta) * max_turn, band = reach * (sizeof(R) == 8 ? R(4e-15) : R(2e-6));
+  if (CAV_LIKELY(v > R(0) && max_turn > R(0) && rabs(want - reach) > band)) {
+    full_lock = want > reach;
+  } else {
+    const R mta = (csa < R(0) ? R(-2) : R(2)) * dt * v / max_turn;
+    full_lock = tta / mta > R(1);
+  }
+  if (full_lock) return csa;
   const R ta = tta;
   const R steer = atan_(R(2) * wb * rsqrt_((ta * ta) / (R(4) * (v * v) * (dt * dt) - (wb * wb) * (ta * ta))));
   return ta < R(0) ? -steer : steer;
@@ -306,7 +319,11 @@ __device__ __forceinline__ R choose_crossing_action(const DevScenario<R>& sc, co
 template <typename R>
 __device__ __forceinline__ void crossing_feedback(const DevScenario<R>& sc, const R st[4], R ag[CAV_AGENT_WORDS], bool& dirty) {
   if (!isnan_(ag[1])) {
-    if (point_distance(st[0], st[1], ag[1], ag[2]) < R(1)) {
+    // point_distance(body, waypoint) < 1 (pedestrian.py:40-41).  sqrt is correctly rounded and monotone, and the largest
+    // number below 1 has a square root that rounds to itself, so "sqrt(d2) < 1" and "d2 < 1" are the same predicate: no
+    // square root for the ~400 steps a pedestrian walks towards its waypoint.
+    const R wdy = ag[2] - st[1], wdx = ag[1] - st[0];
+    if ((wdy * wdy) + (wdx * wdx) < R(1)) {
       ag[1] = nan_<R>(); ag[2] = nan_<R>(); ag[3] = ag[4]; ag[4] = nan_<R>();
       dirty = true;
     }
