@@ -319,11 +319,7 @@ __device__ __forceinline__ R choose_crossing_action(const DevScenario<R>& sc, co
 template <typename R>
 __device__ __forceinline__ void crossing_feedback(const DevScenario<R>& sc, const R st[4], R ag[CAV_AGENT_WORDS], bool& dirty) {
   if (!isnan_(ag[1])) {
-    // point_distance(body, waypoint) < 1 (pedestrian.py:40-41).  sqrt is correctly rounded and monotone, and the largest
-    // number below 1 has a square root that rounds to itself, so "sqrt(d2) < 1" and "d2 < 1" are the same predicate: no
-    // square root for the ~400 steps a pedestrian walks towards its waypoint.
-    const R wdy = ag[2] - st[1], wdx = ag[1] - st[0];
-    if ((wdy * wdy) + (wdx * wdx) < R(1)) {
+    if (point_distance(st[0], st[1], ag[1], ag[2]) < R(1)) {
       ag[1] = nan_<R>(); ag[2] = nan_<R>(); ag[3] = ag[4]; ag[4] = nan_<R>();
       dirty = true;
     }
