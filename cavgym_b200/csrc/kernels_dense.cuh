@@ -126,7 +126,9 @@ __device__ __noinline__ R dense_road_share_edge(const DevScenario<R>& sc, const 
     const bool x_edge = mx < my;
     const R lo = x_edge ? mx : my, hi = x_edge ? my : mx;
     const R opposite = x_edge ? rmax(m0, m1) : rmax(m2, m3);
-    if (lo <= -tau && hi >= tau && opposite >= tau) {
+    if (lo > -tau && hi >= tau && opposite >= tau) {   // (lo < tau here: the caller returned 1 otherwise)
+      result = kerb_touch_share(sm.c[b], sm.s[b], k.hl, k.hw, lo, x_edge, ex, ey, near); settled = true;
+    } else if (lo <= -tau && hi >= tau && opposite >= tau) {
       const R ac = rabs(sm.c[b]), as = rabs(sm.s[b]);
       const R p = kerb_share(lo + (x_edge ? ex : ey), (x_edge ? ac : as) * k.hl, (x_edge ? as : ac) * k.hw);
       if (rabs(p - R(0.5)) < tau) near = true;

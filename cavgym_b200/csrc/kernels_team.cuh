@@ -44,6 +44,7 @@ __device__ __forceinline__ R team_road_share(const DevScenario<R>& sc, const Dev
     const R lo = x_edge ? mx : my, hi = x_edge ? my : mx;
     if (lo >= tau) return R(1);
     const R opposite = x_edge ? rmax(m0, m1) : rmax(m2, m3);
+    if (lo > -tau && hi >= tau && opposite >= tau) return kerb_touch_share(c, s, k.hl, k.hw, lo, x_edge, ex, ey, near);
     if (lo <= -tau && hi >= tau && opposite >= tau) {
       const R ac = rabs(c), as = rabs(s);
       const R p = kerb_share(lo + (x_edge ? ex : ey), (x_edge ? ac : as) * k.hl, (x_edge ? as : ac) * k.hw);
