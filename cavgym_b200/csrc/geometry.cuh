@@ -387,13 +387,48 @@ __device__ __noinline__ R corner_share(Pose<R> a, R sx, R bx, R sy, R by) {
   return fast_div(rabs(acc) * R(0.5), a.length * a.width);
 }
 
+// area(box ∩ Q) for a rotated box that CONTAINS the road corner (the apex of the open quadrant Q outside both crossed edges),
+// in box coordinates: p along the length, q across, the box is [-hl, hl] x [-hw, hw], the apex P = (pu, pv) lies inside it, and
+// Q is the 90-degree wedge spanned from P by dX = (ux, vx) and dY = (uy, vy), the road's edge directions seen from the box.
+// Each ray leaves the box through one side; between the two exits the wedge takes in at most two box vertices (from an
+// interior point three consecutive vertices subtend more than 90 degrees), so the region is a fan of at most three triangles
+// around P.  Two divisions per ray, no vertex list, no loop over polygon edges.
+template <typename R>
+__device__ __forceinline__ R wedge_in_box_area(R pu, R pv, R hl, R hw, R ux, R uy, R vx, R vy) {
+  // sides counter-clockwise: 0 p = +hl, 1 q = +hw, 2 p = -hl, 3 q = -hw; vertex k follows side k counter-clockwise
+  auto leave = [&](R dp, R dq, R& ep, R& eq) {
+    const R bp = dp > R(0) ? hl : -hl, bq = dq > R(0) ? hw : -hw;
+    const R tp = fast_div(bp - pu, dp), tq = fast_div(bq - pv, dq);   // both >= 0: P is inside; dp, dq != 0: the box is rotated
+    if (tp <= tq) { ep = bp; eq = pv + tp * dq; return dp > R(0) ? 0 : 2; }
+    ep = pu + tq * dp; eq = bq; return dq > R(0) ? 1 : 3;
+  };
+  R e1p, e1q, e2p, e2q;
+  const int s1 = leave(ux, vx, e1p, e1q), s2 = leave(uy, vy, e2p, e2q);
+  const int dir = (ux * vy - vx * uy) > R(0) ? 1 : 3;   // +1 / -1 mod 4: the sense in which dX turns towards dY
+  R acc = R(0), cp = e1p - pu, cq = e1q - pv;
+  int k = s1;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (k != s2) {
+      const int vi = dir == 1 ? k : (k + 3) & 3;        // the vertex between side k and the next side in that sense
+      const R wp = ((vi == 0 || vi == 3) ? hl : -hl) - pu, wq = (vi <= 1 ? hw : -hw) - pv;
+      acc += rabs(cp * wq - cq * wp);
+      cp = wp; cq = wq;
+      k = (k + dir) & 3;
+    }
+  }
+  acc += rabs(cp * (e2q - pv) - cq * (e2p - pu));
+  return acc * R(0.5);
+}
+
 // The same share without clipping whenever possible.  With Hx, Hy the half-planes of the two crossed edges and Q the open
 // quadrant outside both,  area(box ∩ Hx ∩ Hy) = area(box ∩ Hx) + area(box ∩ Hy) − area(box) + area(box ∩ Q)
 // (inclusion-exclusion).  The first two terms are kerb shares (closed form); box ∩ Q is empty when a box axis separates the
 // box from Q and a rectangle when the box is axis-aligned (a pedestrian that has turned onto ±pi/2, the case that actually
 // occurs: it stays on a road corner for the ~65 steps of its kerb crossing, and the ~500 dependent instructions of the
-// streaming clipper made its warp — and with it the whole CTA of a fused replay launch — run at half speed).  Only a
-// rotated box that really reaches into Q still goes to corner_share.
+// streaming clipper made its warp — and with it the whole CTA of a fused replay launch — run at half speed); a rotated box
+// that contains the road corner gets the wedge area above.  Only a rotated box that reaches into Q without containing the
+// corner still goes to corner_share.
 //   tx, ty   signed distance of the box centre from the crossed x-edge / y-edge, positive inside the road
 //   sx, sy   outward direction (+-1) of those edges; bx, by as for corner_share
 template <typename R>
@@ -415,7 +450,12 @@ __device__ __noinline__ R corner_share_closed(Pose<R> a, R tx, R ty, R sx, R bx,
       if (ux <= R(0) && uy <= R(0)) apart |= -pu >= hl + tau;
       if (vx >= R(0) && vy >= R(0)) apart |= pv >= hw + tau;
       if (vx <= R(0) && vy <= R(0)) apart |= -pv >= hw + tau;
-      if (!apart) return corner_share(a, sx, bx, sy, by);
+      if (!apart) {
+        // the road corner inside the box (a car that swerves over the kerb while still astride the end of its road): the
+        // wedge area in closed form; only a box that reaches into Q without containing the corner is clipped
+        if (rabs(pu) < hl && rabs(pv) < hw) outside = wedge_in_box_area(pu, pv, hl, hw, ux, uy, vx, vy);
+        else return corner_share(a, sx, bx, sy, by);
+      }
     }
   }
   const R p = ((kerb_share(tx, ac * hl, as * hw) + kerb_share(ty, as * hl, ac * hw)) - R(1)) + fast_div(outside, a.length * a.width);
