@@ -237,7 +237,7 @@ def test_tma_replay_kernel_is_bitwise_equal_to_plain_kernel(name, dtype, n):
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
-@pytest.mark.parametrize("n", [224 * 300, 224 * 37 + 48, 224 * 900 + 16])   # one wave and a bit, a ragged single wave, three waves
+@pytest.mark.parametrize("n", [224 * 300, 224 * 37 + 48, 224 * 900 + 16, 224 * 20 + 100])   # one wave and a bit, a ragged single wave, three waves, a tail for the plain kernel (n % 16 != 0)
 def test_chained_replay_launches_are_bitwise_equal_to_the_plain_kernel(dtype, n):
     """Back-to-back cavgym_replay launches chain tile by tile (kernels_tma.cuh: a CTA waits for ITS tile's sequence number,
     not for the whole previous grid), so consecutive launches overlap on the device.  A train of launches issued without any
