@@ -191,7 +191,11 @@ int cavgym_rollout(CavEngine* engine, int n_steps, int auto_reset, cudaStream_t 
  * actions real[T][M][2][N]; trajectory outputs (each nullable) state real[T][M][4][N],
  * reward real[T][M][N], done u8[T][N], winner i32[T][N], tangent u8[T][N].
  * Every pointer may also be page-locked, device-mapped HOST memory (cavgym_host_alloc, tensor.pin_memory()): the kernel
- * then streams actions in and trajectories out over PCIe inside the launch (BatchedCAVEnv.replay_host). */
+ * then streams actions in and trajectories out over PCIe inside the launch (BatchedCAVEnv.replay_host).
+ * Calls that follow one another directly (no other call on this engine in between) on the same stream are ordered env tile
+ * by env tile rather than grid by grid, so their launches overlap on the device; to everything else in the stream — and to
+ * the host — they complete in order as usual.  Engine state (cavgym_state_ptr etc.) must not be written by other work of the
+ * stream between two such calls without an API call on the engine in between (cavgym_reset, cavgym_step ... all qualify). */
 int cavgym_replay(CavEngine* engine, int n_steps, const void* actions, void* state_traj, void* reward_traj,
                   uint8_t* done_traj, int32_t* winner_traj, uint8_t* tangent_traj, cudaStream_t stream);
 
