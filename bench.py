@@ -338,6 +338,30 @@ def run_ours(args):
                       "api": "BatchedCAVEnv.replay_host = cavgym_replay on pinned host tensors: one launch per call reads the joint actions of "
                              "its steps from and writes state/reward/done/winner/tangent of every step to host memory over PCIe; the caller "
                              "waits for each call's results before issuing the next"}
+        # (a2) the same calls with TWO in flight (double-buffered results): the caller issues call k + 1 before it consumes the
+        #      results of call k, which a replayed-action workload allows; back-to-back launches overlap on the device, so the
+        #      PCIe reads of one call cover the draining writes of the one before.  Reported beside the synchronous figure.
+        t_out2 = {k_: torch.empty_like(v_).pin_memory() for k_, v_ in t_out.items()}
+        results, ready = [t_out, t_out2], [torch.cuda.Event(), torch.cuda.Event()]
+        env.reset(init_state=init)
+        torch.cuda.synchronize(device)
+        barrier()
+        s0 = env.stats()
+        t0 = time.perf_counter()
+        for i, window in enumerate(windows):
+            if i >= 2:
+                ready[i % 2].synchronize()          # the results of call i - 2 are in host memory and consumed: its buffers are free
+            env.replay_host(window, wait=False, **results[i % 2])
+            ready[i % 2].record(torch.cuda.current_stream(device))
+        torch.cuda.synchronize(device)
+        pipe_s = time.perf_counter() - t0
+        s1 = env.stats()
+        pipe_time, pipe_units = sharding.reduce_timing(pipe_s, s1["env_steps"] - s0["env_steps"], device)
+        out["e2e"]["two_calls_in_flight"] = {"value": pipe_units / pipe_time, "unit": "env-steps/s", "steps": len(windows) * call,
+                                             "steps_per_call": call,
+                                             "api": "the same replay_host calls, the next one issued before the previous one's results are "
+                                                    "consumed (two result buffers, one CUDA event per call)"}
+        del t_out2, results
         # (b) the per-step API: one cavgym_step_host call per step (what a host-side agent that needs every observation uses)
         e2e_steps = max(3, min(args.e2e_steps, segment - 3))
         env.reset(init_state=init)

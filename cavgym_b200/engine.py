@@ -171,11 +171,13 @@ class BatchedCAVEnv:
             return pointer
         raise ValueError(f"{name} must be a contiguous host array of shape {tuple(shape)} and dtype {dtype}")
 
-    def replay_host(self, actions, state=None, reward=None, done=None, winner=None, tangent=None):
+    def replay_host(self, actions, state=None, reward=None, done=None, winner=None, tangent=None, wait=True):
         """cavgym_replay with PINNED HOST tensors: T fused steps in one launch whose kernel reads the joint actions [T,M,2,N]
         from and writes the trajectories ([T,M,4,N] state, [T,M,N] reward, [T,N] done / winner / tangent; each optional) to host
         memory over PCIe — reads of later steps overlap writes of earlier ones, which one cavgym_step_host call per step cannot
-        do.  Returns when the results are in the host tensors."""
+        do.  Returns when the results are in the host tensors; with wait=False it returns once the launch is queued on the
+        current stream (record an event and wait for that before touching the tensors): consecutive calls then overlap on the
+        device tile by tile, the reads of one covering the draining writes of the one before."""
         n, m = self.num_envs, self.num_bodies
         t = int(actions.shape[0])
         wanted = (("actions", actions, (t, m, 2, n), self.dtype), ("state", state, (t, m, 4, n), self.dtype),
@@ -192,7 +194,8 @@ class BatchedCAVEnv:
             pointers.append(C.c_void_p(tensor.data_ptr()))
         stream = torch.cuda.current_stream(self.device)
         _native.check(self._lib.cavgym_replay(self._handle, t, *pointers, C.c_void_p(stream.cuda_stream)))
-        stream.synchronize()
+        if wait:
+            stream.synchronize()
 
     def step_host(self, actions, state_out=None, reward_out=None, done_out=None, winner_out=None, tangent_out=None):
         """cavgym_step_host: host buffers in and out (numpy arrays or CPU tensors in the engine's layout).  Pinned buffers
