@@ -19,7 +19,11 @@
 //     box / braking zone, reaction zone — environment.py:148-206), so all warps agree on termination, winner and the
 //     near-tangent flag without a further exchange.  Later stages are evaluated speculatively and GATED when folding:
 //     a stage the reference would not have reached contributes nothing (its near-tangent bits included).
-// Two block-wide barriers per step (three with proximity agents, which look at the ego before it moves).
+// Two block-wide barriers per step (four with proximity agents, which look at the ego before it moves).
+// MEASURED: no faster than the thread-per-env kernel (bus stop 52 ms against 44.5 ms per 100 steps of 1 M envs, pelican
+// crossing 31.0 against 31.6; the local-memory stall is gone, the waits at the two barriers and the instruction-fetch stall
+// take its place — DESIGN 4.6), so cavgym_rollout uses it only on request (cavgym_set_rollout_path).  It stays as an independent
+// third implementation of the transition that must agree bit for bit with the other two.
 // The arithmetic and its order are those of transition_body.inc (the same device functions; a pair is evaluated with the
 // lower body index first), so results — state, agent state, liveness, counters, near-tangent flags — are bitwise those of
 // the thread-per-env and warp-per-env kernels (tests/test_gpu_team.py, tests/test_gpu_dense.py).
